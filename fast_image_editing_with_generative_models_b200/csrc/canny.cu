@@ -1,0 +1,186 @@
+// Integer Canny edge detector, bit-exact with cv2.cvtColor(RGB2GRAY) + cv2.Canny(gray, low, high)
+// (aperture 3, L1 gradient, no blur) as called by the reference at src/pipeline.py:200,205.
+//
+// Stages (all integer):
+//   k_gray      u8 RGB -> u8 gray, 15-bit fixed point (4 px / thread, 3x32-bit loads -> 1x32-bit store)
+//   k_nms       gray tile + 2-px halo staged in shared memory -> Sobel (replicate border), L1 magnitude
+//               (0 outside the image), integer-tangent NMS, double threshold -> state {0,1 weak,2 strong}
+//               and union-find parent init (strong pixels get the smaller label so they win the root)
+//   k_union     lock-free union-find over 8-connected candidate pixels (atomicMin on roots)
+//   k_finalize  edge = candidate whose root is a strong pixel -> 0/255 (optionally replicated x3)
+// The hysteresis result is the unique closure of strong pixels through candidates, so the union-find
+// formulation is bit-exact with OpenCV's stack-based flood fill without any host round trip.
+#include "fie_common.cuh"
+
+namespace fie {
+
+static constexpr uint32_t kWeakBit = 1u << 30;
+static constexpr uint32_t kIdxMask = kWeakBit - 1;
+static constexpr int TG22 = 13573;
+
+__global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, long long npix4, long long npix) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < npix4; i += (long long)gridDim.x * blockDim.x) {
+        long long p = i * 4;
+        if (p + 4 <= npix) {
+            const uint32_t* s = reinterpret_cast<const uint32_t*>(rgb + p * 3);   // 12-byte aligned group
+            uint32_t w0 = __ldg(s), w1 = __ldg(s + 1), w2 = __ldg(s + 2);
+            uint32_t r0 = w0 & 255, g0 = (w0 >> 8) & 255, b0 = (w0 >> 16) & 255;
+            uint32_t r1 = w0 >> 24, g1 = w1 & 255, b1 = (w1 >> 8) & 255;
+            uint32_t r2 = (w1 >> 16) & 255, g2 = w1 >> 24, b2 = w2 & 255;
+            uint32_t r3 = (w2 >> 8) & 255, g3 = (w2 >> 16) & 255, b3 = w2 >> 24;
+            uint32_t y0 = (9798u * r0 + 19235u * g0 + 3735u * b0 + 16384u) >> 15;
+            uint32_t y1 = (9798u * r1 + 19235u * g1 + 3735u * b1 + 16384u) >> 15;
+            uint32_t y2 = (9798u * r2 + 19235u * g2 + 3735u * b2 + 16384u) >> 15;
+            uint32_t y3 = (9798u * r3 + 19235u * g3 + 3735u * b3 + 16384u) >> 15;
+            *reinterpret_cast<uint32_t*>(gray + p) = y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+        } else {
+            for (long long q = p; q < npix; ++q) {
+                uint32_t r = rgb[q * 3], g = rgb[q * 3 + 1], b = rgb[q * 3 + 2];
+                gray[q] = (uint8_t)((9798u * r + 19235u * g + 3735u * b + 16384u) >> 15);
+            }
+        }
+    }
+}
+
+constexpr int TW = 64, TH = 16;   // output tile per CTA (256 threads, 4 px each)
+
+__global__ void __launch_bounds__(256) k_nms(const uint8_t* __restrict__ gray, uint8_t* __restrict__ state,
+                                             uint32_t* __restrict__ parent, int H, int W, int low, int high) {
+    __shared__ uint8_t  sg[TH + 4][TW + 4 + 4];
+    __shared__ int16_t  sdx[TH + 2][TW + 2], sdy[TH + 2][TW + 2], smg[TH + 2][TW + 2];
+    const int img = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const uint8_t* g = gray + (size_t)img * H * W;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (TH + 4) * (TW + 4); i += 256) {
+        int ly = i / (TW + 4), lx = i % (TW + 4);
+        int y = min(max(y0 + ly - 2, 0), H - 1), x = min(max(x0 + lx - 2, 0), W - 1);   // BORDER_REPLICATE
+        sg[ly][lx] = __ldg(g + (size_t)y * W + x);
+    }
+    __syncthreads();
+    for (int i = tid; i < (TH + 2) * (TW + 2); i += 256) {
+        int ly = i / (TW + 2), lx = i % (TW + 2);
+        int y = y0 + ly - 1, x = x0 + lx - 1;
+        int dx = 0, dy = 0, m = 0;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            // gray coordinates of (y,x) in sg are (ly+1, lx+1); at image borders the replicate clamp must be
+            // relative to the pixel itself, which the clamped halo load already guarantees for in-image pixels.
+            int a00 = sg[ly][lx], a01 = sg[ly][lx + 1], a02 = sg[ly][lx + 2];
+            int a10 = sg[ly + 1][lx], a12 = sg[ly + 1][lx + 2];
+            int a20 = sg[ly + 2][lx], a21 = sg[ly + 2][lx + 1], a22 = sg[ly + 2][lx + 2];
+            dx = (a02 + 2 * a12 + a22) - (a00 + 2 * a10 + a20);
+            dy = (a20 + 2 * a21 + a22) - (a00 + 2 * a01 + a02);
+            m = abs(dx) + abs(dy);
+        }
+        sdx[ly][lx] = (int16_t)dx; sdy[ly][lx] = (int16_t)dy; smg[ly][lx] = (int16_t)m;   // m = 0 outside the image
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * TW; i += 256) {
+        int ly = i / TW, lx = i % TW;
+        int y = y0 + ly, x = x0 + lx;
+        if (y >= H || x >= W) continue;
+        int cy = ly + 1, cx = lx + 1;
+        int m = smg[cy][cx];
+        uint8_t s = 0;
+        if (m > low) {
+            int dx = sdx[cy][cx], dy = sdy[cy][cx];
+            int ax = abs(dx), ay = abs(dy) << 15;          // <= 1020<<15 < 2^31
+            int t22 = ax * TG22;                           // <= 1020*13573 < 2^31
+            long long t67 = (long long)t22 + ((long long)ax << 16);
+            bool keep;
+            if (ay < t22) keep = m > smg[cy][cx - 1] && m >= smg[cy][cx + 1];
+            else if ((long long)ay > t67) keep = m > smg[cy - 1][cx] && m >= smg[cy + 1][cx];
+            else { int sg_ = ((dx ^ dy) < 0) ? -1 : 1; keep = m > smg[cy - 1][cx - sg_] && m > smg[cy + 1][cx + sg_]; }
+            if (keep) s = (m > high) ? 2 : 1;
+        }
+        size_t o = (size_t)img * H * W + (size_t)y * W + x;
+        state[o] = s;
+        if (s) parent[o] = (uint32_t)(y * W + x) | (s == 2 ? 0u : kWeakBit);
+    }
+}
+
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* P, uint32_t idx) {
+    uint32_t v = ((volatile const uint32_t*)P)[idx];
+    while ((v & kIdxMask) != idx) { idx = v & kIdxMask; v = ((volatile const uint32_t*)P)[idx]; }
+    return v;   // root's label value (strong roots have kWeakBit clear)
+}
+__device__ __forceinline__ void uf_union(uint32_t* P, uint32_t i, uint32_t j) {
+    uint32_t a = uf_find(P, i), b = uf_find(P, j);
+    while ((a & kIdxMask) != (b & kIdxMask)) {
+        if (a > b) { uint32_t t = a; a = b; b = t; }
+        uint32_t old = atomicMin(&P[b & kIdxMask], a);
+        if (old == b) break;
+        b = uf_find(P, old & kIdxMask);
+        a = uf_find(P, a & kIdxMask);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_union(const uint8_t* __restrict__ state, uint32_t* __restrict__ parent, int H, int W) {
+    const int img = blockIdx.z;
+    int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    const uint8_t* s = state + (size_t)img * H * W;
+    uint32_t* P = parent + (size_t)img * H * W;
+    if (!s[(size_t)y * W + x]) return;
+    uint32_t me = y * W + x;
+    if (x > 0 && s[(size_t)y * W + x - 1]) uf_union(P, me, me - 1);
+    if (y > 0) {
+        const uint8_t* r = s + (size_t)(y - 1) * W;
+        if (x > 0 && r[x - 1]) uf_union(P, me, me - W - 1);
+        if (r[x]) uf_union(P, me, me - W);
+        if (x < W - 1 && r[x + 1]) uf_union(P, me, me - W + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ state, const uint32_t* __restrict__ parent,
+                                                  uint8_t* __restrict__ out, int H, int W, int out_channels) {
+    const int img = blockIdx.z;
+    int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= W || y >= H) return;
+    size_t o = (size_t)img * H * W + (size_t)y * W + x;
+    uint8_t v = 0;
+    if (state[o]) { uint32_t r = uf_find(parent + (size_t)img * H * W, y * W + x); v = (r & kWeakBit) ? 0 : 255; }
+    if (out_channels == 1) out[o] = v;
+    else { out[o * 3] = v; out[o * 3 + 1] = v; out[o * 3 + 2] = v; }
+}
+
+}  // namespace fie
+
+extern "C" size_t fie_canny_workspace_bytes(int n, int h, int w) {
+    size_t px = (size_t)n * h * w;
+    // gray u8 + state u8 (each rounded to 256 B) + parent u32
+    return ((px + 255) / 256) * 256 * 2 + px * 4;
+}
+
+extern "C" int fie_canny_u8(const void* img, void* edges, int n, int h, int w, int in_channels, int out_channels,
+                            int low, int high, void* workspace, size_t workspace_bytes, void* stream_) {
+    using namespace fie;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FIE_REQUIRE(n >= 0 && h > 0 && w > 0, "fie_canny_u8: bad shape n=%d h=%d w=%d", n, h, w);
+    FIE_REQUIRE(in_channels == 1 || in_channels == 3, "fie_canny_u8: in_channels must be 1 or 3");
+    FIE_REQUIRE(out_channels == 1 || out_channels == 3, "fie_canny_u8: out_channels must be 1 or 3");
+    FIE_REQUIRE((long long)h * w < (1ll << 30), "fie_canny_u8: image too large");
+    FIE_REQUIRE(n <= 65535, "fie_canny_u8: batch too large");
+    if (n == 0) return FIE_OK;
+    FIE_REQUIRE(img && edges && workspace, "fie_canny_u8: null pointer");
+    FIE_REQUIRE(workspace_bytes >= fie_canny_workspace_bytes(n, h, w), "fie_canny_u8: workspace too small");
+    if (low > high) { int t = low; low = high; high = t; }
+    size_t px = (size_t)n * h * w, pxr = ((px + 255) / 256) * 256;
+    uint8_t* gray = (uint8_t*)workspace;
+    uint8_t* state = gray + pxr;
+    uint32_t* parent = (uint32_t*)(state + pxr);
+    const uint8_t* g = (const uint8_t*)img;
+    if (in_channels == 3) {
+        long long n4 = (long long)((px + 3) / 4);
+        int blocks = (int)((n4 + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+        k_gray<<<blocks, 256, 0, stream>>>((const uint8_t*)img, gray, n4, (long long)px);
+        g = gray;
+    }
+    dim3 g1(ceil_div(w, TW), ceil_div(h, TH), n);
+    k_nms<<<g1, 256, 0, stream>>>(g, state, parent, h, w, low, high);
+    dim3 g2(ceil_div(w, 64), ceil_div(h, 4), n);
+    k_union<<<g2, 256, 0, stream>>>(state, parent, h, w);
+    k_finalize<<<g2, 256, 0, stream>>>(state, parent, (uint8_t*)edges, h, w, out_channels);
+    return check_launch("fie_canny_u8");
+}

@@ -1,0 +1,217 @@
+// Memory-bound helper kernels: pre/post-processing, residual adds, nearest upsample, sinusoidal embedding,
+// row softmax, VAE posterior sample + add_noise, fused CFG + LCMScheduler.step.
+// All use 128-bit accesses where the layout allows and grid-stride loops sized to the SM count.
+#include "fie_common.cuh"
+
+namespace fie {
+
+static inline int grid_for(long long work_items, int block) {
+    long long b = (work_items + block - 1) / block;
+    long long cap = 148ll * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---- VaeImageProcessor.preprocess: u8 HWC -> fp16 NHWC (x/127.5 - 1 computed as 2*(x/255)-1 in fp32) ----
+__global__ void __launch_bounds__(256) k_pre(const uint8_t* __restrict__ in, __half* __restrict__ out, long long npix, int c_out, int normalize) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { float x = (float)in[i * 3 + c] / 255.0f; v[c] = normalize ? 2.0f * x - 1.0f : x; }
+        __half* o = out + i * c_out;
+        if (c_out == 4) {
+            __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], 0.0f);
+            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(o) = u;
+        } else {
+            for (int c = 0; c < c_out; ++c) o[c] = __float2half_rn(c < 3 ? v[c] : 0.0f);
+        }
+    }
+}
+
+// ---- VaeImageProcessor.postprocess: clamp(x/2+0.5,0,1) -> round(x*255) -> u8 ----
+__global__ void __launch_bounds__(256) k_post(const __half* __restrict__ in, int ld, uint8_t* __restrict__ out, long long npix) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // the reference computes x/2+0.5 and the clamp in the model dtype (fp16), then *255 and round in fp32
+            __half hx = __float2half_rn(__half2float(in[i * ld + c]) / 2.0f);
+            hx = __float2half_rn(__half2float(hx) + 0.5f);
+            float x = fminf(fmaxf(__half2float(hx), 0.0f), 1.0f);
+            out[i * 3 + c] = (uint8_t)rintf(x * 255.0f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_add(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        uint4 x = __ldg(a + i), y = __ldg(b + i), r;
+        const __half2* xh = reinterpret_cast<const __half2*>(&x); const __half2* yh = reinterpret_cast<const __half2*>(&y);
+        __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 fa = __half22float2(xh[j]), fb = __half22float2(yh[j]); rh[j] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y); }
+        o[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_silu(const uint4* __restrict__ a, uint4* __restrict__ o, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        uint4 x = __ldg(a + i), r;
+        const __half2* xh = reinterpret_cast<const __half2*>(&x); __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __half22float2(xh[j]); rh[j] = __floats2half2_rn(silu_f(f.x), silu_f(f.y)); }
+        o[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_up2x(const uint4* __restrict__ x, uint4* __restrict__ o, int n, int h, int w, int c8) {
+    const long long total = (long long)n * 2 * h * 2 * w * c8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int cv = (int)(i % c8); long long t = i / c8;
+        int ox = (int)(t % (2 * w)); t /= (2 * w);
+        int oy = (int)(t % (2 * h)); int img = (int)(t / (2 * h));
+        o[i] = __ldg(x + (((long long)img * h + (oy >> 1)) * w + (ox >> 1)) * c8 + cv);
+    }
+}
+
+struct SinCosArgs { float vals[64]; };
+__global__ void k_sincos(SinCosArgs a, int count, int dim, __half* __restrict__ out) {
+    const int half = dim / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count * half; i += gridDim.x * blockDim.x) {
+        int r = i / half, j = i % half;
+        float freq = expf(-logf(10000.0f) * (float)j / (float)half);
+        float arg = a.vals[r] * freq;
+        out[r * dim + j] = __float2half_rn(cosf(arg));
+        out[r * dim + half + j] = __float2half_rn(sinf(arg));
+    }
+}
+
+// one CTA per row; cols up to 64K
+__global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ s, long long ld_in, __half* __restrict__ p, long long ld_out, int cols, float scale) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const float* row = s + (long long)blockIdx.x * ld_in;
+    __half* orow = p + (long long)blockIdx.x * ld_out;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float mx = -INFINITY;
+    for (int i = tid * 4; i < cols; i += 1024) {
+        if (i + 4 <= cols) { float4 v = *reinterpret_cast<const float4*>(row + i); mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); }
+        else for (int j = i; j < cols; ++j) mx = fmaxf(mx, row[j]);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[wid] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bc = m; }
+    __syncthreads();
+    mx = bc;
+    const float sl2 = scale * 1.4426950408889634f;
+    float sum = 0.f;
+    for (int i = tid * 4; i < cols; i += 1024) {
+        if (i + 4 <= cols) { float4 v = *reinterpret_cast<const float4*>(row + i); sum += exp2f((v.x - mx) * sl2) + exp2f((v.y - mx) * sl2) + exp2f((v.z - mx) * sl2) + exp2f((v.w - mx) * sl2); }
+        else for (int j = i; j < cols; ++j) sum += exp2f((row[j] - mx) * sl2);
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    if (tid == 0) { float t = 0; for (int i = 0; i < 8; ++i) t += red[i]; bc = 1.0f / t; }
+    __syncthreads();
+    const float inv = bc;
+    for (int i = tid * 4; i < cols; i += 1024) {
+        if (i + 4 <= cols) {
+            float4 v = *reinterpret_cast<const float4*>(row + i);
+            __half2 a = __floats2half2_rn(exp2f((v.x - mx) * sl2) * inv, exp2f((v.y - mx) * sl2) * inv);
+            __half2 b = __floats2half2_rn(exp2f((v.z - mx) * sl2) * inv, exp2f((v.w - mx) * sl2) * inv);
+            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(orow + i) = u;
+        } else for (int j = i; j < cols; ++j) orow[j] = __float2half_rn(exp2f((row[j] - mx) * sl2) * inv);
+    }
+}
+
+// z0 = (mean + exp(0.5*clamp(logvar,-30,20))*xi)*scaling ; x = sqrt_a*z0 + sqrt_1ma*noise   (fp16 rounding points as the reference)
+__global__ void __launch_bounds__(256) k_vae_sample(const __half* __restrict__ mom, int ld_m, const __half* __restrict__ xi, const __half* __restrict__ noise,
+                                                    __half* __restrict__ out, long long npx, float scaling, float sa, float s1) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx * 4; i += (long long)gridDim.x * blockDim.x) {
+        long long px = i >> 2; int c = (int)(i & 3);
+        float mean = __half2float(mom[px * ld_m + c]);
+        float logvar = fminf(fmaxf(__half2float(mom[px * ld_m + 4 + c]), -30.0f), 20.0f);
+        float stdv = __half2float(__float2half_rn(expf(0.5f * logvar)));
+        float z = __half2float(__float2half_rn(mean + __half2float(__float2half_rn(stdv * __half2float(xi[i])))));
+        z = __half2float(__float2half_rn(z * scaling));
+        float a = __half2float(__float2half_rn(sa * z)), b = __half2float(__float2half_rn(s1 * __half2float(noise[i])));
+        out[i] = __float2half_rn(a + b);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cfg_lcm(const __half* __restrict__ eu, const __half* __restrict__ ec, int ld_e, const __half* __restrict__ x,
+                                                 const __half* __restrict__ noise, __half* __restrict__ out, long long npx, float g, float sa, float s1,
+                                                 float c_skip, float c_out, float sap, float s1p, int last) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx * 4; i += (long long)gridDim.x * blockDim.x) {
+        long long px = i >> 2; int c = (int)(i & 3);
+        float u = __half2float(eu[px * ld_e + c]), cc = __half2float(ec[px * ld_e + c]);
+        float eps = u + g * (cc - u);
+        float xv = __half2float(x[i]);
+        float x0 = (xv - s1 * eps) / sa;
+        float den = c_out * x0 + c_skip * xv;
+        float r = last ? den : sap * den + s1p * __half2float(noise[i]);
+        out[i] = __float2half_rn(r);
+    }
+}
+
+}  // namespace fie
+using namespace fie;
+
+extern "C" int fie_preprocess_u8_to_f16(const void* img, void* out, int n, int h, int w, int c_out, int normalize, void* stream) {
+    FIE_REQUIRE(img && out && n > 0 && h > 0 && w > 0 && c_out >= 3, "fie_preprocess_u8_to_f16: bad args");
+    long long npix = (long long)n * h * w;
+    k_pre<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img, (__half*)out, npix, c_out, normalize);
+    return check_launch("fie_preprocess_u8_to_f16");
+}
+extern "C" int fie_postprocess_f16_to_u8(const void* x, int ld, void* out, int n, int h, int w, void* stream) {
+    FIE_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && ld >= 3, "fie_postprocess_f16_to_u8: bad args");
+    long long npix = (long long)n * h * w;
+    k_post<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ld, (uint8_t*)out, npix);
+    return check_launch("fie_postprocess_f16_to_u8");
+}
+extern "C" int fie_add_f16(const void* a, const void* b, void* out, long long count, void* stream) {
+    FIE_REQUIRE(a && b && out && count > 0 && (count % 8) == 0, "fie_add_f16: count must be a positive multiple of 8");
+    k_add<<<grid_for(count / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (const uint4*)b, (uint4*)out, count / 8);
+    return check_launch("fie_add_f16");
+}
+extern "C" int fie_silu_f16(const void* a, void* out, long long count, void* stream) {
+    FIE_REQUIRE(a && out && count > 0 && (count % 8) == 0, "fie_silu_f16: count must be a positive multiple of 8");
+    k_silu<<<grid_for(count / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, (uint4*)out, count / 8);
+    return check_launch("fie_silu_f16");
+}
+extern "C" int fie_upsample2x_f16(const void* x, void* out, int n, int h, int w, int c, void* stream) {
+    FIE_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && c > 0 && (c % 8) == 0, "fie_upsample2x_f16: c must be a multiple of 8");
+    long long total = (long long)n * 4 * h * w * (c / 8);
+    k_up2x<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n, h, w, c / 8);
+    return check_launch("fie_upsample2x_f16");
+}
+extern "C" int fie_sincos_embedding(const float* host_vals, int count, int dim, void* out, void* stream) {
+    FIE_REQUIRE(host_vals && out && count > 0 && count <= 64 && dim > 0 && (dim % 2) == 0, "fie_sincos_embedding: bad args");
+    SinCosArgs a; for (int i = 0; i < 64; ++i) a.vals[i] = i < count ? host_vals[i] : 0.f;
+    k_sincos<<<ceil_div((long long)count * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(a, count, dim, (__half*)out);
+    return check_launch("fie_sincos_embedding");
+}
+extern "C" int fie_softmax_rows_f32_to_f16(const void* s, long long ld_in, void* p, long long ld_out, long long rows, int cols, float scale, void* stream) {
+    FIE_REQUIRE(s && p && rows > 0 && rows < (1ll << 31) && cols > 0 && (ld_in % 4) == 0 && (ld_out % 4) == 0, "fie_softmax_rows: bad args");
+    k_softmax_rows<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const float*)s, ld_in, (__half*)p, ld_out, cols, scale);
+    return check_launch("fie_softmax_rows_f32_to_f16");
+}
+extern "C" int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, void* x_out,
+                                        long long count_px, float scaling, float sqrt_a, float sqrt_1ma, void* stream) {
+    FIE_REQUIRE(moments && xi && noise && x_out && count_px > 0 && ld_m >= 8, "fie_vae_sample_add_noise: bad args");
+    k_vae_sample<<<grid_for(count_px * 4, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)moments, ld_m, (const __half*)xi, (const __half*)noise,
+                                                                                (__half*)x_out, count_px, scaling, sqrt_a, sqrt_1ma);
+    return check_launch("fie_vae_sample_add_noise");
+}
+extern "C" int fie_cfg_lcm_step(const void* eps_u, const void* eps_c, int ld_e, const void* x, const void* noise, void* x_out,
+                                long long count_px, float guidance, float sqrt_a, float sqrt_1ma, float c_skip, float c_out,
+                                float sqrt_a_prev, float sqrt_1ma_prev, int last, void* stream) {
+    FIE_REQUIRE(eps_u && eps_c && x && x_out && count_px > 0 && ld_e >= 4 && (last || noise), "fie_cfg_lcm_step: bad args");
+    k_cfg_lcm<<<grid_for(count_px * 4, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)eps_u, (const __half*)eps_c, ld_e, (const __half*)x,
+                                                                              (const __half*)noise, (__half*)x_out, count_px, guidance, sqrt_a, sqrt_1ma,
+                                                                              c_skip, c_out, sqrt_a_prev, sqrt_1ma_prev, last);
+    return check_launch("fie_cfg_lcm_step");
+}

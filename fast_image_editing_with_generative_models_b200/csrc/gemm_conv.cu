@@ -1,0 +1,455 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M, N] = epilogue( A[M, K] * B[N, K]^T )     fp16 operands, fp32 accumulators in TMEM
+//
+// Replaces F.linear / F.conv2d (cuBLASLt / cuDNN) in every diffusers module on the reference's edit path
+// (UNet2DConditionModel, ControlNetModel, AutoencoderKL; reference call site src/pipeline.py:261-272).
+//
+// Data movement: TMA (cp.async.bulk.tensor) with 128-byte swizzle into a ring of shared-memory stages.
+//   GEMM mode:  A tile = 2-D box {64 k, 128 rows} of the row-major activation matrix.
+//   CONV mode:  A tile = 4-D box {64 ch, bw, bh, bn} (bw*bh*bn = 128 output pixels) of the NHWC activation,
+//               shifted by the filter tap; zero padding comes from TMA out-of-bounds fill, so im2col is never
+//               materialised.  Stride-2 convolutions read four parity-split views of the input.
+//   B tile = 2-D box {64 k, block_n rows} of the packed weight matrix [N][K].
+// Math: one elected thread issues tcgen05.mma (M=128, N=block_n, K=16) into a double-buffered TMEM accumulator.
+// Epilogue: 4 warps read TMEM (tcgen05.ld 32x32b), fuse bias / time-embedding broadcast / SiLU / GEGLU /
+//           scale / residual, and store fp16 (or fp32) rows.
+//
+// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 epilogue.
+#include "tc_common.cuh"
+
+namespace fie {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct GemmParams {
+    CUtensorMap a_maps[4];
+    CUtensorMap b_map;
+    int mode;         // 0 = GEMM, 1 = CONV
+    int num_kb;       // K blocks of 64
+    int kb_per_tap;   // CONV: cin/64
+    int kb_split;     // GEMM: k-blocks taken from a_maps[0]; the rest from a_maps[1]
+    int8_t tap_map[12], tap_dh[12], tap_dw[12];
+    int OH, OW;
+    long long M;
+    int N;            // accumulator columns (B rows)
+    int block_n;
+    int num_m_blocks, num_n_blocks;
+    int num_stages;
+    int tmem_cols;
+    // epilogue
+    void* D;
+    long long ldd;
+    int n_store;      // number of valid output columns
+    const float* col_bias;
+    const float* row_bias;
+    long long rows_per_group;
+    const float* m_bias;
+    const __half* residual;
+    long long ld_res;
+    float scale;
+    int act;
+    int out_f32;
+};
+
+__device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, int n0, const float (&v)[32]) {
+    // stores v[0..31] to output row m, columns n0..n0+31 (masked by n_store)
+    if (p.out_f32) {
+        float* d = reinterpret_cast<float*>(p.D) + m * p.ldd + n0;
+        if (n0 + 32 <= p.n_store && (p.ldd & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(d)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+            for (int i = 0; i < 32; ++i) if (n0 + i < p.n_store) d[i] = v[i];
+        }
+    } else {
+        __half* d = reinterpret_cast<__half*>(p.D) + m * p.ldd + n0;
+        if (n0 + 32 <= p.n_store && (p.ldd & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                __half2 h0 = __floats2half2_rn(v[8 * i], v[8 * i + 1]), h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
+                __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]), h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                reinterpret_cast<uint4*>(d)[i] = u;
+            }
+        } else {
+            for (int i = 0; i < 32; ++i) if (n0 + i < p.n_store) d[i] = __float2half_rn(v[i]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ GemmParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is only guaranteed 16-byte aligned by the ABI; round up to 1024 for the 128B swizzle
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int block_n = p.block_n;
+    const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+    const int num_stages = p.num_stages;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
+        tma_prefetch_desc(&p.b_map);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+                const long long m0 = (long long)m_blk * BLOCK_M;
+                int n0i = 0, h0 = 0, w0 = 0;
+                if (p.mode == 1) {
+                    const long long pix = (long long)p.OH * p.OW;
+                    n0i = (int)(m0 / pix);
+                    const int rem = (int)(m0 % pix);
+                    h0 = rem / p.OW; w0 = rem % p.OW;
+                }
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                    if (p.mode == 0) {
+                        if (kb < p.kb_split) tma_load_2d(&p.a_maps[0], &full_bar[stage], sa, kb * BLOCK_K, (int)m0);
+                        else tma_load_2d(&p.a_maps[1], &full_bar[stage], sa, (kb - p.kb_split) * BLOCK_K, (int)m0);
+                    } else {
+                        const int tap = kb / p.kb_per_tap;
+                        const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                        tma_load_4d(&p.a_maps[p.tap_map[tap]], &full_bar[stage], sa, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0i);
+                    }
+                    tma_load_2d(&p.b_map, &full_bar[stage], sb, kb * BLOCK_K, n_blk * block_n);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = umma_idesc_f16(BLOCK_M, block_n);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * block_n);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / 16; ++k)
+                        umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == p.num_kb - 1) umma_commit(&tmem_full[buf]);
+                }
+                __syncwarp();
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== Epilogue =====================
+        const int ew = warp & 3;                       // TMEM lane quadrant accessible to this warp
+        const int row_in_tile = ew * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        const bool geglu = p.act == FIE_ACT_GEGLU;
+        const int half_n = block_n >> 1;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+            const long long m = (long long)m_blk * BLOCK_M + row_in_tile;
+            const bool row_ok = m < p.M;
+            mbar_wait(&tmem_full[buf], acc_phase);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + lane_addr + (uint32_t)(buf * block_n);
+            const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
+            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.N : nullptr;
+            const int nchunks = (geglu ? half_n : block_n) / 32;
+            for (int c = 0; c < nchunks; ++c) {
+                uint32_t r[32];
+                float v[32];
+                tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
+                tmem_ld_wait();
+                const int nacc = n_blk * block_n + c * 32;        // accumulator column (B row) of v[0]
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + mb;
+                if (p.col_bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(p.col_bias + nacc + i);
+                }
+                if (rb) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(rb + nacc + i);
+                }
+                int nout = nacc;
+                if (geglu) {
+                    uint32_t g[32];
+                    tmem_ld_32x32(tacc + (uint32_t)(half_n + c * 32), g);
+                    tmem_ld_wait();
+                    const int ng = nacc + half_n;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float gate = __uint_as_float(g[i]);
+                        if (p.col_bias && ng + i < p.N) gate += __ldg(p.col_bias + ng + i);
+                        v[i] *= gelu_erf_f(gate);
+                    }
+                    nout = n_blk * half_n + c * 32;
+                } else if (p.act == FIE_ACT_SILU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                }
+                if (p.scale != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+                }
+                if (row_ok && nout < p.n_store) {
+                    if (p.residual) {
+                        const __half* rp = p.residual + m * p.ld_res + nout;
+                        if (nout + 32 <= p.n_store && (p.ld_res & 7) == 0) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
+                                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
+                            }
+                        } else {
+                            for (int i = 0; i < 32; ++i) if (nout + i < p.n_store) v[i] += __half2float(rp[i]);
+                        }
+                    }
+                    store_chunk(p, m, nout, v);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available (driver too old?)"); return FIE_ERR_CUDA; }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) { set_error("TMA base pointer %p not 16-byte aligned", base); return FIE_ERR_INVALID; }
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; if (box[i] > 256 || box[i] == 0) { set_error("TMA box dim %d = %u out of range", i, box[i]); return FIE_ERR_INVALID; } }
+    for (int i = 0; i + 1 < rank; ++i) { gs[i] = strides_bytes[i]; if (gs[i] & 15) { set_error("TMA stride %d = %llu not a multiple of 16 bytes", i, (unsigned long long)gs[i]); return FIE_ERR_INVALID; } }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r, rank,
+                                       (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0); return FIE_ERR_CUDA; }
+    return FIE_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
+    return g_num_sms;
+}
+
+static int pick_block_n(long long M, int N, bool geglu) {
+    // GEGLU weights are pre-interleaved per tile by the host, so the tile width may depend on N only.
+    if (geglu) return fie_geglu_block_n(N);
+    const int step = 32;
+    const long long mblocks = (M + BLOCK_M - 1) / BLOCK_M;
+    const int sms = num_sms();
+    int best = step; double best_cost = 1e30;
+    for (int bn = step; bn <= 256; bn += step) {
+        const long long tiles = mblocks * ((N + bn - 1) / bn);
+        const long long waves = (tiles + sms - 1) / sms;
+        // per-tile time ~ MMA (prop. to bn) + fixed overhead; smaller tiles re-read A more often
+        const double cost = (double)waves * (bn + 40);
+        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
+    static const fie_epilogue kDefault = {nullptr, nullptr, 1, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0};
+    if (!ep) ep = &kDefault;
+    p.D = D; p.ldd = ldd;
+    p.col_bias = ep->col_bias; p.row_bias = ep->row_bias; p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+    p.m_bias = ep->m_bias; p.residual = (const __half*)ep->residual; p.ld_res = ep->ld_res;
+    p.scale = ep->scale; p.act = ep->act; p.out_f32 = ep->out_f32;
+    FIE_REQUIRE(p.act >= 0 && p.act <= 2, "epilogue: bad act %d", p.act);
+    FIE_REQUIRE(!(p.act == FIE_ACT_GEGLU && (N % 64)), "GEGLU needs N %% 64 == 0");
+    FIE_REQUIRE(!(p.residual && p.ld_res <= 0), "epilogue: residual needs ld_res");
+    (void)M;
+    return FIE_OK;
+}
+
+static int launch(GemmParams& p, cudaStream_t stream) {
+    const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+    int stages = SMEM_BUDGET / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) stages = 2;
+    p.num_stages = stages;
+    int cols = 2 * p.block_n, tc = 32; while (tc < cols) tc <<= 1;
+    p.tmem_cols = tc;
+    size_t smem = (size_t)stages * stage_bytes + 1024;
+    // >113 KiB of dynamic smem guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
+    if (tc > 256 && smem < 120 * 1024) smem = 120 * 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gemm_conv): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+        attr_set = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks;
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    k_gemm_conv<<<grid, 256, smem, stream>>>(p);
+    return check_launch("k_gemm_conv");
+}
+
+}  // namespace fie
+
+using namespace fie;
+
+extern "C" int fie_geglu_block_n(int N) { return (N % 256) == 0 ? 256 : ((N % 128) == 0 ? 128 : 64); }
+
+extern "C" int fie_gemm_f16(const void* A, long long lda, const void* A1, long long lda1, int k_split,
+                            const void* B, void* D, long long ldd, long long M, int N, int K,
+                            const fie_epilogue* ep, void* stream) {
+    FIE_REQUIRE(A && B && D, "fie_gemm_f16: null pointer");
+    FIE_REQUIRE(M > 0 && N > 0 && K > 0, "fie_gemm_f16: bad shape M=%lld N=%d K=%d", M, N, K);
+    FIE_REQUIRE(M < (1ll << 31), "fie_gemm_f16: M too large");
+    FIE_REQUIRE((lda % 8) == 0 && (K % 8) == 0 && lda >= (A1 ? k_split : K), "fie_gemm_f16: lda/K must be multiples of 8");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = fill_epilogue(p, ep, M, N, D, ldd);
+    if (rc) return rc;
+    const bool geglu = p.act == FIE_ACT_GEGLU;
+    p.mode = 0; p.M = M; p.N = N;
+    p.block_n = pick_block_n(M, N, geglu);
+    p.num_m_blocks = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    p.num_n_blocks = (N + p.block_n - 1) / p.block_n;
+    p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb_per_tap = p.num_kb; p.kb_split = p.num_kb;
+    p.n_store = geglu ? N / 2 : N;
+    uint64_t dims[2], strides[1]; uint32_t box[2];
+    if (A1) {
+        FIE_REQUIRE(k_split > 0 && k_split < K && (k_split % BLOCK_K) == 0 && (lda1 % 8) == 0 && lda1 >= K - k_split, "fie_gemm_f16: bad two-source split");
+        p.kb_split = k_split / BLOCK_K;
+        dims[0] = (uint64_t)k_split; dims[1] = (uint64_t)M; strides[0] = (uint64_t)lda * 2; box[0] = BLOCK_K; box[1] = BLOCK_M;
+        if ((rc = make_tmap_f16(&p.a_maps[0], A, 2, dims, strides, box))) return rc;
+        dims[0] = (uint64_t)(K - k_split); strides[0] = (uint64_t)lda1 * 2;
+        if ((rc = make_tmap_f16(&p.a_maps[1], A1, 2, dims, strides, box))) return rc;
+    } else {
+        dims[0] = (uint64_t)K; dims[1] = (uint64_t)M; strides[0] = (uint64_t)lda * 2; box[0] = BLOCK_K; box[1] = BLOCK_M;
+        if ((rc = make_tmap_f16(&p.a_maps[0], A, 2, dims, strides, box))) return rc;
+        p.a_maps[1] = p.a_maps[0];
+    }
+    p.a_maps[2] = p.a_maps[0]; p.a_maps[3] = p.a_maps[0];
+    dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; strides[0] = (uint64_t)K * 2; box[0] = BLOCK_K; box[1] = (uint32_t)p.block_n;
+    if ((rc = make_tmap_f16(&p.b_map, B, 2, dims, strides, box))) return rc;
+    return launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long long ldd, int n, int h, int w, int cin, int cout,
+                               int cout_valid, int stride, int pad_mode, const fie_epilogue* ep, void* stream) {
+    FIE_REQUIRE(x && wgt && out, "fie_conv3x3_f16: null pointer");
+    FIE_REQUIRE(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "fie_conv3x3_f16: bad shape");
+    FIE_REQUIRE((cin % BLOCK_K) == 0, "fie_conv3x3_f16: cin=%d must be a multiple of 64", cin);
+    FIE_REQUIRE((cout % 32) == 0, "fie_conv3x3_f16: cout=%d (weight rows) must be a multiple of 32", cout);
+    FIE_REQUIRE(stride == 1 || stride == 2, "fie_conv3x3_f16: stride must be 1 or 2");
+    FIE_REQUIRE(stride == 1 || ((h % 2) == 0 && (w % 2) == 0), "fie_conv3x3_f16: stride 2 needs even h, w");
+    const int OH = h / stride, OW = w / stride;
+    int bw, bh, bn;
+    if (OW >= 128) { FIE_REQUIRE((OW % 128) == 0, "fie_conv3x3_f16: output width %d must be a multiple of 128", OW); bw = 128; bh = 1; bn = 1; }
+    else {
+        FIE_REQUIRE((128 % OW) == 0, "fie_conv3x3_f16: output width %d must divide 128", OW);
+        bw = OW; bh = 128 / OW;
+        if (bh <= OH) { FIE_REQUIRE((OH % bh) == 0, "fie_conv3x3_f16: output height %d not a multiple of %d", OH, bh); bn = 1; }
+        else { FIE_REQUIRE((bh % OH) == 0, "fie_conv3x3_f16: output height %d must divide %d", OH, bh); bn = bh / OH; bh = OH; }
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const long long M = (long long)n * OH * OW;
+    int rc = fill_epilogue(p, ep, M, cout, out, ldd);
+    if (rc) return rc;
+    FIE_REQUIRE(p.act != FIE_ACT_GEGLU, "fie_conv3x3_f16: GEGLU epilogue not supported for conv");
+    p.mode = 1; p.M = M; p.N = cout; p.OH = OH; p.OW = OW;
+    p.block_n = pick_block_n(M, cout, false);
+    p.num_m_blocks = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
+    p.kb_per_tap = cin / BLOCK_K;
+    p.num_kb = 9 * p.kb_per_tap;
+    p.kb_split = p.num_kb;
+    p.n_store = cout_valid > 0 ? cout_valid : cout;
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    if (stride == 1) {
+        const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+        if ((rc = make_tmap_f16(&p.a_maps[0], x, 4, dims, strides, box))) return rc;
+        p.a_maps[1] = p.a_maps[0]; p.a_maps[2] = p.a_maps[0]; p.a_maps[3] = p.a_maps[0];
+        for (int t = 0; t < 9; ++t) { p.tap_map[t] = 0; p.tap_dh[t] = (int8_t)(t / 3 - 1); p.tap_dw[t] = (int8_t)(t % 3 - 1); }
+    } else {
+        // parity-split views: element (c, w2, h2, n) of view (hp, wp) is x[n, 2*h2+hp, 2*w2+wp, c]
+        const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)(w / 2), (uint64_t)(h / 2), (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 2};
+        for (int hp = 0; hp < 2; ++hp)
+            for (int wp = 0; wp < 2; ++wp) {
+                const uint8_t* base = (const uint8_t*)x + ((size_t)hp * w + wp) * cin * 2;
+                if ((rc = make_tmap_f16(&p.a_maps[hp * 2 + wp], base, 4, dims, strides, box))) return rc;
+            }
+        // input row = 2*oh + k - pad:  pad 1: k=0 -> (parity 1, shift -1), k=1 -> (0, 0), k=2 -> (1, 0)
+        //                              pad 0 (asymmetric (0,1) padding): k=0 -> (0, 0), k=1 -> (1, 0), k=2 -> (0, +1)
+        static const int par1[3] = {1, 0, 1}, sh1[3] = {-1, 0, 0}, par0[3] = {0, 1, 0}, sh0[3] = {0, 0, 1};
+        const int* par = pad_mode == 0 ? par1 : par0; const int* sh = pad_mode == 0 ? sh1 : sh0;
+        for (int t = 0; t < 9; ++t) {
+            const int kh = t / 3, kw = t % 3;
+            p.tap_map[t] = (int8_t)(par[kh] * 2 + par[kw]); p.tap_dh[t] = (int8_t)sh[kh]; p.tap_dw[t] = (int8_t)sh[kw];
+        }
+    }
+    const uint64_t bdims[2] = {(uint64_t)9 * cin, (uint64_t)cout};
+    const uint64_t bstr[1] = {(uint64_t)9 * cin * 2};
+    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)p.block_n};
+    if ((rc = make_tmap_f16(&p.b_map, wgt, 2, bdims, bstr, bbox))) return rc;
+    return launch(p, (cudaStream_t)stream);
+}

@@ -1,0 +1,184 @@
+// GroupNorm(+SiLU) and LayerNorm on NHWC / token-major fp16 activations (memory-bound).
+//   GroupNorm: pass 1 accumulates per-(image, group) sum / sum-of-squares (fp32, 128-bit loads, warp-shuffle +
+//   shared-memory reduction, one atomicAdd pair per CTA and group); pass 2 applies (x-mean)*rstd*gamma+beta (+SiLU)
+//   and writes fp16.  An optional second source realises the torch.cat([h, skip]) of the UNet up blocks so the
+//   concatenated tensor is only ever written once, already normalised.
+//   LayerNorm: one warp per row, row kept in registers, two-pass mean / variance in fp32.
+// Replaces F.group_norm / F.silu / F.layer_norm in diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock.
+#include "fie_common.cuh"
+
+namespace fie {
+
+struct GNArgs {
+    const uint4* x0; const uint4* x1; uint4* out;
+    int c0v, c1v, cv;          // channel vectors (8 fp16) per source / total
+    long long hw; int groups; int cpg;   // channels per group
+    const float* gamma; const float* beta; float eps; int silu; float* stats;
+    int rows_per_cta; int rows_in_flight;
+};
+
+__global__ void __launch_bounds__(512) k_gn_stats(GNArgs a) {
+    __shared__ float gs[64], gq[64];
+    const int img = blockIdx.y;
+    const int v = threadIdx.x % a.cv, rsub = threadIdx.x / a.cv;
+    for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) { if (i < a.groups) gs[i] = 0.f; else gq[i - a.groups] = 0.f; }
+    __syncthreads();
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (rsub < a.rows_in_flight) {
+        const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
+        const long long r1 = min(r0 + (long long)a.rows_per_cta, a.hw);
+        const bool first = v < a.c0v;
+        const uint4* src = first ? a.x0 + (long long)img * a.hw * a.c0v + v : a.x1 + (long long)img * a.hw * a.c1v + (v - a.c0v);
+        const int stride = first ? a.c0v : a.c1v;
+        for (long long r = r0 + rsub; r < r1; r += a.rows_in_flight) {
+            uint4 u = __ldg(src + r * stride);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); s[2 * j] += f.x; q[2 * j] += f.x * f.x; s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y; }
+        }
+        // channels v*8 .. v*8+7 -> groups
+        if (a.cpg >= 8 && (a.cpg % 8) == 0) {
+            float ts = 0.f, tq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ts += s[j]; tq += q[j]; }
+            int g = (v * 8) / a.cpg;
+            atomicAdd(&gs[g], ts); atomicAdd(&gq[g], tq);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { int g = (v * 8 + j) / a.cpg; atomicAdd(&gs[g], s[j]); atomicAdd(&gq[g], q[j]); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.groups; i += blockDim.x) {
+        atomicAdd(&a.stats[((long long)img * a.groups + i) * 2], gs[i]);
+        atomicAdd(&a.stats[((long long)img * a.groups + i) * 2 + 1], gq[i]);
+    }
+}
+
+__global__ void __launch_bounds__(512) k_gn_apply(GNArgs a) {
+    const int img = blockIdx.y;
+    const int v = threadIdx.x % a.cv, rsub = threadIdx.x / a.cv;
+    if (rsub >= a.rows_in_flight) return;
+    float ga[8], be[8], mu[8], rs[8];
+    const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int c = v * 8 + j, g = c / a.cpg;
+        float sum = a.stats[((long long)img * a.groups + g) * 2], sq = a.stats[((long long)img * a.groups + g) * 2 + 1];
+        float mean = sum * inv_cnt, var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+        mu[j] = mean; rs[j] = rsqrtf(var + a.eps);
+        ga[j] = __ldg(a.gamma + c); be[j] = __ldg(a.beta + c);
+    }
+    const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
+    const long long r1 = min(r0 + (long long)a.rows_per_cta, a.hw);
+    const bool first = v < a.c0v;
+    const uint4* src = first ? a.x0 + (long long)img * a.hw * a.c0v + v : a.x1 + (long long)img * a.hw * a.c1v + (v - a.c0v);
+    const int stride = first ? a.c0v : a.c1v;
+    uint4* dst = a.out + (long long)img * a.hw * a.cv + v;
+    for (long long r = r0 + rsub; r < r1; r += a.rows_in_flight) {
+        uint4 u = __ldg(src + r * stride), o;
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h[j]);
+            float y0 = (f.x - mu[2 * j]) * rs[2 * j] * ga[2 * j] + be[2 * j];
+            float y1 = (f.y - mu[2 * j + 1]) * rs[2 * j + 1] * ga[2 * j + 1] + be[2 * j + 1];
+            if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+            oh[j] = __floats2half2_rn(y0, y1);
+        }
+        dst[r * a.cv] = o;
+    }
+}
+
+// ---- LayerNorm: warp per row, up to 8 vectors (2048 channels) per lane ----
+template <int MAXV>
+__global__ void __launch_bounds__(256) k_layernorm(const uint4* __restrict__ x, uint4* __restrict__ out, long long rows, int cv,
+                                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const uint4* src = x + row * cv;
+    float vals[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int v = lane + i * 32;
+        if (v < cv) {
+            uint4 u = __ldg(src + v);
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); vals[i][2 * j] = f.x; vals[i][2 * j + 1] = f.y; sum += f.x + f.y; }
+        }
+    }
+    const float c = (float)(cv * 8);
+    const float mean = warp_sum(sum) / c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < cv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float d = vals[i][j] - mean; sq += d * d; }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / c + eps);
+    uint4* dst = out + row * cv;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        int v = lane + i * 32;
+        if (v < cv) {
+            float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + v * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + v * 2 + 1);
+            float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + v * 2), b1 = __ldg(reinterpret_cast<const float4*>(beta) + v * 2 + 1);
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint4 o; __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                oh[j] = __floats2half2_rn((vals[i][2 * j] - mean) * rstd * g[2 * j] + b[2 * j], (vals[i][2 * j + 1] - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
+            dst[v] = o;
+        }
+    }
+}
+
+}  // namespace fie
+using namespace fie;
+
+extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, void* out, int n, long long hw, int groups,
+                                 const float* gamma, const float* beta, float eps, int fuse_silu, float* stats_ws, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FIE_REQUIRE(x0 && out && gamma && beta && stats_ws, "fie_groupnorm_f16: null pointer");
+    if (!x1) c1 = 0;
+    const int c = c0 + c1;
+    FIE_REQUIRE(n > 0 && n <= 65535 && hw > 0 && c0 > 0 && (c0 % 8) == 0 && (c1 % 8) == 0, "fie_groupnorm_f16: channels must be multiples of 8");
+    FIE_REQUIRE(groups > 0 && groups <= 64 && (c % groups) == 0, "fie_groupnorm_f16: bad groups");
+    FIE_REQUIRE(c / 8 <= 512, "fie_groupnorm_f16: too many channels (%d)", c);
+    GNArgs a;
+    a.x0 = (const uint4*)x0; a.x1 = (const uint4*)x1; a.out = (uint4*)out;
+    a.c0v = c0 / 8; a.c1v = c1 / 8; a.cv = c / 8; a.hw = hw; a.groups = groups; a.cpg = c / groups;
+    a.gamma = gamma; a.beta = beta; a.eps = eps; a.silu = fuse_silu; a.stats = stats_ws;
+    a.rows_in_flight = 512 / a.cv; if (a.rows_in_flight < 1) a.rows_in_flight = 1;
+    const int threads = ((a.cv * a.rows_in_flight + 31) / 32) * 32;
+    // enough CTAs to cover the machine a few times, at least rows_in_flight*4 rows each
+    long long want = (148ll * 4 + n - 1) / n;
+    long long rows_per_cta = (hw + want - 1) / want;
+    if (rows_per_cta < (long long)a.rows_in_flight * 4) rows_per_cta = (long long)a.rows_in_flight * 4;
+    a.rows_per_cta = (int)rows_per_cta;
+    dim3 grid((unsigned)((hw + rows_per_cta - 1) / rows_per_cta), n);
+    cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * n, stream);
+    if (e != cudaSuccess) { set_error("fie_groupnorm_f16: memset: %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+    k_gn_stats<<<grid, threads, 0, stream>>>(a);
+    k_gn_apply<<<grid, threads, 0, stream>>>(a);
+    return check_launch("fie_groupnorm_f16");
+}
+
+extern "C" int fie_layernorm_f16(const void* x, void* out, long long rows, int c, const float* gamma, const float* beta, float eps, void* stream) {
+    FIE_REQUIRE(x && out && gamma && beta && rows > 0 && c > 0 && (c % 8) == 0 && c <= 2048, "fie_layernorm_f16: c must be a multiple of 8, <= 2048");
+    const int cv = c / 8;
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (cv <= 64) k_layernorm<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
+    else if (cv <= 160) k_layernorm<5><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
+    else k_layernorm<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
+    return check_launch("fie_layernorm_f16");
+}

@@ -1,0 +1,243 @@
+"""Thin Python wrappers over the C-ABI: torch owns device memory and streams, the kernels do the work.
+
+Activations are NHWC / token-major fp16 tensors.  Every wrapper raises if the CUDA library is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+LAUNCHES = 0  # number of our kernels launched through this module (bench reports it)
+_KERNELS_PER_CALL = {"canny3": 4, "canny1": 3, "groupnorm": 2}
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.FieError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.FieError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.FieError(f"{name}: expected a contiguous tensor")
+
+
+def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: int = 1) -> torch.Tensor:
+    """uint8 [N,H,W,3] (RGB) or [N,H,W] (gray) -> uint8 edges [N,H,W] or [N,H,W,3] (0/255); == cv2.Canny."""
+    _req(img_u8, torch.uint8, "canny")
+    in_ch = 3 if img_u8.dim() == 4 else 1
+    n, h, w = img_u8.shape[:3]
+    L = _lib.lib()
+    ws_bytes = L.fie_canny_workspace_bytes(n, h, w)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=img_u8.device)
+    out = torch.empty((n, h, w, 3) if out_channels == 3 else (n, h, w), dtype=torch.uint8, device=img_u8.device)
+    check(L.fie_canny_u8(_p(img_u8), _p(out), n, h, w, in_ch, out_channels, int(low), int(high), _p(ws), ws_bytes, _stream()), "fie_canny_u8")
+    _count(4 if in_ch == 3 else 3)
+    return out
+
+
+def preprocess(img_u8: torch.Tensor, c_out: int = 4, normalize: bool = True) -> torch.Tensor:
+    _req(img_u8, torch.uint8, "preprocess")
+    n, h, w, _ = img_u8.shape
+    out = torch.empty((n, h, w, c_out), dtype=torch.float16, device=img_u8.device)
+    check(_lib.lib().fie_preprocess_u8_to_f16(_p(img_u8), _p(out), n, h, w, c_out, int(normalize), _stream()), "fie_preprocess_u8_to_f16")
+    _count()
+    return out
+
+
+def postprocess(x: torch.Tensor) -> torch.Tensor:
+    """fp16 [N,H,W,C>=3] -> uint8 [N,H,W,3]."""
+    _req(x, torch.float16, "postprocess")
+    n, h, w, c = x.shape
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
+    check(_lib.lib().fie_postprocess_f16_to_u8(_p(x), c, _p(out), n, h, w, _stream()), "fie_postprocess_f16_to_u8")
+    _count()
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(a, torch.float16, "add"); _req(b, torch.float16, "add")
+    out = torch.empty_like(a) if out is None else out
+    check(_lib.lib().fie_add_f16(_p(a), _p(b), _p(out), a.numel(), _stream()), "fie_add_f16")
+    _count()
+    return out
+
+
+def silu(a: torch.Tensor) -> torch.Tensor:
+    _req(a, torch.float16, "silu")
+    out = torch.empty_like(a)
+    check(_lib.lib().fie_silu_f16(_p(a), _p(out), a.numel(), _stream()), "fie_silu_f16")
+    _count()
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.float16, "upsample2x")
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
+    check(_lib.lib().fie_upsample2x_f16(_p(x), _p(out), n, h, w, c, _stream()), "fie_upsample2x_f16")
+    _count()
+    return out
+
+
+def sincos_embedding(vals, dim: int, device) -> torch.Tensor:
+    vals = [float(v) for v in vals]
+    arr = (ctypes.c_float * len(vals))(*vals)
+    out = torch.empty((len(vals), dim), dtype=torch.float16, device=device)
+    check(_lib.lib().fie_sincos_embedding(arr, len(vals), dim, _p(out), _stream()), "fie_sincos_embedding")
+    _count()
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(s, torch.float32, "softmax_rows")
+    rows, cols = s.shape
+    out = torch.empty((rows, cols), dtype=torch.float16, device=s.device) if out is None else out
+    check(_lib.lib().fie_softmax_rows_f32_to_f16(_p(s), s.stride(0), _p(out), out.stride(0), rows, cols, float(scale), _stream()), "fie_softmax_rows")
+    _count()
+    return out
+
+
+def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, groups: int = 32,
+              x1: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x0 [N,H,W,C0] (+ optional concatenated x1 [N,H,W,C1]) -> [N,H,W,C0+C1] normalised (+SiLU)."""
+    _req(x0, torch.float16, "groupnorm")
+    n = x0.shape[0]
+    c0 = x0.shape[-1]
+    hw = x0.numel() // (n * c0)
+    c1 = 0
+    if x1 is not None:
+        _req(x1, torch.float16, "groupnorm")
+        c1 = x1.shape[-1]
+    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), dtype=torch.float16, device=x0.device)
+    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x0.device)
+    check(_lib.lib().fie_groupnorm_f16(_p(x0), c0, _p(x1), c1, _p(out), n, hw, groups, _p(gamma), _p(beta), float(eps), int(silu),
+                                        _p(stats), _stream()), "fie_groupnorm_f16")
+    _count(2)
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _req(x, torch.float16, "layernorm")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    out = torch.empty_like(x)
+    check(_lib.lib().fie_layernorm_f16(_p(x), _p(out), rows, c, _p(gamma), _p(beta), float(eps), _stream()), "fie_layernorm_f16")
+    _count()
+    return out
+
+
+def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False):
+    ep = Epilogue()
+    ep.col_bias = _p(col_bias); ep.row_bias = _p(row_bias); ep.rows_per_group = int(rows_per_group); ep.m_bias = _p(m_bias)
+    ep.residual = _p(residual); ep.ld_res = residual.stride(-2) if residual is not None else 0
+    ep.scale = float(scale); ep.act = int(act); ep.out_f32 = int(out_f32)
+    return ep
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, n_valid: Optional[int] = None,
+         col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False) -> torch.Tensor:
+    """D = epilogue(A @ W^T).  a: [..., K] fp16 rows (row stride may exceed K), w: [N, K] fp16; optional a1 continues K."""
+    if a.dtype != torch.float16 or w.dtype != torch.float16 or not a.is_cuda:
+        raise _lib.FieError("gemm: fp16 CUDA tensors required")
+    k0 = a.shape[-1]
+    m = a.numel() // k0
+    lda = a.stride(-2) if a.dim() >= 2 else k0
+    n, k = w.shape
+    k_split, lda1 = 0, 0
+    if a1 is not None:
+        k_split = k0
+        lda1 = a1.stride(-2)
+        assert k0 + a1.shape[-1] == k
+    else:
+        assert k0 == k, (k0, k)
+    n_out = n // 2 if act == ACT_GEGLU else n
+    if out is None:
+        out = torch.empty(tuple(a.shape[:-1]) + (n_out,), dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
+    ldd = out.stride(-2) if out.dim() >= 2 else n_out
+    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32)
+    check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")
+    _count()
+    return out
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad_mode: int = 0, cout_valid: Optional[int] = None,
+            out: Optional[torch.Tensor] = None, col_bias=None, row_bias=None, rows_per_group=1, residual=None, scale=1.0, act=ACT_NONE) -> torch.Tensor:
+    """x [N,H,W,Cin] fp16, w packed [Cout, 9*Cin] fp16 -> [N,H/stride,W/stride,cout_valid]."""
+    _req(x, torch.float16, "conv3x3")
+    n, h, wd, cin = x.shape
+    cout = w.shape[0]
+    assert w.shape[1] == 9 * cin, (w.shape, cin)
+    cv = cout if cout_valid is None else cout_valid
+    if out is None:
+        out = torch.empty((n, h // stride, wd // stride, cv), dtype=torch.float16, device=x.device)
+    ep = _epilogue(col_bias, row_bias, rows_per_group, None, residual, scale, act, False)
+    check(_lib.lib().fie_conv3x3_f16(_p(x), _p(w), _p(out), out.stride(-2), n, h, wd, cin, cout, cv, stride, pad_mode, ctypes.byref(ep), _stream()),
+          "fie_conv3x3_f16")
+    _count()
+    return out
+
+
+def conv3x3_cin4(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ld_out: Optional[int] = None, act=ACT_NONE) -> torch.Tensor:
+    """x [N,H,W,4] fp16, w fp32 [cout,3,3,4] -> [N,H,W,ld_out] fp16 (channels >= cout zero)."""
+    _req(x, torch.float16, "conv3x3_cin4")
+    n, h, wd, c = x.shape
+    assert c == 4
+    ld = cout if ld_out is None else ld_out
+    out = torch.empty((n, h, wd, ld), dtype=torch.float16, device=x.device)
+    check(_lib.lib().fie_conv3x3_cin4_f16(_p(x), _p(w), _p(bias), _p(out), ld, n, h, wd, cout, int(act), _stream()), "fie_conv3x3_cin4_f16")
+    _count()
+    return out
+
+
+def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, heads: int, nq: int, nkv: int, out: Optional[torch.Tensor] = None,
+                  scale: float = 0.125) -> torch.Tensor:
+    """q [b*nq, >=heads*64] (row-strided views allowed), k/v [b*nkv, ...] -> [b*nq, heads*64]."""
+    for t in (q, k, v):
+        if t.dtype != torch.float16 or not t.is_cuda or t.stride(-1) != 1:
+            raise _lib.FieError("attention_d64: fp16 CUDA tensors with unit inner stride required")
+    if out is None:
+        out = torch.empty((b * nq, heads * 64), dtype=torch.float16, device=q.device)
+    check(_lib.lib().fie_attention_d64_f16(_p(q), q.stride(-2), _p(k), k.stride(-2), _p(v), v.stride(-2), _p(out), out.stride(-2),
+                                            b, heads, nq, nkv, float(scale), _stream()), "fie_attention_d64_f16")
+    _count()
+    return out
+
+
+def vae_sample_add_noise(moments: torch.Tensor, xi: torch.Tensor, noise: torch.Tensor, scaling: float, sqrt_a: float, sqrt_1ma: float) -> torch.Tensor:
+    """moments [N,H,W,>=8] fp16, xi/noise [N,H,W,4] fp16 -> noisy latents [N,H,W,4] fp16."""
+    _req(moments, torch.float16, "vae_sample_add_noise")
+    out = torch.empty_like(xi)
+    npx = xi.numel() // 4
+    check(_lib.lib().fie_vae_sample_add_noise(_p(moments), moments.shape[-1], _p(xi), _p(noise), _p(out), npx, float(scaling), float(sqrt_a), float(sqrt_1ma),
+                                               _stream()), "fie_vae_sample_add_noise")
+    _count()
+    return out
+
+
+def cfg_lcm_step(eps_u: torch.Tensor, eps_c: torch.Tensor, x: torch.Tensor, noise: Optional[torch.Tensor], guidance: float, c: dict) -> torch.Tensor:
+    """eps_u/eps_c: [N,H,W,ld] views (first 4 channels used); x [N,H,W,4]; c = LCM step coefficients."""
+    out = torch.empty_like(x)
+    npx = x.numel() // 4
+    check(_lib.lib().fie_cfg_lcm_step(_p(eps_u), _p(eps_c), eps_u.stride(-2), _p(x), _p(noise), _p(out), npx, float(guidance), float(c["sqrt_a"]),
+                                       float(c["sqrt_1ma"]), float(c["c_skip"]), float(c["c_out"]), float(c["sqrt_a_prev"]), float(c["sqrt_1ma_prev"]),
+                                       int(bool(c["last"])), _stream()), "fie_cfg_lcm_step")
+    _count()
+    return out

@@ -1,0 +1,43 @@
+"""Load-time weight layout transforms for the CUDA kernels (the cold path of ``FastEditor.__init__``,
+reference ``src/pipeline.py:45-181``): conv weights to [Cout][kh][kw][Cin], GEGLU row interleave, LoRA fuse."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+
+def pack_conv3x3(w: torch.Tensor, pad_cout_to: Optional[int] = None, pad_cin_to: Optional[int] = None) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> fp16 [Cout_p, 9*Cin_p] with K order (kh, kw, cin); zero padding of channels on request."""
+    cout, cin = w.shape[:2]
+    cp = pad_cin_to or cin
+    op = pad_cout_to or cout
+    out = torch.zeros((op, 3, 3, cp), dtype=torch.float16, device=w.device)
+    out[:cout, :, :, :cin] = w.permute(0, 2, 3, 1).to(torch.float16)
+    return out.reshape(op, 9 * cp).contiguous()
+
+
+def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """GEGLU projection [8C, C] (value rows first, gate rows second) -> rows interleaved per accumulator tile:
+    tile j = [value rows j*h..(j+1)*h | gate rows 4C+j*h..], h = fie_geglu_block_n(8C)/2."""
+    n = w.shape[0]
+    half = n // 2
+    h = _lib.lib().fie_geglu_block_n(n) // 2
+    assert half % h == 0
+    idx = torch.arange(n, device=w.device).view(2, half // h, h).permute(1, 0, 2).reshape(-1)
+    wp = w.index_select(0, idx).contiguous()
+    bp = None if b is None else b.index_select(0, idx).float().contiguous()
+    return wp, bp
+
+
+def fuse_lora(w: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float) -> torch.Tensor:
+    """W' = W + scale * B A  (re-association of the reference's unfused peft path, src/pipeline.py:154).
+    Linear: A [r, in], B [out, r].  Conv: A [r, in, k, k], B [out, r, 1, 1]."""
+    w32 = w.float()
+    if w.dim() == 4:
+        delta = torch.einsum("or,rikl->oikl", lora_b.float()[:, :, 0, 0], lora_a.float())
+    else:
+        delta = lora_b.float() @ lora_a.float()
+    return w32 + scale * delta

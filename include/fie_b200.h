@@ -1,0 +1,136 @@
+/* fie_b200 — C-ABI of the B200-native (sm_100a) hot path behind the reference's FastEditor.edit().
+ *
+ * The reference (vismaychuriwala/Fast-Image-Editing-with-Generative-Models) is pure Python: its edit path
+ * (src/pipeline.py:212-274) runs cv2.Canny on the CPU (:205) and then hands everything to the diffusers
+ * pipeline (:261-272), which dispatches torch ops (conv2d / linear / group_norm / layer_norm / SDPA ...) to
+ * cuDNN / cuBLAS / ATen.  The reference has no FFI of its own; the entry points below are what a binding for
+ * this path would bind: one per hot op, raw device pointers + explicit shapes + a cudaStream_t, no torch
+ * types, no allocation inside (workspace is passed in), no global mutable state besides the error string.
+ *
+ * Conventions
+ *   - all functions return FIE_OK (0) or a negative error code; fie_last_error() gives a message (thread-local)
+ *   - all pointers are DEVICE pointers unless stated otherwise; `stream` is a cudaStream_t passed as void*
+ *   - activations are NHWC / token-major fp16: an image tensor [N,H,W,C] is the matrix [N*H*W, C]
+ *   - weights are pre-packed by the host: conv [Cout][kh][kw][Cin] fp16, linear [out][in] fp16
+ */
+#ifndef FIE_B200_H
+#define FIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIE_OK 0
+#define FIE_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define FIE_ERR_CUDA (-2)    /* CUDA runtime / launch error */
+
+const char* fie_last_error(void);
+int fie_version(void);
+/* 1 if the current device is sm_100 (tcgen05/TMA kernels usable). */
+int fie_device_supported(void);
+
+/* ---- Canny: replaces cv2.cvtColor + cv2.Canny at reference src/pipeline.py:200,205 (and np.stack :208) ----
+ * img:   uint8 [n,h,w,in_channels] (in_channels 3 = RGB, 1 = gray)
+ * edges: uint8 [n,h,w,out_channels] (out_channels 1, or 3 = replicated), values 0/255
+ * Integer only; bit-exact with OpenCV (aperture 3, L1 gradient, no blur). */
+size_t fie_canny_workspace_bytes(int n, int h, int w);
+int fie_canny_u8(const void* img, void* edges, int n, int h, int w, int in_channels, int out_channels,
+                 int low, int high, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- Pre/post-processing: replaces VaeImageProcessor.preprocess/postprocess inside the diffusers call
+ *      at reference src/pipeline.py:261-272 ---- */
+/* uint8 [n,h,w,3] -> fp16 [n,h,w,c_out] (c_out >= 3, extra channels zero): x/127.5-1 (normalize=1) or x/255 */
+int fie_preprocess_u8_to_f16(const void* img_u8, void* out_f16, int n, int h, int w, int c_out, int normalize, void* stream);
+/* fp16 [n,h,w,ld] (first 3 channels) -> uint8 [n,h,w,3]: round(clamp(x/2+0.5,0,1)*255) */
+int fie_postprocess_f16_to_u8(const void* x_f16, int ld, void* out_u8, int n, int h, int w, void* stream);
+
+/* ---- Elementwise helpers ---- */
+/* out = a + b (fp16, count elements, multiple of 8) */
+int fie_add_f16(const void* a, const void* b, void* out, long long count, void* stream);
+/* out = silu(a) */
+int fie_silu_f16(const void* a, void* out, long long count, void* stream);
+/* nearest 2x upsample, NHWC fp16: [n,h,w,c] -> [n,2h,2w,c] */
+int fie_upsample2x_f16(const void* x, void* out, int n, int h, int w, int c, void* stream);
+/* sinusoidal embedding (diffusers Timesteps, flip_sin_to_cos, shift 0): vals fp32 [count] (HOST pointer,
+ * count <= 64) -> fp16 [count, dim] = cat(cos, sin) */
+int fie_sincos_embedding(const float* host_vals, int count, int dim, void* out_f16, void* stream);
+/* softmax over rows: fp32 [rows, cols] (ld_in) * scale -> fp16 [rows, cols] (ld_out) */
+int fie_softmax_rows_f32_to_f16(const void* s_f32, long long ld_in, void* p_f16, long long ld_out,
+                                long long rows, int cols, float scale, void* stream);
+
+/* ---- GroupNorm(+SiLU), NHWC fp16: replaces F.group_norm (+F.silu) in ResnetBlock2D / Transformer2DModel ----
+ * x0: [n, hw, c0]; optional x1: [n, hw, c1] is the channel-concatenated second source (torch.cat of the skip
+ * connection in the up blocks); out: [n, hw, c0+c1].  stats_ws: fp32 [n, groups, 2] scratch. */
+int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, void* out, int n, long long hw, int groups,
+                      const float* gamma, const float* beta, float eps, int fuse_silu, float* stats_ws, void* stream);
+
+/* ---- LayerNorm over the last dim, fp16 rows: replaces F.layer_norm in BasicTransformerBlock ---- */
+int fie_layernorm_f16(const void* x, void* out, long long rows, int c, const float* gamma, const float* beta,
+                      float eps, void* stream);
+
+/* ---- Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA) ----
+ * D[M, N] = epilogue( A[M, K] * B[N, K]^T ), fp16 operands, fp32 accumulation in TMEM.
+ * Replaces F.linear (cuBLASLt) and F.conv2d (cuDNN) in every diffusers module on the path. */
+enum { FIE_ACT_NONE = 0, FIE_ACT_SILU = 1, FIE_ACT_GEGLU = 2 };
+
+typedef struct {
+    /* epilogue: v = acc + col_bias[n] + row_bias[m / rows_per_group][n]  (+ chan_bias[m] if per-row bias)
+     *           v = act(v); v *= scale; v += residual[m, n]; store */
+    const float* col_bias;   /* [N] or NULL */
+    const float* row_bias;   /* [ceil(M / rows_per_group), N] or NULL (time-embedding broadcast) */
+    long long rows_per_group;
+    const float* m_bias;     /* [M] per-output-row bias or NULL (used for transposed projections) */
+    const void* residual;    /* fp16 [M, ld_res] or NULL */
+    long long ld_res;
+    float scale;             /* applied before the residual add */
+    int act;                 /* FIE_ACT_* ; GEGLU: B rows interleaved per tile (value half | gate half), N_out = N/2 */
+    int out_f32;             /* 1: D is fp32, else fp16 */
+} fie_epilogue;
+
+/* Accumulator tile width used for a GEGLU projection with N = 8C weight rows.  The host packs those rows per tile as
+ * [value rows j*h..(j+1)*h | gate rows 4C + j*h ..] with h = fie_geglu_block_n(N)/2 (bias likewise). */
+int fie_geglu_block_n(int N);
+
+/* A: fp16 [M, K] with row stride lda (elements, multiple of 8); optional second source A1 supplies
+ * K columns [k_split, K) (k_split multiple of 64) — a virtual torch.cat along K.
+ * B: fp16 [N, K] row-major (ldb = K).  D: [M, N_out] row stride ldd. */
+int fie_gemm_f16(const void* A, long long lda, const void* A1, long long lda1, int k_split,
+                 const void* B, void* D, long long ldd, long long M, int N, int K,
+                 const fie_epilogue* ep, void* stream);
+
+/* 3x3 convolution as implicit GEMM, NHWC fp16.  x: [n,h,w,cin] (cin multiple of 64), wgt: [cout][3][3][cin],
+ * out: [n,oh,ow,cout].  stride 1: pad 1.  stride 2: pad_mode 0 = symmetric pad 1 (UNet Downsample2D),
+ * pad_mode 1 = F.pad(0,1,0,1) then pad 0 (VAE encoder Downsample2D).  cout_valid <= cout columns are stored
+ * (weights may be zero-padded to a multiple of 32 output channels). */
+int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long long ldd, int n, int h, int w, int cin, int cout,
+                    int cout_valid, int stride, int pad_mode, const fie_epilogue* ep, void* stream);
+
+/* 3x3 convolution with tiny Cin (<= 4, NHWC fp16 with 4 channels), CUDA cores: conv_in of UNet/ControlNet/VAE.
+ * wgt: fp32 [cout][3][3][4]; bias fp32 [cout]; out fp16 [n,h,w,ld_out] (channels >= cout are zero-filled up to ld_out). */
+int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float* bias, void* out, int ld_out,
+                         int n, int h, int w, int cout, int act, void* stream);
+
+/* ---- Flash attention, head_dim 64 (tcgen05): replaces F.scaled_dot_product_attention in AttnProcessor2_0 ----
+ * q: fp16 rows [b*nq, ldq] (head h at columns h*64..), k/v: [b*nkv, ldk/ldv], out: [b*nq, ldo]. No mask. */
+int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                          void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, void* stream);
+
+/* ---- Scheduler / latent math: replaces DiagonalGaussianDistribution.sample, LCMScheduler.add_noise,
+ *      the CFG combine and LCMScheduler.step inside the diffusers call ---- */
+/* moments fp16 [n,hw,ld_m] (mean = ch 0..3, logvar = ch 4..7), xi/noise fp16 [n,hw,4]:
+ * z0 = (mean + exp(0.5*clamp(logvar,-30,20))*xi)*scaling; x = sqrt_a*z0 + sqrt_1ma*noise. Writes x (fp16 [n,hw,4]) */
+int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, void* x_out,
+                             long long count_px, float scaling, float sqrt_a, float sqrt_1ma, void* stream);
+/* eps_u/eps_c fp16 [count_px, ld_e] (first 4 ch), x fp16 [count_px,4], noise or NULL:
+ * eps = eps_u + g*(eps_c-eps_u); x0 = (x - s1*eps)/sa; den = c_out*x0 + c_skip*x; x' = sap*den + s1p*noise */
+int fie_cfg_lcm_step(const void* eps_u, const void* eps_c, int ld_e, const void* x, const void* noise, void* x_out,
+                     long long count_px, float guidance, float sqrt_a, float sqrt_1ma, float c_skip, float c_out,
+                     float sqrt_a_prev, float sqrt_1ma_prev, int last, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIE_B200_H */

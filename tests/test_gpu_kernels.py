@@ -1,0 +1,255 @@
+"""GPU: each hand-written kernel (through the C-ABI) against the torch op it replaces, fp32 math on the same
+fp16-rounded inputs.  Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from fast_image_editing_with_generative_models_b200 import ops
+    return ops
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator("cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+# ------------------------------------------------------------------ elementwise / norms
+def test_pre_post_process(cuda_dev):
+    ops = _ops()
+    img = torch.randint(0, 256, (2, 64, 96, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0)).to(cuda_dev)
+    x = ops.preprocess(img, 4, True)
+    ref = (2.0 * (img.float() / 255.0) - 1.0).half()
+    assert torch.equal(x[..., :3], ref) and float(x[..., 3].abs().max()) == 0.0
+    c = ops.preprocess(img, 4, False)
+    assert torch.equal(c[..., :3], (img.float() / 255.0).half())
+    y = _rand((2, 64, 96, 4), cuda_dev, 1).half()
+    out = ops.postprocess(y)
+    ref = ((y[..., :3] / 2 + 0.5).clamp(0, 1).float() * 255).round().to(torch.uint8)
+    assert torch.equal(out, ref)
+
+
+def test_add_silu_upsample(cuda_dev):
+    ops = _ops()
+    a = _rand((2, 16, 16, 64), cuda_dev, 2).half()
+    b = _rand((2, 16, 16, 64), cuda_dev, 3).half()
+    assert torch.equal(ops.add(a, b), (a.float() + b.float()).half())
+    assert rel_err(ops.silu(a), F.silu(a.float())) < 2e-3
+    up = ops.upsample2x(a)
+    ref = F.interpolate(a.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1).half()
+    assert torch.equal(up, ref)
+
+
+def test_sincos(cuda_dev):
+    ops = _ops()
+    from oracle.diffusion_oracle import sincos_embedding
+    vals = [499.0, 259.0, 1024.0, 0.0]
+    out = ops.sincos_embedding(vals, 320, cuda_dev)
+    ref = sincos_embedding(torch.tensor(vals), 320).to(cuda_dev)
+    assert float((out.float() - ref).abs().max()) < 2e-3   # fp16 output of values in [-1,1]
+
+
+@pytest.mark.parametrize("n,hw,c0,c1,silu,eps", [(2, 256, 64, 0, True, 1e-5), (2, 1024, 320, 0, True, 1e-5), (1, 4096, 128, 0, False, 1e-6),
+                                                 (2, 64, 1280, 640, True, 1e-5), (2, 256, 640, 320, True, 1e-5), (1, 300, 512, 0, True, 1e-6)])
+def test_groupnorm(cuda_dev, n, hw, c0, c1, silu, eps):
+    ops = _ops()
+    x0 = (_rand((n, hw, c0), cuda_dev, 4) * 1.5 + 0.3).half()
+    x1 = (_rand((n, hw, c1), cuda_dev, 5) * 0.7 - 0.2).half() if c1 else None
+    c = c0 + c1
+    gamma = _rand((c,), cuda_dev, 6) * 0.1 + 1
+    beta = _rand((c,), cuda_dev, 7) * 0.1
+    out = ops.groupnorm(x0, gamma, beta, eps, silu, 32, x1)
+    xc = torch.cat([x0, x1], dim=-1) if c1 else x0
+    ref = F.group_norm(xc.float().permute(0, 2, 1), 32, gamma, beta, eps)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 1)
+    assert float((out.float() - ref).abs().max()) < 8e-3     # fp16 output rounding of O(1..4) values
+
+
+@pytest.mark.parametrize("rows,c", [(300, 128), (1024, 640), (2048, 1280), (77, 256)])
+def test_layernorm(cuda_dev, rows, c):
+    ops = _ops()
+    x = (_rand((rows, c), cuda_dev, 8) * 2 + 0.5).half()
+    gamma = _rand((c,), cuda_dev, 9) * 0.1 + 1
+    beta = _rand((c,), cuda_dev, 10) * 0.1
+    out = ops.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x.float(), (c,), gamma, beta, 1e-5)
+    assert float((out.float() - ref).abs().max()) < 6e-3
+
+
+def test_softmax_rows(cuda_dev):
+    ops = _ops()
+    s = _rand((100, 1000), cuda_dev, 11) * 5
+    out = ops.softmax_rows(s, 0.3)
+    ref = torch.softmax(s * 0.3, dim=-1)
+    assert float((out.float() - ref).abs().max()) < 1e-3
+
+
+def test_scheduler_kernels(cuda_dev):
+    ops = _ops()
+    from oracle.diffusion_oracle import LCMSchedule, vae_sample
+    sched = LCMSchedule()
+    ts, begin = sched.img2img_timesteps(4, 0.5)
+    mom = _rand((2, 16, 16, 8), cuda_dev, 12).half()
+    xi = _rand((2, 16, 16, 4), cuda_dev, 13).half()
+    nz = _rand((2, 16, 16, 4), cuda_dev, 14).half()
+    sa, s1 = sched.add_noise_coeffs(ts[0])
+    out = ops.vae_sample_add_noise(mom, xi, nz, 0.13025, sa, s1)
+    z0 = vae_sample(mom.permute(0, 3, 1, 2).float(), xi.permute(0, 3, 1, 2).float(), 0.13025)
+    ref = (sa * z0 + s1 * nz.permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1)
+    assert float((out.float() - ref).abs().max()) < 3e-3
+    eps = _rand((4, 16, 16, 32), cuda_dev, 15).half()
+    x = _rand((2, 16, 16, 4), cuda_dev, 16).half()
+    for k in (0, 1):
+        c = sched.step_coeffs(begin + k)
+        got = ops.cfg_lcm_step(eps[:2], eps[2:], x, None if c["last"] else nz, 1.5, c)
+        e = eps[:2, ..., :4].float() + 1.5 * (eps[2:, ..., :4].float() - eps[:2, ..., :4].float())
+        ref = sched.step(e, begin + k, x.float(), nz.float())
+        assert float((got.float() - ref).abs().max()) < 6e-3
+
+
+# ------------------------------------------------------------------ tensor-core GEMM / conv
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (256, 160, 320), (300, 320, 640), (2048, 1280, 1280), (77, 640, 2048), (4096, 1920, 640), (2, 1280, 320)])
+def test_gemm_plain(cuda_dev, m, n, k):
+    ops = _ops()
+    a = _rand((m, k), cuda_dev, 20).half()
+    w = (_rand((n, k), cuda_dev, 21) / math.sqrt(k)).half()
+    bias = _rand((n,), cuda_dev, 22)
+    out = ops.gemm(a, w, col_bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+
+
+def test_gemm_epilogues(cuda_dev):
+    ops = _ops()
+    m, n, k = 512, 640, 640
+    a = _rand((m, k), cuda_dev, 23).half()
+    w = (_rand((n, k), cuda_dev, 24) / math.sqrt(k)).half()
+    bias = _rand((n,), cuda_dev, 25)
+    res = _rand((m, n), cuda_dev, 26).half()
+    rowb = _rand((2, n), cuda_dev, 27)
+    base = a.float() @ w.float().t()
+    out = ops.gemm(a, w, col_bias=bias, residual=res, scale=0.5)
+    assert rel_err(out, (base + bias) * 0.5 + res.float()) < 2e-3
+    out = ops.gemm(a, w, row_bias=rowb, rows_per_group=256, act=ops.ACT_SILU)
+    ref = F.silu(base + rowb.repeat_interleave(256, dim=0))
+    assert rel_err(out, ref) < 2e-3
+    out = ops.gemm(a, w, out_f32=True)
+    assert out.dtype == torch.float32 and rel_err(out, base) < 1e-5
+    mb = _rand((m,), cuda_dev, 28)
+    out = ops.gemm(a, w, m_bias=mb)
+    assert rel_err(out, base + mb[:, None]) < 2e-3
+    # two-source K (virtual concat)
+    a0, a1 = a[:, :384].contiguous(), a[:, 384:].contiguous()
+    out = ops.gemm(a0, w, a1=a1)
+    assert rel_err(out, base) < 2e-3
+    # strided A view (row stride > K) and strided output
+    big = _rand((m, 3 * k), cuda_dev, 29).half()
+    out = ops.gemm(big[:, k:2 * k], w)
+    assert rel_err(out, big[:, k:2 * k].float() @ w.float().t()) < 2e-3
+
+
+@pytest.mark.parametrize("m,c", [(256, 64), (1024, 640), (300, 128)])
+def test_gemm_geglu(cuda_dev, m, c):
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_geglu
+    a = _rand((m, c), cuda_dev, 30).half()
+    w = (_rand((8 * c, c), cuda_dev, 31) / math.sqrt(c)).half()
+    b = _rand((8 * c,), cuda_dev, 32) * 0.5
+    wp, bp = pack_geglu(w, b)
+    out = ops.gemm(a, wp, col_bias=bp, act=ops.ACT_GEGLU)
+    h = a.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * F.gelu(gate)
+    assert out.shape == (m, 4 * c)
+    assert rel_err(out, ref) < 3e-3, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,stride,pad_mode", [
+    (2, 16, 16, 64, 64, 1, 0), (2, 32, 32, 128, 320, 1, 0), (1, 128, 128, 64, 128, 1, 0), (2, 8, 8, 256, 256, 1, 0),
+    (1, 256, 128, 64, 96, 1, 0), (2, 64, 64, 320, 320, 2, 0), (1, 64, 64, 128, 128, 2, 1), (2, 16, 16, 64, 64, 2, 0), (1, 256, 256, 64, 64, 2, 1)])
+def test_conv3x3(cuda_dev, n, h, w, cin, cout, stride, pad_mode):
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
+    x = _rand((n, h, w, cin), cuda_dev, 40).half()
+    wt = (_rand((cout, cin, 3, 3), cuda_dev, 41) / math.sqrt(9 * cin)).half()
+    bias = _rand((cout,), cuda_dev, 42)
+    out = ops.conv3x3(x, pack_conv3x3(wt), stride=stride, pad_mode=pad_mode, col_bias=bias)
+    xn = x.permute(0, 3, 1, 2).float()
+    if stride == 2 and pad_mode == 1:
+        ref = F.conv2d(F.pad(xn, (0, 1, 0, 1)), wt.float(), bias, stride=2, padding=0)
+    else:
+        ref = F.conv2d(xn, wt.float(), bias, stride=stride, padding=1)
+    ref = ref.permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+
+
+def test_conv3x3_small_cout_and_epilogue(cuda_dev):
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
+    n, h, w, cin, cout = 2, 32, 32, 128, 4
+    x = _rand((n, h, w, cin), cuda_dev, 43).half()
+    wt = (_rand((cout, cin, 3, 3), cuda_dev, 44) / math.sqrt(9 * cin)).half()
+    bias = _rand((cout,), cuda_dev, 45)
+    wp = pack_conv3x3(wt, pad_cout_to=32)
+    bp = torch.zeros(32, device=cuda_dev); bp[:cout] = bias
+    out = ops.conv3x3(x, wp, cout_valid=cout, col_bias=bp)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == (n, h, w, cout) and rel_err(out, ref) < 2e-3
+    # time-embedding broadcast + residual
+    cout = 128
+    wt = (_rand((cout, cin, 3, 3), cuda_dev, 46) / math.sqrt(9 * cin)).half()
+    temb = _rand((n, cout), cuda_dev, 47)
+    res = _rand((n, h, w, cout), cuda_dev, 48).half()
+    out = ops.conv3x3(x, pack_conv3x3(wt), row_bias=temb, rows_per_group=h * w, residual=res)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), None, padding=1).permute(0, 2, 3, 1) + temb[:, None, None, :] + res.float()
+    assert rel_err(out, ref) < 2e-3
+
+
+def test_conv3x3_cin4(cuda_dev):
+    ops = _ops()
+    n, h, w, cout = 2, 40, 56, 320
+    x = _rand((n, h, w, 4), cuda_dev, 50).half()
+    wt = _rand((cout, 4, 3, 3), cuda_dev, 51) / 6
+    bias = _rand((cout,), cuda_dev, 52)
+    out = ops.conv3x3_cin4(x, wt.permute(0, 2, 3, 1).contiguous(), bias, cout)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt, bias, padding=1).permute(0, 2, 3, 1)
+    assert rel_err(out, ref) < 2e-3
+    out = ops.conv3x3_cin4(x, wt[:16].permute(0, 2, 3, 1).contiguous(), bias[:16], 16, ld_out=64, act=ops.ACT_SILU)
+    ref = F.silu(F.conv2d(x.permute(0, 3, 1, 2).float(), wt[:16], bias[:16], padding=1)).permute(0, 2, 3, 1)
+    assert rel_err(out[..., :16], ref) < 2e-3 and float(out[..., 16:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("b,heads,nq,nkv", [(1, 1, 128, 128), (2, 2, 256, 256), (2, 10, 1024, 1024), (2, 4, 256, 77), (1, 2, 64, 64), (2, 2, 4096, 4096), (1, 3, 200, 333)])
+def test_attention_d64(cuda_dev, b, heads, nq, nkv):
+    ops = _ops()
+    c = heads * 64
+    q = _rand((b * nq, c), cuda_dev, 60).half()
+    k = _rand((b * nkv, c), cuda_dev, 61).half()
+    v = _rand((b * nkv, c), cuda_dev, 62).half()
+    out = ops.attention_d64(q, k, v, b, heads, nq, nkv)
+    qh = q.float().view(b, nq, heads, 64).transpose(1, 2)
+    kh = k.float().view(b, nkv, heads, 64).transpose(1, 2)
+    vh = v.float().view(b, nkv, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(b * nq, c)
+    err = float((out.float() - ref).abs().max())
+    assert err < 4e-3, err     # P is rounded to fp16 before the PV product
+
+
+def test_attention_fused_qkv_views(cuda_dev):
+    ops = _ops()
+    b, heads, n = 2, 5, 256
+    c = heads * 64
+    qkv = _rand((b * n, 3 * c), cuda_dev, 63).half()
+    out = ops.attention_d64(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], b, heads, n, n)
+    q, k, v = [t.float().reshape(b, n, heads, 64).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+    ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b * n, c)
+    assert float((out.float() - ref).abs().max()) < 4e-3
