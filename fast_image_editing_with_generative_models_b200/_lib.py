@@ -17,7 +17,7 @@ c_void_p, c_int, c_ll, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes
 
 class Epilogue(ctypes.Structure):
     """Mirror of ``fie_epilogue`` (include/fie_b200.h)."""
-    _fields_ = [("col_bias", c_void_p), ("row_bias", c_void_p), ("rows_per_group", c_ll), ("m_bias", c_void_p),
+    _fields_ = [("col_bias", c_void_p), ("row_bias", c_void_p), ("rows_per_group", c_ll), ("ld_row_bias", c_ll), ("m_bias", c_void_p),
                 ("residual", c_void_p), ("ld_res", c_ll), ("scale", c_float), ("act", c_int), ("out_f32", c_int)]
 
 

@@ -27,6 +27,27 @@ __global__ void __launch_bounds__(128) k_conv_cin4(const uint2* __restrict__ x, 
         } else { patch[4 * t] = patch[4 * t + 1] = patch[4 * t + 2] = patch[4 * t + 3] = 0.f; }
     }
     __half* o = out + pix * ld_out;
+    if (ld_out & 7) {   // narrow outputs (e.g. 4 channels): 64-bit stores
+        for (int co = 0; co < ld_out; co += 4) {
+            float acc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float s = 0.f;
+                if (co + j < cout) {
+                    const float* wr = sw + (co + j) * 36;
+                    s = sw[cout * 36 + co + j];
+#pragma unroll
+                    for (int k = 0; k < 36; ++k) s = fmaf(patch[k], wr[k], s);
+                    if (act == FIE_ACT_SILU) s = silu_f(s);
+                }
+                acc[j] = s;
+            }
+            uint2 u; __half2* hh = reinterpret_cast<__half2*>(&u);
+            hh[0] = __floats2half2_rn(acc[0], acc[1]); hh[1] = __floats2half2_rn(acc[2], acc[3]);
+            *reinterpret_cast<uint2*>(o + co) = u;
+        }
+        return;
+    }
     for (int co = 0; co < ld_out; co += 8) {
         float acc[8];
 #pragma unroll
@@ -54,7 +75,7 @@ using namespace fie;
 extern "C" int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float* bias, void* out, int ld_out,
                                     int n, int h, int w, int cout, int act, void* stream) {
     FIE_REQUIRE(x && wgt && out && n > 0 && h > 0 && w > 0 && cout > 0, "fie_conv3x3_cin4_f16: bad args");
-    FIE_REQUIRE(ld_out >= cout && (ld_out % 8) == 0, "fie_conv3x3_cin4_f16: ld_out must be >= cout and a multiple of 8");
+    FIE_REQUIRE(ld_out >= cout && (ld_out % 4) == 0, "fie_conv3x3_cin4_f16: ld_out must be >= cout and a multiple of 4");
     const size_t smem = (size_t)cout * 37 * sizeof(float);
     FIE_REQUIRE(smem <= 96 * 1024, "fie_conv3x3_cin4_f16: cout too large");
     static bool attr = false;

@@ -48,6 +48,7 @@ struct GemmParams {
     const float* col_bias;
     const float* row_bias;
     long long rows_per_group;
+    long long ld_row_bias;
     const float* m_bias;
     const __half* residual;
     long long ld_res;
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
             tc_fence_after();
             const uint32_t tacc = tmem_base + lane_addr + (uint32_t)(buf * block_n);
             const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
-            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.N : nullptr;
+            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
             const int nchunks = (geglu ? half_n : block_n) / 32;
             for (int c = 0; c < nchunks; ++c) {
                 uint32_t r[32];
@@ -312,10 +313,11 @@ static int pick_block_n(long long M, int N, bool geglu) {
 }
 
 static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
-    static const fie_epilogue kDefault = {nullptr, nullptr, 1, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0};
+    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0};
     if (!ep) ep = &kDefault;
     p.D = D; p.ldd = ldd;
     p.col_bias = ep->col_bias; p.row_bias = ep->row_bias; p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+    p.ld_row_bias = ep->ld_row_bias > 0 ? ep->ld_row_bias : N;
     p.m_bias = ep->m_bias; p.residual = (const __half*)ep->residual; p.ld_res = ep->ld_res;
     p.scale = ep->scale; p.act = ep->act; p.out_f32 = ep->out_f32;
     FIE_REQUIRE(p.act >= 0 && p.act <= 2, "epilogue: bad act %d", p.act);

@@ -146,7 +146,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False):
     ep = Epilogue()
-    ep.col_bias = _p(col_bias); ep.row_bias = _p(row_bias); ep.rows_per_group = int(rows_per_group); ep.m_bias = _p(m_bias)
+    ep.col_bias = _p(col_bias); ep.row_bias = _p(row_bias); ep.rows_per_group = int(rows_per_group)
+    ep.ld_row_bias = row_bias.stride(-2) if (row_bias is not None and row_bias.dim() >= 2) else 0
+    ep.m_bias = _p(m_bias)
     ep.residual = _p(residual); ep.ld_res = residual.stride(-2) if residual is not None else 0
     ep.scale = float(scale); ep.act = int(act); ep.out_f32 = int(out_f32)
     return ep

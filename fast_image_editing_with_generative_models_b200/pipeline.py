@@ -1,0 +1,95 @@
+"""The guided img2img edit path on the B200 kernels: the work ``StableDiffusionXLControlNetImg2ImgPipeline.__call__``
+does for the reference at ``src/pipeline.py:261-272`` (order per SURVEY Appendix A.1), batched over images."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .configs import ControlNetConfig, UNetConfig, VAEConfig
+from .engine import VAE, ControlNet, UNet
+from .scheduler import LCMSchedule
+
+Tensor = torch.Tensor
+
+
+@dataclass
+class EditOutput:
+    images: Tensor                      # uint8 [B,H,W,3] on the device
+    edges: Tensor                       # uint8 [B,H,W,3] Canny control image
+    latents: Optional[Tensor] = None    # fp16 [B,h,w,4] final latents (before decode)
+    extras: Optional[Dict] = None
+
+
+class EditEngine:
+    """Owns the packed weights of one (UNet, ControlNet, VAE) triple on one GPU and runs batched edits."""
+
+    def __init__(self, unet_params, unet_cfg: UNetConfig, cn_params, cn_cfg: ControlNetConfig, vae_params, vae_cfg: VAEConfig,
+                 device="cuda", lora=None, lora_scale: float = 1.0):
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("EditEngine runs on CUDA (sm_100a) only; there is no CPU path")
+        with torch.cuda.device(self.dev):
+            self.unet = UNet(unet_params, unet_cfg, self.dev, lora, lora_scale)
+            self.cn = ControlNet(cn_params, cn_cfg, self.dev)
+            self.vae = VAE(vae_params, vae_cfg, self.dev)
+        self.sched = LCMSchedule()
+
+    @torch.no_grad()
+    def edit_batch(self, images_u8: Tensor, prompt_embeds: Tensor, pooled: Tensor, noises: Sequence[Tensor], strength: float = 0.5,
+                   num_inference_steps: int = 4, guidance_scale: float = 1.5, controlnet_conditioning_scale: float = 0.5,
+                   canny_low: int = 100, canny_high: int = 200, return_latents: bool = False, return_extras: bool = False) -> EditOutput:
+        """images_u8: uint8 [B,H,W,3] (CUDA, H and W multiples of 8; 1024 for the reference path).
+        prompt_embeds [2,77,D] / pooled [2,P] (row 0 negative, row 1 positive; shared by the batch) or per image
+        [B,2,77,D] / [B,2,P].  noises: [xi, n, z1, ...] each [B,4,h,w] (reference RNG order)."""
+        dev = self.dev
+        B, H, W, _ = images_u8.shape
+        sched = self.sched
+        timesteps, begin = sched.img2img_timesteps(num_inference_steps, strength)
+        do_cfg = guidance_scale > 1
+        nrow = 2 if do_cfg else 1
+        nz = [n.to(dev, torch.float16).permute(0, 2, 3, 1).contiguous() for n in noises]
+        # ---- Canny control image + conditioning embedding (step-invariant) ----
+        edges3 = ops.canny(images_u8, canny_low, canny_high, out_channels=3)
+        cond_emb = self.cn.cond_embedding(ops.preprocess(edges3, 4, normalize=False))
+        if do_cfg:
+            cond_emb = torch.cat([cond_emb, cond_emb], 0)
+        # ---- VAE encode -> posterior sample -> scale -> add_noise ----
+        moments = self.vae.encode_moments(ops.preprocess(images_u8, 4, normalize=True))
+        sa, s1 = sched.add_noise_coeffs(timesteps[0]) if timesteps else (1.0, 0.0)
+        x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)
+        # ---- prompt conditioning (step-invariant): rows [neg]*B + [pos]*B as diffusers ----
+        pe = prompt_embeds.to(dev, torch.float16)
+        pl = pooled.to(dev, torch.float16)
+        if pe.dim() == 3:
+            pe, pl = pe[None].expand(B, -1, -1, -1), pl[None].expand(B, -1, -1)
+        rows = [0, 1] if do_cfg else [1]
+        ctx = torch.cat([pe[:, r] for r in rows], 0).contiguous()
+        te = torch.cat([pl[:, r] for r in rows], 0).contiguous()
+        time_ids = [float(H), float(W), 0.0, 0.0, float(H), float(W)]
+        nctx = ctx.shape[1]
+        ps_cn = self.cn.prepare_prompt(ctx, te, time_ids)
+        ps_un = self.unet.prepare_prompt(ctx, te, time_ids)
+        # ---- denoising loop ----
+        zi = 2
+        eps_list = []
+        for k, t in enumerate(timesteps):
+            x2 = torch.cat([x] * nrow, 0) if do_cfg else x
+            down, mid = self.cn.forward(x2, float(t), ps_cn, cond_emb, controlnet_conditioning_scale, nctx)
+            eps = self.unet.forward(x2, float(t), ps_un, down, mid, nctx)
+            c = sched.step_coeffs(begin + k)
+            z = None
+            if not c["last"]:
+                z = nz[zi]
+                zi += 1
+            eu, ec = (eps[:B], eps[B:]) if do_cfg else (eps, eps)
+            if return_extras:
+                eps_list.append(eps)
+            x = ops.cfg_lcm_step(eu, ec, x, z, guidance_scale if do_cfg else 1.0, c)
+        # ---- VAE decode (latents / scaling folded into post_quant_conv) + postprocess ----
+        decoded = self.vae.decode(x)
+        images = ops.postprocess(decoded)
+        extras = dict(moments=moments, eps=eps_list, decoded=decoded) if return_extras else None
+        return EditOutput(images=images, edges=edges3, latents=x if (return_latents or return_extras) else None, extras=extras)

@@ -80,8 +80,9 @@ typedef struct {
     /* epilogue: v = acc + col_bias[n] + row_bias[m / rows_per_group][n]  (+ chan_bias[m] if per-row bias)
      *           v = act(v); v *= scale; v += residual[m, n]; store */
     const float* col_bias;   /* [N] or NULL */
-    const float* row_bias;   /* [ceil(M / rows_per_group), N] or NULL (time-embedding broadcast) */
+    const float* row_bias;   /* [ceil(M / rows_per_group), >= N] or NULL (time-embedding broadcast) */
     long long rows_per_group;
+    long long ld_row_bias;   /* row stride of row_bias in elements (0 = N) */
     const float* m_bias;     /* [M] per-output-row bias or NULL (used for transposed projections) */
     const void* residual;    /* fp16 [M, ld_res] or NULL */
     long long ld_res;

@@ -27,349 +27,21 @@ fixtures for this path and diffusers cannot be imported here).  What IS pinned o
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
 import torch
 import torch.nn.functional as F
 
+# Configs and the seeded synthetic-weight recipe are shared with the product package (data only, no kernels).
+from fast_image_editing_with_generative_models_b200.configs import (  # noqa: F401
+    ControlNetConfig, UNetConfig, VAEConfig, controlnet_config, sdxl_unet_config, skip_channels, ssd1b_unet_config,
+    tiny_controlnet_config, tiny_unet_config, tiny_vae_config)
+from fast_image_editing_with_generative_models_b200.synthetic import (  # noqa: F401
+    count_params, make_controlnet_params, make_lora_params, make_unet_params, make_vae_params, shapes_only, to_dtype)
+
 Tensor = torch.Tensor
 Params = Dict[str, Tensor]
-
-# ----------------------------------------------------------------------------------------------
-# Configurations (diffusers config.json equivalents)
-# ----------------------------------------------------------------------------------------------
-
-
-@dataclass
-class UNetConfig:
-    name: str
-    in_channels: int = 4
-    out_channels: int = 4
-    block_out_channels: Sequence[int] = (320, 640, 1280)
-    layers_per_block: int = 2
-    # transformer depth of each attention in each down block ([] = DownBlock2D without attention)
-    down_depths: Sequence[Sequence[int]] = ((), (2, 2), (10, 10))
-    # mid block: depth of its Transformer2D, or None for a single attention-free ResnetBlock2D
-    mid_depth: Optional[int] = 10
-    # up blocks listed in execution order (first = deepest); 3 resnets each
-    up_depths: Sequence[Sequence[int]] = ((10, 10, 10), (2, 2, 2), ())
-    head_dim: int = 64
-    cross_attention_dim: int = 2048
-    norm_groups: int = 32
-    norm_eps: float = 1e-5
-    time_embed_dim: int = 1280
-    addition_time_embed_dim: int = 256
-    projection_class_embeddings_input_dim: int = 2816
-    # synthetic-weight recipe: gain folded into conv_out so std(eps) ~ 1
-    conv_out_gain: float = 1.0
-    seed: int = 0
-
-
-def sdxl_unet_config() -> UNetConfig:
-    return UNetConfig(name="sdxl", seed=11)
-
-
-def ssd1b_unet_config() -> UNetConfig:
-    # segmind/SSD-1B: transformer_layers_per_block [1,[2,2],[4,4]], reverse [[4,4,10],[2,1,1],1],
-    # mid = UNetMidBlock2D(num_layers=0, add_attention=False)
-    return UNetConfig(name="ssd-1b", down_depths=((), (2, 2), (4, 4)), mid_depth=None,
-                      up_depths=((4, 4, 10), (2, 1, 1), ()), seed=12)
-
-
-def tiny_unet_config(name="tiny", mid_depth: Optional[int] = 1) -> UNetConfig:
-    """Small same-topology UNet for CPU-sized parity tests (channels stay multiples of 64)."""
-    return UNetConfig(name=name, block_out_channels=(64, 128, 256), down_depths=((), (1, 1), (2, 1)),
-                      mid_depth=mid_depth, up_depths=((1, 2, 1), (1, 1, 1), ()), cross_attention_dim=128,
-                      time_embed_dim=256, addition_time_embed_dim=32, projection_class_embeddings_input_dim=64 + 6 * 32,
-                      seed=21)
-
-
-@dataclass
-class ControlNetConfig:
-    name: str
-    unet: UNetConfig = field(default_factory=sdxl_unet_config)
-    full: bool = False  # full: CrossAttn blocks (1,2,10)+mid depth 10; small: attention-free, 1-resnet mid
-    cond_channels: Sequence[int] = (16, 32, 96, 256)
-    seed: int = 13
-
-
-def controlnet_config(full: bool = False, base: Optional[UNetConfig] = None) -> ControlNetConfig:
-    base = base or sdxl_unet_config()
-    if full:
-        enc = UNetConfig(name="cn-full", block_out_channels=base.block_out_channels, down_depths=((), (2, 2), (10, 10)),
-                         mid_depth=10, up_depths=(), cross_attention_dim=base.cross_attention_dim,
-                         time_embed_dim=base.time_embed_dim, addition_time_embed_dim=base.addition_time_embed_dim,
-                         projection_class_embeddings_input_dim=base.projection_class_embeddings_input_dim)
-        return ControlNetConfig(name="cn-full", unet=enc, full=True, seed=14)
-    enc = UNetConfig(name="cn-small", block_out_channels=base.block_out_channels, down_depths=((), (), ()),
-                     mid_depth=None, up_depths=(), cross_attention_dim=base.cross_attention_dim,
-                     time_embed_dim=base.time_embed_dim, addition_time_embed_dim=base.addition_time_embed_dim,
-                     projection_class_embeddings_input_dim=base.projection_class_embeddings_input_dim)
-    return ControlNetConfig(name="cn-small", unet=enc, full=False, seed=13)
-
-
-def tiny_controlnet_config(full=False) -> ControlNetConfig:
-    base = tiny_unet_config()
-    enc = UNetConfig(name="cn-tiny", block_out_channels=base.block_out_channels,
-                     down_depths=((), (1, 1), (2, 1)) if full else ((), (), ()), mid_depth=1 if full else None,
-                     up_depths=(), cross_attention_dim=base.cross_attention_dim, time_embed_dim=base.time_embed_dim,
-                     addition_time_embed_dim=base.addition_time_embed_dim,
-                     projection_class_embeddings_input_dim=base.projection_class_embeddings_input_dim)
-    return ControlNetConfig(name="cn-tiny-full" if full else "cn-tiny", unet=enc, full=full,
-                            cond_channels=(16, 32, 96, 256), seed=23)
-
-
-@dataclass
-class VAEConfig:
-    name: str = "sdxl-vae"
-    block_out_channels: Sequence[int] = (128, 256, 512, 512)
-    layers_per_block: int = 2
-    latent_channels: int = 4
-    norm_groups: int = 32
-    norm_eps: float = 1e-6
-    scaling_factor: float = 0.13025
-    conv_out_gain: float = 1.0  # synthetic recipe: decoder conv_out gain so image std ~0.3-0.5
-    seed: int = 15
-
-
-def tiny_vae_config() -> VAEConfig:
-    return VAEConfig(name="tiny-vae", block_out_channels=(64, 64, 128, 128), seed=25)
-
-
-# ----------------------------------------------------------------------------------------------
-# Synthetic weights (torch default init as Model.from_config would give; SURVEY 8(d))
-# ----------------------------------------------------------------------------------------------
-
-
-class _Init:
-    meta = False  # class-level switch: shape-only parameters on the meta device (for counting)
-
-    def __init__(self, seed: int):
-        self.g = torch.Generator("cpu").manual_seed(seed)
-        self.p: Params = {}
-
-    def uniform(self, shape, bound):
-        if _Init.meta:
-            return torch.empty(shape, device="meta")
-        return (torch.rand(shape, generator=self.g, dtype=torch.float32) * 2 - 1) * bound
-
-    def conv(self, name, cin, cout, k):
-        b = 1.0 / math.sqrt(cin * k * k)
-        self.p[name + ".weight"] = self.uniform((cout, cin, k, k), b)
-        self.p[name + ".bias"] = self.uniform((cout,), b)
-
-    def linear(self, name, cin, cout, bias=True):
-        b = 1.0 / math.sqrt(cin)
-        self.p[name + ".weight"] = self.uniform((cout, cin), b)
-        if bias:
-            self.p[name + ".bias"] = self.uniform((cout,), b)
-
-    def norm(self, name, c):
-        # gamma=1, beta=0 is the from_config default; a seeded perturbation exercises the affine path.
-        self.p[name + ".weight"] = 1.0 + self.uniform((c,), 0.1)
-        self.p[name + ".bias"] = self.uniform((c,), 0.1)
-
-
-def _init_resnet(I: _Init, pre, cin, cout, temb_dim):
-    I.norm(pre + ".norm1", cin)
-    I.conv(pre + ".conv1", cin, cout, 3)
-    if temb_dim:
-        I.linear(pre + ".time_emb_proj", temb_dim, cout)
-    I.norm(pre + ".norm2", cout)
-    I.conv(pre + ".conv2", cout, cout, 3)
-    if cin != cout:
-        I.conv(pre + ".conv_shortcut", cin, cout, 1)
-
-
-def _init_transformer(I: _Init, pre, c, depth, ctx_dim):
-    I.norm(pre + ".norm", c)
-    I.linear(pre + ".proj_in", c, c)
-    for k in range(depth):
-        b = f"{pre}.transformer_blocks.{k}"
-        I.norm(b + ".norm1", c)
-        for nm in ("to_q", "to_k", "to_v"):
-            I.linear(f"{b}.attn1.{nm}", c, c, bias=False)
-        I.linear(b + ".attn1.to_out.0", c, c)
-        I.norm(b + ".norm2", c)
-        I.linear(b + ".attn2.to_q", c, c, bias=False)
-        I.linear(b + ".attn2.to_k", ctx_dim, c, bias=False)
-        I.linear(b + ".attn2.to_v", ctx_dim, c, bias=False)
-        I.linear(b + ".attn2.to_out.0", c, c)
-        I.norm(b + ".norm3", c)
-        I.linear(b + ".ff.net.0.proj", c, 8 * c)
-        I.linear(b + ".ff.net.2", 4 * c, c)
-    I.linear(pre + ".proj_out", c, c)
-
-
-def _init_encoder_part(I: _Init, cfg: UNetConfig):
-    ch = cfg.block_out_channels
-    T = cfg.time_embed_dim
-    I.conv("conv_in", cfg.in_channels, ch[0], 3)
-    I.linear("time_embedding.linear_1", ch[0], T)
-    I.linear("time_embedding.linear_2", T, T)
-    I.linear("add_embedding.linear_1", cfg.projection_class_embeddings_input_dim, T)
-    I.linear("add_embedding.linear_2", T, T)
-    cin = ch[0]
-    for i, cout in enumerate(ch):
-        for j in range(cfg.layers_per_block):
-            _init_resnet(I, f"down_blocks.{i}.resnets.{j}", cin, cout, T)
-            cin = cout
-            if len(cfg.down_depths[i]):
-                _init_transformer(I, f"down_blocks.{i}.attentions.{j}", cout, cfg.down_depths[i][j], cfg.cross_attention_dim)
-        if i < len(ch) - 1:
-            I.conv(f"down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
-    c = ch[-1]
-    _init_resnet(I, "mid_block.resnets.0", c, c, T)
-    if cfg.mid_depth is not None:
-        _init_transformer(I, "mid_block.attentions.0", c, cfg.mid_depth, cfg.cross_attention_dim)
-        _init_resnet(I, "mid_block.resnets.1", c, c, T)
-
-
-def skip_channels(cfg: UNetConfig) -> List[int]:
-    ch = cfg.block_out_channels
-    out = [ch[0]]
-    for i, c in enumerate(ch):
-        out += [c] * cfg.layers_per_block
-        if i < len(ch) - 1:
-            out.append(c)
-    return out
-
-
-def make_unet_params(cfg: UNetConfig) -> Params:
-    I = _Init(cfg.seed)
-    _init_encoder_part(I, cfg)
-    ch = cfg.block_out_channels
-    T = cfg.time_embed_dim
-    skips = skip_channels(cfg)
-    rev = list(reversed(ch))
-    prev = ch[-1]
-    for i, cout in enumerate(rev):
-        for j in range(cfg.layers_per_block + 1):
-            sc = skips.pop()
-            _init_resnet(I, f"up_blocks.{i}.resnets.{j}", prev + sc, cout, T)
-            prev = cout
-            if len(cfg.up_depths[i]):
-                _init_transformer(I, f"up_blocks.{i}.attentions.{j}", cout, cfg.up_depths[i][j], cfg.cross_attention_dim)
-        if i < len(rev) - 1:
-            I.conv(f"up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
-    I.norm("conv_norm_out", ch[0])
-    I.conv("conv_out", ch[0], cfg.out_channels, 3)
-    I.p["conv_out.weight"] *= cfg.conv_out_gain
-    I.p["conv_out.bias"] *= cfg.conv_out_gain
-    return I.p
-
-
-def make_controlnet_params(cfg: ControlNetConfig) -> Params:
-    I = _Init(cfg.seed)
-    _init_encoder_part(I, cfg.unet)
-    cc = cfg.cond_channels
-    I.conv("controlnet_cond_embedding.conv_in", 3, cc[0], 3)
-    for i in range(len(cc) - 1):
-        I.conv(f"controlnet_cond_embedding.blocks.{2 * i}", cc[i], cc[i], 3)
-        I.conv(f"controlnet_cond_embedding.blocks.{2 * i + 1}", cc[i], cc[i + 1], 3)
-    # diffusers zero-inits conv_out and the zero-convs; the synthetic recipe uses default init so the
-    # residual path is non-zero (SURVEY 8(d)).
-    I.conv("controlnet_cond_embedding.conv_out", cc[-1], cfg.unet.block_out_channels[0], 3)
-    for i, c in enumerate(skip_channels(cfg.unet)):
-        I.conv(f"controlnet_down_blocks.{i}", c, c, 1)
-    c = cfg.unet.block_out_channels[-1]
-    I.conv("controlnet_mid_block", c, c, 1)
-    return I.p
-
-
-def _init_vae_resnet(I, pre, cin, cout):
-    _init_resnet(I, pre, cin, cout, 0)
-
-
-def _init_vae_attn(I, pre, c):
-    I.norm(pre + ".group_norm", c)
-    for nm in ("to_q", "to_k", "to_v", "to_out.0"):
-        I.linear(f"{pre}.{nm}", c, c)
-
-
-def make_vae_params(cfg: VAEConfig) -> Params:
-    I = _Init(cfg.seed)
-    ch = cfg.block_out_channels
-    L = cfg.latent_channels
-    I.conv("encoder.conv_in", 3, ch[0], 3)
-    cin = ch[0]
-    for i, cout in enumerate(ch):
-        for j in range(cfg.layers_per_block):
-            _init_vae_resnet(I, f"encoder.down_blocks.{i}.resnets.{j}", cin, cout)
-            cin = cout
-        if i < len(ch) - 1:
-            I.conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
-    c = ch[-1]
-    _init_vae_resnet(I, "encoder.mid_block.resnets.0", c, c)
-    _init_vae_attn(I, "encoder.mid_block.attentions.0", c)
-    _init_vae_resnet(I, "encoder.mid_block.resnets.1", c, c)
-    I.norm("encoder.conv_norm_out", c)
-    I.conv("encoder.conv_out", c, 2 * L, 3)
-    I.conv("quant_conv", 2 * L, 2 * L, 1)
-    I.conv("post_quant_conv", L, L, 1)
-    I.conv("decoder.conv_in", L, c, 3)
-    _init_vae_resnet(I, "decoder.mid_block.resnets.0", c, c)
-    _init_vae_attn(I, "decoder.mid_block.attentions.0", c)
-    _init_vae_resnet(I, "decoder.mid_block.resnets.1", c, c)
-    rev = list(reversed(ch))
-    cin = c
-    for i, cout in enumerate(rev):
-        for j in range(cfg.layers_per_block + 1):
-            _init_vae_resnet(I, f"decoder.up_blocks.{i}.resnets.{j}", cin, cout)
-            cin = cout
-        if i < len(rev) - 1:
-            I.conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
-    I.norm("decoder.conv_norm_out", ch[0])
-    I.conv("decoder.conv_out", ch[0], 3, 3)
-    I.p["decoder.conv_out.weight"] *= cfg.conv_out_gain
-    I.p["decoder.conv_out.bias"] *= cfg.conv_out_gain
-    return I.p
-
-
-# ---- LCM-LoRA (peft) -------------------------------------------------------------------------
-
-LORA_TARGET_SUFFIXES = ("to_q", "to_k", "to_v", "to_out.0", "proj_in", "proj_out", "ff.net.0.proj", "ff.net.2",
-                        "conv1", "conv2", "conv_shortcut", "downsamplers.0.conv", "upsamplers.0.conv", "time_emb_proj")
-
-
-def make_lora_params(unet_params: Params, rank: int = 64, seed: int = 16, b_scale: float = 0.02) -> Params:
-    """Synthetic LCM-LoRA (r=64, alpha=64): A default-init, B small non-zero (peft zero-inits B)."""
-    I = _Init(seed)
-    out: Params = {}
-    for k, w in unet_params.items():
-        if not k.endswith(".weight"):
-            continue
-        base = k[: -len(".weight")]
-        if not base.endswith(LORA_TARGET_SUFFIXES) or w.dim() < 2:
-            continue
-        cout, cin = w.shape[0], w.shape[1]
-        if w.dim() == 4:
-            kk = w.shape[2]
-            out[base + ".lora_A.weight"] = I.uniform((rank, cin, kk, kk), 1.0 / math.sqrt(cin * kk * kk))
-            out[base + ".lora_B.weight"] = I.uniform((cout, rank, 1, 1), b_scale / math.sqrt(rank))
-        else:
-            out[base + ".lora_A.weight"] = I.uniform((rank, cin), 1.0 / math.sqrt(cin))
-            out[base + ".lora_B.weight"] = I.uniform((cout, rank), b_scale / math.sqrt(rank))
-    return out
-
-
-class shapes_only:
-    """Context manager: make_*_params() return meta tensors (no memory) — for parameter counting."""
-
-    def __enter__(self):
-        _Init.meta = True
-
-    def __exit__(self, *a):
-        _Init.meta = False
-
-
-def count_params(p: Params) -> int:
-    return sum(v.numel() for v in p.values())
-
-
-def to_dtype(p: Params, dtype, device=None) -> Params:
-    return {k: v.to(device=device, dtype=dtype) for k, v in p.items()}
 
 
 # ----------------------------------------------------------------------------------------------

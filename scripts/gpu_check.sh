@@ -19,5 +19,6 @@ run gemm_epi tests/test_gpu_kernels.py -k "gemm_epilogues"
 run gemm_geglu tests/test_gpu_kernels.py -k "gemm_geglu"
 run conv tests/test_gpu_kernels.py -k "test_conv3x3 and not cin4"
 run attention tests/test_gpu_kernels.py -k "attention"
+run engine tests/test_gpu_engine.py -s
 for extra in "$@"; do run extra tests -k "$extra"; done
 grep -E "^=== .* rc=" gpurun_out/gpu_check.log

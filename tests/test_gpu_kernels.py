@@ -115,7 +115,7 @@ def test_scheduler_kernels(cuda_dev):
 
 
 # ------------------------------------------------------------------ tensor-core GEMM / conv
-@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (256, 160, 320), (300, 320, 640), (2048, 1280, 1280), (77, 640, 2048), (4096, 1920, 640), (2, 1280, 320)])
+@pytest.mark.parametrize("m,n,k", [(128, 64, 64), (256, 160, 320), (300, 320, 640), (2048, 1280, 1280), (77, 640, 2048), (4096, 1920, 640), (2, 1280, 320), (512, 8, 8), (16384, 512, 512)])
 def test_gemm_plain(cuda_dev, m, n, k):
     ops = _ops()
     a = _rand((m, k), cuda_dev, 20).half()
