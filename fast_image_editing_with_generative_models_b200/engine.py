@@ -213,7 +213,7 @@ class _EncoderPart:
         b = ctx.shape[0]
         cfg = self.cfg
         ctx_kv = ops.gemm(ctx.reshape(b * ctx.shape[1], ctx.shape[2]), self.kv_w) if self.kv_w is not None else None
-        tid = ops.sincos_embedding(list(time_ids) * b, cfg.addition_time_embed_dim, ctx.device).view(b, -1)
+        tid = ops.sincos_embedding(list(time_ids), cfg.addition_time_embed_dim, ctx.device).view(1, -1).expand(b, -1).contiguous()
         h = ops.gemm(text_embeds, self.a1[0], a1=tid, col_bias=self.a1[1], act=ops.ACT_SILU)
         aug = ops.gemm(h, self.a2[0], col_bias=self.a2[1])
         return ctx_kv, aug
@@ -221,7 +221,7 @@ class _EncoderPart:
     def time_rows(self, t: float, aug: Tensor) -> Tensor:
         """Per-step: fp32 [B, sum Cout] row biases (time_emb_proj(SiLU(emb)) + conv1.bias) for every resnet."""
         b = aug.shape[0]
-        te = ops.sincos_embedding([t] * b, self.cfg.block_out_channels[0], aug.device)
+        te = ops.sincos_embedding([t], self.cfg.block_out_channels[0], aug.device).expand(b, -1).contiguous()
         h = ops.gemm(te, self.t1[0], col_bias=self.t1[1], act=ops.ACT_SILU)
         emb = ops.gemm(h, self.t2[0], col_bias=self.t2[1], residual=aug)
         return ops.gemm(ops.silu(emb), self.temb_w, col_bias=self.temb_b, out_f32=True)

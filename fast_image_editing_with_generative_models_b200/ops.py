@@ -17,9 +17,46 @@ LAUNCHES = 0  # number of our kernels launched through this module (bench report
 _KERNELS_PER_CALL = {"canny3": 4, "canny1": 3, "groupnorm": 2}
 
 
+PROFILE = None  # set to a list to record (kernel family, algorithmic work, start event, end event) per call
+
+
 def _count(n=1):
     global LAUNCHES
     LAUNCHES += n
+
+
+class _prof:
+    """Context manager: when ops.PROFILE is a list, brackets one C-ABI call with CUDA events on the launch stream."""
+
+    def __init__(self, family: str, work: float, unit: str):
+        self.on = PROFILE is not None
+        if self.on:
+            self.family, self.work, self.unit = family, work, unit
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1))
+        return False
+
+
+def profile_summary():
+    """-> {family: dict(calls, ms, work, unit)} from the recorded events (synchronises)."""
+    torch.cuda.synchronize()
+    out = {}
+    for fam, work, unit, e0, e1 in PROFILE or []:
+        d = out.setdefault(fam, dict(calls=0, ms=0.0, work=0.0, unit=unit))
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+    return out
 
 
 def _stream() -> int:
@@ -48,7 +85,8 @@ def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: i
     ws_bytes = L.fie_canny_workspace_bytes(n, h, w)
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=img_u8.device)
     out = torch.empty((n, h, w, 3) if out_channels == 3 else (n, h, w), dtype=torch.uint8, device=img_u8.device)
-    check(L.fie_canny_u8(_p(img_u8), _p(out), n, h, w, in_ch, out_channels, int(low), int(high), _p(ws), ws_bytes, _stream()), "fie_canny_u8")
+    with _prof("canny", float(n) * h * w * (in_ch + out_channels), "B"):
+        check(L.fie_canny_u8(_p(img_u8), _p(out), n, h, w, in_ch, out_channels, int(low), int(high), _p(ws), ws_bytes, _stream()), "fie_canny_u8")
     _count(4 if in_ch == 3 else 3)
     return out
 
@@ -75,7 +113,8 @@ def postprocess(x: torch.Tensor) -> torch.Tensor:
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req(a, torch.float16, "add"); _req(b, torch.float16, "add")
     out = torch.empty_like(a) if out is None else out
-    check(_lib.lib().fie_add_f16(_p(a), _p(b), _p(out), a.numel(), _stream()), "fie_add_f16")
+    with _prof("add", 6.0 * a.numel(), "B"):
+        check(_lib.lib().fie_add_f16(_p(a), _p(b), _p(out), a.numel(), _stream()), "fie_add_f16")
     _count()
     return out
 
@@ -92,7 +131,8 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     _req(x, torch.float16, "upsample2x")
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
-    check(_lib.lib().fie_upsample2x_f16(_p(x), _p(out), n, h, w, c, _stream()), "fie_upsample2x_f16")
+    with _prof("upsample2x", 2.0 * out.numel() + 2.0 * x.numel(), "B"):
+        check(_lib.lib().fie_upsample2x_f16(_p(x), _p(out), n, h, w, c, _stream()), "fie_upsample2x_f16")
     _count()
     return out
 
@@ -110,7 +150,8 @@ def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
     _req(s, torch.float32, "softmax_rows")
     rows, cols = s.shape
     out = torch.empty((rows, cols), dtype=torch.float16, device=s.device) if out is None else out
-    check(_lib.lib().fie_softmax_rows_f32_to_f16(_p(s), s.stride(0), _p(out), out.stride(0), rows, cols, float(scale), _stream()), "fie_softmax_rows")
+    with _prof("softmax_rows", 6.0 * rows * cols, "B"):
+        check(_lib.lib().fie_softmax_rows_f32_to_f16(_p(s), s.stride(0), _p(out), out.stride(0), rows, cols, float(scale), _stream()), "fie_softmax_rows")
     _count()
     return out
 
@@ -128,8 +169,9 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
         c1 = x1.shape[-1]
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), dtype=torch.float16, device=x0.device)
     stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x0.device)
-    check(_lib.lib().fie_groupnorm_f16(_p(x0), c0, _p(x1), c1, _p(out), n, hw, groups, _p(gamma), _p(beta), float(eps), int(silu),
-                                        _p(stats), _stream()), "fie_groupnorm_f16")
+    with _prof("groupnorm", 4.0 * out.numel(), "B"):
+        check(_lib.lib().fie_groupnorm_f16(_p(x0), c0, _p(x1), c1, _p(out), n, hw, groups, _p(gamma), _p(beta), float(eps), int(silu),
+                                            _p(stats), _stream()), "fie_groupnorm_f16")
     _count(2)
     return out
 
@@ -139,7 +181,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty_like(x)
-    check(_lib.lib().fie_layernorm_f16(_p(x), _p(out), rows, c, _p(gamma), _p(beta), float(eps), _stream()), "fie_layernorm_f16")
+    with _prof("layernorm", 4.0 * out.numel(), "B"):
+        check(_lib.lib().fie_layernorm_f16(_p(x), _p(out), rows, c, _p(gamma), _p(beta), float(eps), _stream()), "fie_layernorm_f16")
     _count()
     return out
 
@@ -175,7 +218,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
         out = torch.empty(tuple(a.shape[:-1]) + (n_out,), dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
     ldd = out.stride(-2) if out.dim() >= 2 else n_out
     ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32)
-    check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")
+    with _prof("gemm", 2.0 * m * n * k, "FLOP"):
+        check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")
     _count()
     return out
 
@@ -191,8 +235,9 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad_mode: int 
     if out is None:
         out = torch.empty((n, h // stride, wd // stride, cv), dtype=torch.float16, device=x.device)
     ep = _epilogue(col_bias, row_bias, rows_per_group, None, residual, scale, act, False)
-    check(_lib.lib().fie_conv3x3_f16(_p(x), _p(w), _p(out), out.stride(-2), n, h, wd, cin, cout, cv, stride, pad_mode, ctypes.byref(ep), _stream()),
-          "fie_conv3x3_f16")
+    with _prof("conv3x3", 2.0 * n * (h // stride) * (wd // stride) * cv * 9 * cin, "FLOP"):
+        check(_lib.lib().fie_conv3x3_f16(_p(x), _p(w), _p(out), out.stride(-2), n, h, wd, cin, cout, cv, stride, pad_mode, ctypes.byref(ep), _stream()),
+              "fie_conv3x3_f16")
     _count()
     return out
 
@@ -204,7 +249,8 @@ def conv3x3_cin4(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
     assert c == 4
     ld = cout if ld_out is None else ld_out
     out = torch.empty((n, h, wd, ld), dtype=torch.float16, device=x.device)
-    check(_lib.lib().fie_conv3x3_cin4_f16(_p(x), _p(w), _p(bias), _p(out), ld, n, h, wd, cout, int(act), _stream()), "fie_conv3x3_cin4_f16")
+    with _prof("conv_cin4", 2.0 * out.numel() + 2.0 * x.numel(), "B"):
+        check(_lib.lib().fie_conv3x3_cin4_f16(_p(x), _p(w), _p(bias), _p(out), ld, n, h, wd, cout, int(act), _stream()), "fie_conv3x3_cin4_f16")
     _count()
     return out
 
@@ -217,8 +263,9 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, hea
             raise _lib.FieError("attention_d64: fp16 CUDA tensors with unit inner stride required")
     if out is None:
         out = torch.empty((b * nq, heads * 64), dtype=torch.float16, device=q.device)
-    check(_lib.lib().fie_attention_d64_f16(_p(q), q.stride(-2), _p(k), k.stride(-2), _p(v), v.stride(-2), _p(out), out.stride(-2),
-                                            b, heads, nq, nkv, float(scale), _stream()), "fie_attention_d64_f16")
+    with _prof("attention", 4.0 * b * heads * nq * nkv * 64, "FLOP"):
+        check(_lib.lib().fie_attention_d64_f16(_p(q), q.stride(-2), _p(k), k.stride(-2), _p(v), v.stride(-2), _p(out), out.stride(-2),
+                                                b, heads, nq, nkv, float(scale), _stream()), "fie_attention_d64_f16")
     _count()
     return out
 

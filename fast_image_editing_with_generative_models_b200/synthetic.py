@@ -25,32 +25,66 @@ Params = Dict[str, Tensor]
 
 
 class _Init:
+    """Collects (name, shape, bound, offset) specs, then materialises them in parallel: tensor i of a model with seed
+    ``s`` is ``offset + U(-bound, bound)`` drawn from its own CPU generator seeded ``s * 1000003 + i`` (order-independent,
+    so generation can use every host core)."""
     meta = False  # class-level switch: shape-only parameters on the meta device (for counting)
 
     def __init__(self, seed: int):
-        self.g = torch.Generator("cpu").manual_seed(seed)
+        self.seed = seed
+        self.specs = []
         self.p: Params = {}
 
+    def _add(self, name, shape, bound, offset=0.0):
+        self.specs.append((name, tuple(shape), float(bound), float(offset)))
+        self.p[name] = None
+
     def uniform(self, shape, bound):
+        """Immediate draw (used by the LoRA recipe)."""
         if _Init.meta:
             return torch.empty(shape, device="meta")
-        return (torch.rand(shape, generator=self.g, dtype=torch.float32) * 2 - 1) * bound
+        g = torch.Generator("cpu").manual_seed(self.seed * 1000003 + len(self.specs) + 500000)
+        self.specs.append(("<anon>", tuple(shape), bound, 0.0))
+        return torch.empty(shape, dtype=torch.float32).uniform_(-bound, bound, generator=g)
 
     def conv(self, name, cin, cout, k):
         b = 1.0 / math.sqrt(cin * k * k)
-        self.p[name + ".weight"] = self.uniform((cout, cin, k, k), b)
-        self.p[name + ".bias"] = self.uniform((cout,), b)
+        self._add(name + ".weight", (cout, cin, k, k), b)
+        self._add(name + ".bias", (cout,), b)
 
     def linear(self, name, cin, cout, bias=True):
         b = 1.0 / math.sqrt(cin)
-        self.p[name + ".weight"] = self.uniform((cout, cin), b)
+        self._add(name + ".weight", (cout, cin), b)
         if bias:
-            self.p[name + ".bias"] = self.uniform((cout,), b)
+            self._add(name + ".bias", (cout,), b)
 
     def norm(self, name, c):
         # gamma=1, beta=0 is the from_config default; a seeded perturbation exercises the affine path.
-        self.p[name + ".weight"] = 1.0 + self.uniform((c,), 0.1)
-        self.p[name + ".bias"] = self.uniform((c,), 0.1)
+        self._add(name + ".weight", (c,), 0.1, 1.0)
+        self._add(name + ".bias", (c,), 0.1)
+
+    def finish(self) -> Params:
+        if _Init.meta:
+            for name, shape, _, _ in self.specs:
+                if name != "<anon>":
+                    self.p[name] = torch.empty(shape, device="meta")
+            return self.p
+
+        def make(item):
+            i, (name, shape, bound, offset) = item
+            g = torch.Generator("cpu").manual_seed(self.seed * 1000003 + i)
+            t = torch.empty(shape, dtype=torch.float32).uniform_(-bound, bound, generator=g)
+            if offset:
+                t += offset
+            return name, t
+
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        items = [(i, sp) for i, sp in enumerate(self.specs) if sp[0] != "<anon>"]
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
+            for name, t in ex.map(make, items):
+                self.p[name] = t
+        return self.p
 
 
 def _init_resnet(I: _Init, pre, cin, cout, temb_dim):
@@ -127,6 +161,7 @@ def make_unet_params(cfg: UNetConfig) -> Params:
             I.conv(f"up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
     I.norm("conv_norm_out", ch[0])
     I.conv("conv_out", ch[0], cfg.out_channels, 3)
+    I.finish()
     I.p["conv_out.weight"] *= cfg.conv_out_gain
     I.p["conv_out.bias"] *= cfg.conv_out_gain
     return I.p
@@ -147,7 +182,7 @@ def make_controlnet_params(cfg: ControlNetConfig) -> Params:
         I.conv(f"controlnet_down_blocks.{i}", c, c, 1)
     c = cfg.unet.block_out_channels[-1]
     I.conv("controlnet_mid_block", c, c, 1)
-    return I.p
+    return I.finish()
 
 
 def _init_vae_resnet(I, pre, cin, cout):
@@ -194,6 +229,7 @@ def make_vae_params(cfg: VAEConfig) -> Params:
             I.conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
     I.norm("decoder.conv_norm_out", ch[0])
     I.conv("decoder.conv_out", ch[0], 3, 3)
+    I.finish()
     I.p["decoder.conv_out.weight"] *= cfg.conv_out_gain
     I.p["decoder.conv_out.bias"] *= cfg.conv_out_gain
     return I.p

@@ -1,0 +1,167 @@
+"""Batch editing over a PIE-Bench-style mapping file — same flags and per-image semantics as the reference
+``run_batch.py:44-290`` (filters, ``--skip_existing``, per-image try/except that counts failures and continues),
+on the B200-native engine.
+
+    python run_batch.py --num_images 50 --editing_types 0 1 2
+    torchrun --nproc-per-node 8 run_batch.py ...        # sharded sweep: rank r edits entries[r::world]
+
+Additions over the reference: ``--strength`` and multi-GPU sharding via the torchrun environment.
+"""
+import argparse
+import json
+import os
+import time
+
+from PIL import Image
+
+from fast_image_editing_with_generative_models_b200 import sweep
+from src.pipeline import FastEditor
+
+
+def load_mapping_file(mapping_path):
+    with open(mapping_path, "r") as f:
+        return json.load(f)
+
+
+def safe_join(base_dir, user_path):
+    """Join paths refusing absolute paths and directory traversal (ValueError), as the reference does."""
+    user_path = os.path.normpath(user_path)
+    if os.path.isabs(user_path) or user_path.startswith(".."):
+        raise ValueError(f"Invalid path: {user_path}")
+    full_path = os.path.abspath(os.path.join(base_dir, user_path))
+    if not full_path.startswith(os.path.abspath(base_dir)):
+        raise ValueError(f"Path traversal detected: {user_path}")
+    return full_path
+
+
+def build_parser():
+    p = argparse.ArgumentParser(description="Batch image editing on PIE-Bench")
+    p.add_argument("--mapping_file", type=str, default="data/PIE-Bench_v1/mapping_file.json")
+    p.add_argument("--source_dir", type=str, default="data/PIE-Bench_v1/annotation_images")
+    p.add_argument("--output_dir", type=str, default="outputs")
+    p.add_argument("--model", type=str, default="sdxl", choices=["sdxl", "ssd-1b"])
+    p.add_argument("--num_images", type=int, default=None)
+    p.add_argument("--editing_types", nargs="+", type=str, default=None)
+    p.add_argument("--image_ids", nargs="+", type=str, default=None)
+    p.add_argument("--steps", type=int, default=4)
+    p.add_argument("--guidance", type=float, default=1.5)
+    p.add_argument("--control_scale", type=float, default=0.5)
+    p.add_argument("--canny_low", type=int, default=100)
+    p.add_argument("--canny_high", type=int, default=200)
+    p.add_argument("--seed", type=int, default=None)
+    p.add_argument("--strength", type=float, default=0.80, help="img2img strength (extension; reference default 0.8)")
+    p.add_argument("--negative_prompt", type=str, default="")
+    p.add_argument("--no_cpu_offload", action="store_true")
+    p.add_argument("--quality_mode", action="store_true")
+    p.add_argument("--full_precision", action="store_true")
+    p.add_argument("--full_controlnet", action="store_true")
+    p.add_argument("--skip_existing", action="store_true")
+    p.add_argument("--save_comparisons", action="store_true")
+    return p
+
+
+def select_entries(mapping, args):
+    """The reference's filtering rules (``run_batch.py:117-140``)."""
+    if args.image_ids:
+        return [(i, mapping[i]) for i in args.image_ids if i in mapping]
+    if args.editing_types:
+        sel = [(i, e) for i, e in mapping.items() if e.get("editing_type_id") in args.editing_types]
+    else:
+        sel = list(mapping.items())
+    if args.num_images and args.num_images < len(sel):
+        sel = sel[: args.num_images]
+    return sel
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.quality_mode:
+        args.full_precision = args.full_controlnet = args.no_cpu_offload = True
+    rank, world, local = sweep.init_distributed()
+    say = print if rank == 0 else (lambda *a, **k: None)
+    model_suffix = f"{args.model}_{'fp32' if args.full_precision else 'fp16'}"
+    edited_dir = os.path.join(args.output_dir, "batch", "edited", model_suffix)
+    comparisons_dir = os.path.join(args.output_dir, "batch", "comparisons", model_suffix)
+    os.makedirs(edited_dir, exist_ok=True)
+    say(f"\n[1/3] Loading mapping file from {args.mapping_file}")
+    mapping = load_mapping_file(args.mapping_file)
+    selected = select_entries(mapping, args)
+    say(f"[2/3] Selected {len(selected)} images; world size {world}")
+    if not selected:
+        say("\n      No images selected. Exiting.")
+        return
+    mine = sweep.shard(selected, rank, world)
+    say(f"\n[3/3] Initializing FastEditor ({model_suffix})...")
+    device = f"cuda:{local}" if world > 1 else "cuda"
+    editor = FastEditor(model_name=args.model, device=device, enable_cpu_offload=not args.no_cpu_offload,
+                        use_full_precision=args.full_precision, use_full_controlnet=args.full_controlnet, verbose=rank == 0)
+    if hasattr(editor, "pipe"):
+        editor.pipe.set_progress_bar_config(disable=True)
+    processed = skipped = failed = 0
+    total_time = 0.0
+    try:
+        from tqdm import tqdm
+        it = tqdm(mine, desc=f"Editing[{rank}]", disable=rank != 0)
+    except ImportError:
+        it = mine
+    for image_id, entry in it:
+        try:
+            source_filename = entry["image_path"]
+            source_path = safe_join(args.source_dir, source_filename)
+            output_path = os.path.join(edited_dir, source_filename)
+            if args.skip_existing and os.path.exists(output_path):
+                skipped += 1
+                continue
+            if not os.path.exists(source_path):
+                failed += 1
+                continue
+            os.makedirs(os.path.dirname(output_path), exist_ok=True)
+            source_img = Image.open(source_path).convert("RGB")
+            editing_prompt = entry.get("editing_prompt", "")
+            if not editing_prompt:
+                failed += 1
+                continue
+            t0 = time.time()
+            edited = editor.edit(image=source_img, prompt=editing_prompt, negative_prompt=args.negative_prompt, strength=args.strength,
+                                 num_inference_steps=args.steps, guidance_scale=args.guidance, controlnet_conditioning_scale=args.control_scale,
+                                 canny_low_threshold=args.canny_low, canny_high_threshold=args.canny_high, seed=args.seed)
+            total_time += time.time() - t0
+            edited.save(output_path)
+            processed += 1
+            if args.save_comparisons:
+                from run_single_image import _save_plot
+                cp = os.path.join(comparisons_dir, source_filename.replace(".jpg", ".png"))
+                os.makedirs(os.path.dirname(cp), exist_ok=True)
+                _save_plot(source_img, edited, f"Edited ({args.model.upper()})\n\"{editing_prompt[:60]}\"", cp)
+            if processed % 10 == 0:
+                editor.clear_memory()
+        except FileNotFoundError as e:
+            print(f"\n      File not found for {image_id}: {e}")
+            failed += 1
+        except ValueError as e:
+            print(f"\n      Invalid path for {image_id}: {e}")
+            failed += 1
+        except Exception as e:  # per-image isolation, as the reference
+            print(f"\n      Error processing {image_id} ({type(e).__name__}): {e}")
+            failed += 1
+    import torch
+    dev = torch.device(device)
+    processed_all = int(sweep.sum_over_ranks(processed, dev))
+    skipped_all = int(sweep.sum_over_ranks(skipped, dev))
+    failed_all = int(sweep.sum_over_ranks(failed, dev))
+    time_all = sweep.sum_over_ranks(total_time, dev)
+    wall = sweep.max_over_ranks(total_time, dev)
+    say("\n" + "=" * 60 + "\nBATCH PROCESSING SUMMARY\n" + "=" * 60)
+    say(f"\nProcessed:  {processed_all} images\nSkipped:    {skipped_all} images\nFailed:     {failed_all} images")
+    if processed_all > 0:
+        say(f"\nAverage time per image: {time_all / processed_all:.2f}s")
+        say(f"Total time: {wall:.2f}s ({wall / 60:.1f} minutes) on {world} GPU(s)")
+    else:
+        say("\nWARNING: No images were successfully processed!")
+    say(f"\nOutputs saved to:\n  - Edited images: {edited_dir}")
+    editor.clear_memory()
+    say("\nDone!")
+
+
+if __name__ == "__main__":
+    main()
