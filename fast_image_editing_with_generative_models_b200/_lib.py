@@ -38,6 +38,7 @@ SIGNATURES = {
     "fie_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
     "fie_layernorm_f16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "fie_geglu_block_n": (c_int, [c_int]),
+    "fie_tune_gemm": (None, [c_int, c_int]),
     "fie_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv3x3_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv3x3_cin4_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

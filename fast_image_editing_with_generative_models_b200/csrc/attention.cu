@@ -2,21 +2,27 @@
 // Replaces F.scaled_dot_product_attention (AttnProcessor2_0) for the UNet / ControlNet self- and cross-attention
 // of the reference's edit path (diffusers call at reference src/pipeline.py:261-272).  No mask, scale 1/sqrt(d).
 //
-// One CTA = one 128-row Q tile of one (batch, head); it streams 128-row K/V tiles through a 2-stage TMA ring.
-//   S = Q K^T      tcgen05.mma 128x128x64 -> TMEM columns [0,128)
-//   softmax        4 warps, one thread per row (TMEM lane == row, so no cross-thread reductions); online max / sum;
-//                  P is written as fp16 into shared memory in the K-major 128B-swizzled operand layout
-//   O_j = P V_j    tcgen05.mma 128x64x128 (V consumed MN-major straight from its row-major TMA tile) -> TMEM [128,192)
-//   the running output is kept in registers and rescaled by exp2(m_old - m_new) per tile.
-// Two CTAs fit per SM (112 KiB smem, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMAs.
-// Warp roles (192 threads): w0-3 softmax/epilogue, w4 TMA producer, w5 MMA issuer + TMEM allocator.
+// One CTA = TWO 128-row Q tiles of one (batch, head) sharing every K/V tile (3-stage TMA ring of 128-row tiles).
+// Per Q tile q and K/V tile j:
+//   S_q = Q_q K_j^T   tcgen05.mma 128x128x64 -> TMEM columns [128q, 128q+128)
+//   softmax           one warpgroup per Q tile, one thread per row (TMEM lane == row: no cross-thread reductions),
+//                     online max / sum with 4-way ILP; P_q written as fp16 into shared memory in the K-major
+//                     128B-swizzled operand layout
+//   O_qj = P_q V_j    tcgen05.mma 128x64x128 (V consumed MN-major straight from its row-major TMA tile) -> TMEM
+//   O_q accumulates in TMEM across K/V tiles; it is rescaled by exp2(m_old - m_new) (tcgen05.ld/st) only when the
+//   running row max of a warp moved.
+// The two warpgroups ping-pong: while one does its softmax the tensor core serves the other (FlashAttention-4 style).
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 softmax(q=0), w8-11 softmax(q=1).
 #include "tc_common.cuh"
 
 namespace fie {
 
-constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64;
-constexpr int ATT_TILE_BYTES = 128 * 64 * 2;              // 16 KiB (Q, K or V tile)
-constexpr int ATT_SMEM = ATT_TILE_BYTES * 5 + 32768 + 128;    // Q + 2x(K,V) + P + barriers (2 CTAs / SM)
+constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64, ATT_QT = 2, ATT_KV_STAGES = 3;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                                   // 16 KiB (Q, K or V tile)
+constexpr int ATT_OFF_KV = ATT_QT * ATT_TILE_BYTES;                            // after Q0, Q1
+constexpr int ATT_OFF_P = ATT_OFF_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;     // after the K/V ring
+constexpr int ATT_OFF_BAR = ATT_OFF_P + ATT_QT * 32768;
+constexpr int ATT_SMEM = ATT_OFF_BAR + 256;
 
 struct AttnParams {
     CUtensorMap q_map, k_map, v_map;
@@ -26,176 +32,212 @@ struct AttnParams {
     float scale_log2;
 };
 
-__global__ void __launch_bounds__(192, 2) k_attention_d64(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];     // no static smem in this kernel: base is 1024-aligned
     uint8_t* sQ = smem;
-    uint8_t* sKV = smem + ATT_TILE_BYTES;                 // stage s: K at s*32K, V at s*32K + 16K
-    uint8_t* sP = smem + ATT_TILE_BYTES * 5;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_TILE_BYTES * 5 + 32768);
-    uint64_t& q_full = bars[0]; uint64_t* kv_full = bars + 1; uint64_t* kv_empty = bars + 3;
-    uint64_t& s_full = bars[5]; uint64_t& p_full = bars[6]; uint64_t& o_full = bars[7];
-    uint32_t& tmem_slot = *reinterpret_cast<uint32_t*>(bars + 8);
+    uint8_t* sKV = smem + ATT_OFF_KV;                     // stage s: K at s*32K, V at s*32K + 16K
+    uint8_t* sP = smem + ATT_OFF_P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
+    uint64_t* q_full = bars;                 // [1]
+    uint64_t* kv_full = bars + 1;            // [3]
+    uint64_t* kv_empty = bars + 4;           // [3]
+    uint64_t* s_full = bars + 7;             // [2]
+    uint64_t* p_full = bars + 9;             // [2]
+    uint64_t* o_full = bars + 11;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("fie: attention smem base misaligned\n"); __trap(); }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+    const int qt0 = blockIdx.x * ATT_QT, head = blockIdx.y, b = blockIdx.z;
     const int n_tiles = (p.nkv + ATT_BN - 1) / ATT_BN;
 
     if (threadIdx.x == 0) {
-        mbar_init(&q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(&s_full, 1); mbar_init(&p_full, 128); mbar_init(&o_full, 1);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < ATT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int q = 0; q < ATT_QT; ++q) { mbar_init(&s_full[q], 1); mbar_init(&p_full[q], 128); mbar_init(&o_full[q], 1); }
         mbar_fence_init();
     }
-    if (warp == 4 && lane == 0) { tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.v_map); }
-    if (warp == 5) tmem_alloc(&tmem_slot, 256);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.v_map); }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;
-    const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+    const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(&q_full, ATT_TILE_BYTES);
-            tma_load_3d(&p.q_map, &q_full, sQ, head * ATT_D, qt * ATT_BM, b);
+            mbar_arrive_expect_tx(q_full, ATT_QT * ATT_TILE_BYTES);
+            for (int q = 0; q < ATT_QT; ++q) tma_load_3d(&p.q_map, q_full, sQ + q * ATT_TILE_BYTES, head * ATT_D, (qt0 + q) * ATT_BM, b);
+            int s = 0; uint32_t ph = 0;
             for (int j = 0; j < n_tiles; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_empty[s], (uint32_t)(((j >> 1) & 1) ^ 1));
+                mbar_wait(&kv_empty[s], ph ^ 1);
                 mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
                 tma_load_3d(&p.k_map, &kv_full[s], sKV + s * 2 * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, b);
                 tma_load_3d(&p.v_map, &kv_full[s], sKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, b);
+                if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 1) {
         const uint32_t idesc_qk = umma_idesc_f16(ATT_BM, ATT_BN, 0, 0);
         const uint32_t idesc_pv = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);   // B (= V) is MN-major
-        const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-        auto issue_qk = [&](int j) {
-            const int s = j & 1;
-            mbar_wait(&kv_full[s], (uint32_t)((j >> 1) & 1));
-            tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
+        auto issue_qk = [&](int q, int s) {        // S_q = Q_q K_s^T
             if (lane == 0) {
-                const uint64_t ad = umma_desc_sw128(aQ), bd = umma_desc_sw128(smem_u32(sKV + s * 2 * ATT_TILE_BYTES));
+                const uint64_t ad = umma_desc_sw128(aQ + q * ATT_TILE_BYTES), bd = umma_desc_sw128(aKV + s * 2 * ATT_TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k) umma_f16(tmem_S, ad + 2 * k, bd + 2 * k, idesc_qk, k ? 1u : 0u);
-                umma_commit(&s_full);
+                for (int k = 0; k < ATT_D / 16; ++k) umma_f16(tmem + q * 128, ad + 2 * k, bd + 2 * k, idesc_qk, k ? 1u : 0u);
+                umma_commit(&s_full[q]);
             }
             __syncwarp();
         };
-        mbar_wait(&q_full, 0);
-        issue_qk(0);
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        int s = 0; uint32_t ph = 0;                 // stage / phase of tile j
         for (int j = 0; j < n_tiles; ++j) {
-            const int s = j & 1;
-            mbar_wait(&p_full, (uint32_t)(j & 1));
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t aV = smem_u32(sKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
+            int sn = s + 1; uint32_t phn = ph; if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
+            for (int q = 0; q < ATT_QT; ++q) {
+                mbar_wait(&p_full[q], (uint32_t)(j & 1));
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t aV = aKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
 #pragma unroll
-                for (int k = 0; k < ATT_BN / 16; ++k) {
-                    const uint64_t ad = umma_desc_sw128(aP + (k >> 2) * 16384 + (k & 3) * 32);
-                    const uint64_t bd = umma_desc_sw128(aV + k * 2048, 1024, 1024);
-                    umma_f16(tmem_O, ad, bd, idesc_pv, k ? 1u : 0u);
+                    for (int k = 0; k < ATT_BN / 16; ++k) {
+                        const uint64_t ad = umma_desc_sw128(aP + q * 32768 + (k >> 2) * 16384 + (k & 3) * 32);
+                        const uint64_t bd = umma_desc_sw128(aV + k * 2048, 1024, 1024);
+                        umma_f16(tmem + 256 + q * 64, ad, bd, idesc_pv, (j | k) ? 1u : 0u);   // O accumulates in TMEM across K/V tiles
+                    }
+                    umma_commit(&o_full[q]);
+                    if (q == ATT_QT - 1) umma_commit(&kv_empty[s]);
                 }
-                umma_commit(&kv_empty[s]);
-                umma_commit(&o_full);
+                __syncwarp();
+                if (j + 1 < n_tiles) {
+                    if (q == 0) { mbar_wait(&kv_full[sn], phn); tc_fence_after(); }
+                    issue_qk(q, sn);
+                }
             }
-            __syncwarp();
-            if (j + 1 < n_tiles) issue_qk(j + 1);
+            s = sn; ph = phn;
         }
-    } else {
-        // ===================== softmax / epilogue: thread = row =====================
-        const int row = warp * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        float o_acc[ATT_D];
-#pragma unroll
-        for (int i = 0; i < ATT_D; ++i) o_acc[i] = 0.f;
+    } else if (warp >= 4) {
+        // ===================== softmax / epilogue: warpgroup = Q tile, thread = row =====================
+        const int q = (warp - 4) >> 2;
+        const int wq = warp & 3;                          // TMEM lane quadrant of this warp
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr;
         float m_run = -INFINITY, l_run = 0.f;
         const float sl2 = p.scale_log2;
-        uint8_t* prow = sP + row * 128;
+        uint8_t* prow = sP + q * 32768 + row * 128;
         const int sw = row & 7;
-        for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(&s_full, (uint32_t)(j & 1));
-            tc_fence_after();
-            const int kv_left = p.nkv - j * ATT_BN;     // valid columns in this tile
-            float mx = m_run;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_addr + c * 32, r);
-                tmem_ld_wait();
+        // exp2 of one 64-column half -> fp16 -> swizzled smem; returns the row sum of the half
+        auto exp_store = [&](const uint32_t (&r)[64], int hf, float mneg, int kv_left, bool full_tile) -> float {
+            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+            uint8_t* base = prow + hf * 16384;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) if (c * 32 + i < kv_left) mx = fmaxf(mx, __uint_as_float(r[i]));
-            }
-            const float alpha = exp2f((m_run - mx) * sl2);
-            m_run = mx;
-            if (j > 0) {
-                mbar_wait(&o_full, (uint32_t)((j - 1) & 1));
-                tc_fence_after();
+            for (int u = 0; u < 8; ++u) {                       // 8 units of 8 columns (16 bytes of fp16)
+                uint32_t pk[4];
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_O + lane_addr + c * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(r[i])) * alpha;
-                }
-            }
-            const float mneg = -mx * sl2;
-            float psum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_addr + c * 32, r);
-                tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0 = (c * 32 + 2 * i < kv_left) ? exp2f(fmaf(__uint_as_float(r[2 * i]), sl2, mneg)) : 0.f;
-                    float p1 = (c * 32 + 2 * i + 1 < kv_left) ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), sl2, mneg)) : 0.f;
-                    psum += p0 + p1;
+                for (int i = 0; i < 4; ++i) {
+                    const int c = u * 8 + 2 * i;
+                    float p0 = ex2_approx(fmaf(__uint_as_float(r[c]), sl2, mneg));
+                    float p1 = ex2_approx(fmaf(__uint_as_float(r[c + 1]), sl2, mneg));
+                    if (!full_tile) { if (hf * 64 + c >= kv_left) p0 = 0.f; if (hf * 64 + c + 1 >= kv_left) p1 = 0.f; }
+                    if (i & 1) { ps2 += p0; ps3 += p1; } else { ps0 += p0; ps1 += p1; }
                     __half2 h = __floats2half2_rn(p0, p1);
                     pk[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                uint8_t* base = prow + (c >> 1) * 16384;
+                *reinterpret_cast<uint4*>(base + ((u ^ sw) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            return (ps0 + ps1) + (ps2 + ps3);
+        };
+        auto half_max = [&](const uint32_t (&r)[64], int hf, int kv_left, bool full_tile) -> float {
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            if (full_tile) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int unit = ((c & 1) * 4 + u) ^ sw;
-                    *reinterpret_cast<uint4*>(base + unit * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                for (int i = 0; i < 64; i += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
                 }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) if (hf * 64 + i < kv_left) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+            }
+            return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        };
+        for (int j = 0; j < n_tiles; ++j) {
+            mbar_wait(&s_full[q], (uint32_t)(j & 1));
+            tc_fence_after();
+            const int kv_left = p.nkv - j * ATT_BN;     // valid columns in this tile
+            const bool full_tile = kv_left >= ATT_BN;
+            float mx;
+            {
+                uint32_t ra[64];
+                tmem_ld_32x64(tS, ra);
+                tmem_ld_wait();
+                mx = fmaxf(m_run, half_max(ra, 0, kv_left, full_tile));
+            }
+            uint32_t rb[64];
+            tmem_ld_32x64(tS + 64, rb);
+            tmem_ld_wait();
+            mx = fmaxf(mx, half_max(rb, 1, kv_left, full_tile));
+            const float alpha = ex2_approx((m_run - mx) * sl2);      // first tile: exp2(-inf) = 0
+            m_run = mx;
+            if (j > 0) {
+                // P_q and O_q are free once PV(q, j-1) has completed; O_q lives in TMEM and is rescaled only when the
+                // running max of some row of this warp moved (rare after the first few tiles)
+                mbar_wait(&o_full[q], (uint32_t)((j - 1) & 1));
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                    uint32_t ro[64];
+                    tmem_ld_32x64(tO, ro);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                    tmem_st_32x64(tO, ro);
+                    tmem_st_wait();
+                }
+            }
+            const float mneg = -mx * sl2;
+            float psum = exp_store(rb, 1, mneg, kv_left, full_tile);
+            {
+                uint32_t ra[64];
+                tmem_ld_32x64(tS, ra);
+                tmem_ld_wait();
+                psum += exp_store(ra, 0, mneg, kv_left, full_tile);
             }
             l_run = l_run * alpha + psum;
             fence_proxy_async_smem();
             tc_fence_before();
-            mbar_arrive(&p_full);
+            mbar_arrive(&p_full[q]);
         }
-        mbar_wait(&o_full, (uint32_t)((n_tiles - 1) & 1));
+        mbar_wait(&o_full[q], (uint32_t)((n_tiles - 1) & 1));
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
-        const int qrow = qt * ATT_BM + row;
+        const int qrow = (qt0 + q) * ATT_BM + row;
         __half* orow = p.out + ((long long)b * p.nq + qrow) * p.ldo + head * ATT_D;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tmem_O + lane_addr + c * 32, r);
+        {
+            uint32_t r[64];
+            tmem_ld_32x64(tO, r);
             tmem_ld_wait();
             if (qrow < p.nq) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int e = u * 8 + 2 * i;
-                        hh[i] = __floats2half2_rn((o_acc[c * 32 + e] + __uint_as_float(r[e])) * inv_l, (o_acc[c * 32 + e + 1] + __uint_as_float(r[e + 1])) * inv_l);
+                        hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
                     }
-                    *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = v;
+                    *reinterpret_cast<uint4*>(orow + u * 8) = v;
                 }
             }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 }  // namespace fie
@@ -231,7 +273,7 @@ extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
         attr = true;
     }
-    dim3 grid((nq + ATT_BM - 1) / ATT_BM, heads, b);
-    k_attention_d64<<<grid, 192, ATT_SMEM, (cudaStream_t)stream>>>(p);
+    dim3 grid((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM), heads, b);
+    k_attention_d64<<<grid, 384, ATT_SMEM, (cudaStream_t)stream>>>(p);
     return check_launch("fie_attention_d64_f16");
 }

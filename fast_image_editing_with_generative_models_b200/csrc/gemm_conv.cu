@@ -15,7 +15,7 @@
 // Epilogue: 4 warps read TMEM (tcgen05.ld 32x32b), fuse bias / time-embedding broadcast / SiLU / GEGLU /
 //           scale / residual, and store fp16 (or fp32) rows.
 //
-// Warp roles (256 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 epilogue.
+// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-11 epilogue.
 #include "tc_common.cuh"
 
 namespace fie {
@@ -38,7 +38,10 @@ struct GemmParams {
     long long M;
     int N;            // accumulator columns (B rows)
     int block_n;
-    int num_m_blocks, num_n_blocks;
+    int cg;           // 1 or 2 CTAs per tile
+    int kps;          // 64-wide K blocks per pipeline stage (1 or 2)
+    int dbg;          // debug/tuning: 1 = skip TMA loads, 2 = skip MMA issue, 4 = skip epilogue math/stores
+    int num_m_blocks, num_n_blocks;   // m blocks of 128*cg rows
     int num_stages;
     int tmem_cols;
     // epilogue
@@ -85,7 +88,10 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, in
     }
 }
 
-__global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ GemmParams p) {
+// CG = 1: one CTA per tile (M = 128).  CG = 2: CTA pair (cta_group::2), tile M = 256, each CTA loads half of B.
+// KPS = 64-wide K blocks per pipeline stage (per producer/consumer mbarrier handshake).
+template <int CG, int KPS>
+__global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned by the ABI; round up to 1024 for the 128B swizzle
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -94,9 +100,15 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int block_n = p.block_n;
-    const int stage_bytes = A_STAGE_BYTES + block_n * BLOCK_K * 2;
+    const int b_rows = block_n / CG;                                   // B rows held by this CTA
+    const int b_sub_bytes = b_rows * BLOCK_K * 2;
+    const int stage_bytes = KPS * (A_STAGE_BYTES + b_sub_bytes);
+    const int num_sb = (p.num_kb + KPS - 1) / KPS;                     // pipeline iterations per tile
     const int num_stages = p.num_stages;
-    const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+    const int num_tiles = p.num_m_blocks * p.num_n_blocks;            // m blocks of 128*CG rows
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
@@ -104,12 +116,12 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8 * CG); }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols);
+    if (warp == 2) { if (CG == 2) tmem_alloc_2sm(&tmem_base_slot, (uint32_t)p.tmem_cols); else tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols); }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
@@ -117,9 +129,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-                const long long m0 = (long long)m_blk * BLOCK_M;
+                const long long m0 = ((long long)m_blk * CG + cta_rank) * BLOCK_M;
                 int n0i = 0, h0 = 0, w0 = 0;
                 if (p.mode == 1) {
                     const long long pix = (long long)p.OH * p.OW;
@@ -127,62 +139,86 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
                     const int rem = (int)(m0 % pix);
                     h0 = rem / p.OW; w0 = rem % p.OW;
                 }
-                for (int kb = 0; kb < p.num_kb; ++kb) {
+                for (int sb = 0; sb < num_sb; ++sb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                    if (p.mode == 0) {
-                        if (kb < p.kb_split) tma_load_2d(&p.a_maps[0], &full_bar[stage], sa, kb * BLOCK_K, (int)m0);
-                        else tma_load_2d(&p.a_maps[1], &full_bar[stage], sa, (kb - p.kb_split) * BLOCK_K, (int)m0);
+                    uint8_t* sbase = smem + (size_t)stage * stage_bytes;
+                    if (p.dbg & 1) {
+                        if (CG == 1 || leader) mbar_arrive(&full_bar[stage]);
                     } else {
-                        const int tap = kb / p.kb_per_tap;
-                        const int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-                        tma_load_4d(&p.a_maps[p.tap_map[tap]], &full_bar[stage], sa, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0i);
+                        // the leader's barrier collects the bytes of both CTAs of a pair
+                        if (CG == 1 || leader) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * stage_bytes));
+#pragma unroll
+                        for (int sub = 0; sub < KPS; ++sub) {
+                            const int kb = sb * KPS + sub;                       // kb >= num_kb: coordinates fall outside -> zero fill
+                            uint8_t* sa = sbase + sub * A_STAGE_BYTES;
+                            uint8_t* sbm = sbase + KPS * A_STAGE_BYTES + sub * b_sub_bytes;
+                            if (p.mode == 0) {
+                                const bool first = kb < p.kb_split;
+                                const CUtensorMap* am = first ? &p.a_maps[0] : &p.a_maps[1];
+                                const int kc = (first ? kb : kb - p.kb_split) * BLOCK_K;
+                                if (CG == 1) tma_load_2d(am, &full_bar[stage], sa, kc, (int)m0); else tma_load_2d_2sm(am, &full_bar[stage], sa, kc, (int)m0);
+                            } else {
+                                int tap = kb / p.kb_per_tap;
+                                int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                                if (kb >= p.num_kb) { tap = 0; c0 = p.kb_per_tap * BLOCK_K; }
+                                const CUtensorMap* am = &p.a_maps[p.tap_map[tap]];
+                                if (CG == 1) tma_load_4d(am, &full_bar[stage], sa, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0i);
+                                else tma_load_4d_2sm(am, &full_bar[stage], sa, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0i);
+                            }
+                            if (CG == 1) tma_load_2d(&p.b_map, &full_bar[stage], sbm, kb * BLOCK_K, n_blk * block_n);
+                            else tma_load_2d_2sm(&p.b_map, &full_bar[stage], sbm, kb * BLOCK_K, n_blk * block_n + (int)cta_rank * b_rows);
+                        }
                     }
-                    tma_load_2d(&p.b_map, &full_bar[stage], sb, kb * BLOCK_K, n_blk * block_n);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = umma_idesc_f16(BLOCK_M, block_n);
+    } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (leader CTA of the pair) =====================
+        const uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, block_n);
         int stage = 0; uint32_t phase = 0; int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+            if (CG == 2) mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1); else mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * block_n);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            for (int sb = 0; sb < num_sb; ++sb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+                    const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / 16; ++k)
-                        umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == p.num_kb - 1) umma_commit(&tmem_full[buf]);
+                    for (int sub = 0; sub < KPS; ++sub) {
+                        const uint64_t adesc = umma_desc_sw128(sbase + sub * A_STAGE_BYTES);
+                        const uint64_t bdesc = umma_desc_sw128(sbase + KPS * A_STAGE_BYTES + sub * b_sub_bytes);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / 16; ++k) {
+                            if (p.dbg & 2) continue;
+                            const uint32_t acc = (sb | sub | k) ? 1u : 0u;
+                            if (CG == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                        }
+                    }
+                    if (CG == 2) { umma_commit_2sm(&empty_bar[stage]); if (sb == num_sb - 1) umma_commit_2sm(&tmem_full[buf]); }
+                    else { umma_commit(&empty_bar[stage]); if (sb == num_sb - 1) umma_commit(&tmem_full[buf]); }
                 }
                 __syncwarp();
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ===================== Epilogue =====================
+        // ===================== Epilogue: 8 warps, two per TMEM lane quadrant (even / odd 32-column chunks) =====================
         const int ew = warp & 3;                       // TMEM lane quadrant accessible to this warp
+        const int cpar = (warp - 4) >> 2;              // 0: even chunks, 1: odd chunks
         const int row_in_tile = ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         const bool geglu = p.act == FIE_ACT_GEGLU;
         const int half_n = block_n >> 1;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-            const long long m = (long long)m_blk * BLOCK_M + row_in_tile;
+            const long long m = ((long long)m_blk * CG + cta_rank) * BLOCK_M + row_in_tile;
             const bool row_ok = m < p.M;
             mbar_wait(&tmem_full[buf], acc_phase);
             tc_fence_after();
@@ -190,21 +226,30 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
             const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
             const int nchunks = (geglu ? half_n : block_n) / 32;
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = cpar; c < ((p.dbg & 4) ? 0 : nchunks); c += 2) {
                 uint32_t r[32];
                 float v[32];
                 tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
                 tmem_ld_wait();
                 const int nacc = n_blk * block_n + c * 32;        // accumulator column (B row) of v[0]
+                const bool full = nacc + 32 <= p.N;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + mb;
                 if (p.col_bias) {
+                    if (full) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(p.col_bias + nacc + i);
+                        for (int i = 0; i < 8; ++i) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.col_bias + nacc) + i); v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w; }
+                    } else {
+                        for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(p.col_bias + nacc + i);
+                    }
                 }
                 if (rb) {
+                    if (full && ((p.ld_row_bias | nacc) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.row_bias) & 15) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(rb + nacc + i);
+                        for (int i = 0; i < 8; ++i) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + nacc) + i); v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w; }
+                    } else {
+                        for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(rb + nacc + i);
+                    }
                 }
                 int nout = nacc;
                 if (geglu) {
@@ -247,12 +292,15 @@ __global__ void __launch_bounds__(256, 1) k_gemm_conv(const __grid_constant__ Ge
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+            if (lane == 0) { if (CG == 2) mbar_arrive_remote(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]); }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's MMAs read this CTA's shared memory until the very end
+    if (warp == 2) {
+        tc_fence_after();
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -295,21 +343,34 @@ static int num_sms() {
     return g_num_sms;
 }
 
-static int pick_block_n(long long M, int N, bool geglu) {
-    // GEGLU weights are pre-interleaved per tile by the host, so the tile width may depend on N only.
-    if (geglu) return fie_geglu_block_n(N);
-    const int step = 32;
-    const long long mblocks = (M + BLOCK_M - 1) / BLOCK_M;
+// Tile configuration.  Measured on B200 (scripts/gemm_bench.py, scripts/gemm_dbg.py): the producer/consumer mbarrier
+// handshake costs ~300 ns per pipeline stage regardless of tile width, so the kernel runs 2 K-blocks per stage (KPS = 2)
+// and prefers the CTA-pair form (cta_group::2: 256-row tiles, B split across the pair) with the widest accumulator that
+// does not waste columns: time per tile and K-block ~ (290 + block_n).  Waves are quantised over 74 CTA pairs.
+// fie_tune_gemm() can force the form for experiments.
+static int g_force_cg = -1;
+static int g_force_bn = 0;
+static int g_dbg = 0;
+static int g_force_kps = 0;
+static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out) {
+    if (g_force_cg < 0) { const char* s = getenv("FIE_GEMM_CG"); g_force_cg = s ? atoi(s) : 0; }
     const int sms = num_sms();
-    int best = step; double best_cost = 1e30;
-    for (int bn = step; bn <= 256; bn += step) {
-        const long long tiles = mblocks * ((N + bn - 1) / bn);
-        const long long waves = (tiles + sms - 1) / sms;
-        // per-tile time ~ MMA (prop. to bn) + fixed overhead; smaller tiles re-read A more often
-        const double cost = (double)waves * (bn + 40);
-        if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best)) { best_cost = cost; best = bn; }
+    double best_cost = 1e30; int best_cg = 2, best_bn = 32;
+    for (int cg = 2; cg >= 1; --cg) {
+        if (g_force_cg && cg != g_force_cg) continue;
+        if (!g_force_cg && cg == 1 && M > BLOCK_M) continue;          // single-CTA form only for one-tile-high problems
+        const long long mblocks = (M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
+        const int slots = sms / cg;
+        for (int bn = 32; bn <= 256; bn += 32) {
+            if (geglu && bn != fie_geglu_block_n(N)) continue;   // GEGLU rows are pre-interleaved per tile by the host
+            if (!geglu && g_force_bn && bn != g_force_bn) continue;
+            const long long tiles = mblocks * ((N + bn - 1) / bn);
+            const long long waves = (tiles + slots - 1) / slots;
+            const double cost = (double)waves * (bn + 290.0) * (cg == 1 ? 0.6 : 1.0);
+            if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best_bn)) { best_cost = cost; best_cg = cg; best_bn = bn; }
+        }
     }
-    return best;
+    *cg_out = best_cg; *bn_out = best_bn;
 }
 
 static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
@@ -328,7 +389,12 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
 }
 
 static int launch(GemmParams& p, cudaStream_t stream) {
-    const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+    const int cg = p.cg;
+    p.dbg = g_dbg;
+    int kps = (g_force_kps > 0) ? g_force_kps : (p.num_kb >= 4 ? 2 : 1);
+    if (kps == 2 && SMEM_BUDGET / (2 * (A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2)) < 2) kps = 1;
+    p.kps = kps;
+    const int stage_bytes = kps * (A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2);
     int stages = SMEM_BUDGET / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) stages = 2;
     p.num_stages = stages;
@@ -339,19 +405,37 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     if (tc > 256 && smem < 120 * 1024) smem = 120 * 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_conv<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gemm_conv): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
         attr_set = true;
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks;
-    int grid = tiles < num_sms() ? tiles : num_sms();
-    k_gemm_conv<<<grid, 256, smem, stream>>>(p);
+    if (cg == 1) {
+        const int grid = tiles < num_sms() ? tiles : num_sms();
+        if (kps == 2) k_gemm_conv<1, 2><<<grid, 384, smem, stream>>>(p); else k_gemm_conv<1, 1><<<grid, 384, smem, stream>>>(p);
+    } else {
+        const int slots = num_sms() / 2;
+        const int grid = 2 * (tiles < slots ? tiles : slots);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = (kps == 2) ? cudaLaunchKernelEx(&cfg, k_gemm_conv<2, 2>, p) : cudaLaunchKernelEx(&cfg, k_gemm_conv<2, 1>, p);
+        if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_gemm_conv<2>): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
+    }
     return check_launch("k_gemm_conv");
 }
 
 }  // namespace fie
 
 using namespace fie;
+
+extern "C" void fie_tune_gemm(int force_cg, int force_block_n) { fie::g_force_cg = force_cg & 3; fie::g_force_kps = (force_cg >> 2) & 3; fie::g_dbg = force_cg >> 4; fie::g_force_bn = force_block_n; }
 
 extern "C" int fie_geglu_block_n(int N) { return (N % 256) == 0 ? 256 : ((N % 128) == 0 ? 128 : 64); }
 
@@ -368,8 +452,8 @@ extern "C" int fie_gemm_f16(const void* A, long long lda, const void* A1, long l
     if (rc) return rc;
     const bool geglu = p.act == FIE_ACT_GEGLU;
     p.mode = 0; p.M = M; p.N = N;
-    p.block_n = pick_block_n(M, N, geglu);
-    p.num_m_blocks = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    pick_config(M, N, geglu, &p.cg, &p.block_n);
+    p.num_m_blocks = (int)((M + BLOCK_M * p.cg - 1) / (BLOCK_M * p.cg));
     p.num_n_blocks = (N + p.block_n - 1) / p.block_n;
     p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     p.kb_per_tap = p.num_kb; p.kb_split = p.num_kb;
@@ -388,7 +472,7 @@ extern "C" int fie_gemm_f16(const void* A, long long lda, const void* A1, long l
         p.a_maps[1] = p.a_maps[0];
     }
     p.a_maps[2] = p.a_maps[0]; p.a_maps[3] = p.a_maps[0];
-    dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; strides[0] = (uint64_t)K * 2; box[0] = BLOCK_K; box[1] = (uint32_t)p.block_n;
+    dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; strides[0] = (uint64_t)K * 2; box[0] = BLOCK_K; box[1] = (uint32_t)(p.block_n / p.cg);
     if ((rc = make_tmap_f16(&p.b_map, B, 2, dims, strides, box))) return rc;
     return launch(p, (cudaStream_t)stream);
 }
@@ -417,8 +501,8 @@ extern "C" int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long l
     if (rc) return rc;
     FIE_REQUIRE(p.act != FIE_ACT_GEGLU, "fie_conv3x3_f16: GEGLU epilogue not supported for conv");
     p.mode = 1; p.M = M; p.N = cout; p.OH = OH; p.OW = OW;
-    p.block_n = pick_block_n(M, cout, false);
-    p.num_m_blocks = (int)((M + BLOCK_M - 1) / BLOCK_M);
+    pick_config(M, cout, false, &p.cg, &p.block_n);
+    p.num_m_blocks = (int)((M + BLOCK_M * p.cg - 1) / (BLOCK_M * p.cg));
     p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
     p.kb_per_tap = cin / BLOCK_K;
     p.num_kb = 9 * p.kb_per_tap;
@@ -451,7 +535,7 @@ extern "C" int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long l
     }
     const uint64_t bdims[2] = {(uint64_t)9 * cin, (uint64_t)cout};
     const uint64_t bstr[1] = {(uint64_t)9 * cin * 2};
-    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)p.block_n};
+    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(p.block_n / p.cg)};
     if ((rc = make_tmap_f16(&p.b_map, wgt, 2, bdims, bstr, bbox))) return rc;
     return launch(p, (cudaStream_t)stream);
 }

@@ -95,6 +95,10 @@ typedef struct {
  * [value rows j*h..(j+1)*h | gate rows 4C + j*h ..] with h = fie_geglu_block_n(N)/2 (bias likewise). */
 int fie_geglu_block_n(int N);
 
+/* Tuning / test hook: force the CTA-group form (0 = auto, 1, 2) and the accumulator width (0 = auto) of fie_gemm_f16 /
+ * fie_conv3x3_f16.  Not needed in production. */
+void fie_tune_gemm(int force_cg, int force_block_n);
+
 /* A: fp16 [M, K] with row stride lda (elements, multiple of 8); optional second source A1 supplies
  * K columns [k_split, K) (k_split multiple of 64) — a virtual torch.cat along K.
  * B: fp16 [N, K] row-major (ldb = K).  D: [M, N_out] row stride ldd. */
