@@ -1,71 +1,87 @@
 // 3x3 convolution with Cin <= 4 (NHWC fp16, 4 channels) on CUDA cores: the conv_in layers of the UNet, ControlNet,
-// ControlNet conditioning embedding and VAE (K = 36 is far too small for a tensor-core tile to pay off and the op is
-// bound by the output write).  One thread = one output pixel; the 3x3x4 patch lives in registers, weights in shared
-// memory (broadcast reads), 8 output channels per 128-bit store.
+// ControlNet conditioning embedding and VAE (K = 36 is far too small for a tensor-core tile to pay off; the op is
+// bound by the output write).  A thread computes 8 consecutive output channels of 4 consecutive pixels (128-bit stores);
+// the threads of a pixel are adjacent lanes, so a warp writes whole contiguous output rows.  Weights live in shared
+// memory as [36][cout] so that a warp reads consecutive words (no bank conflicts, broadcast across pixels).
 #include "fie_common.cuh"
 
 namespace fie {
 
-__global__ void __launch_bounds__(128) k_conv_cin4(const uint2* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
-                                                   __half* __restrict__ out, int ld_out, int n, int h, int w, int cout, int act) {
-    extern __shared__ float sw[];   // [cout][36] + bias[cout]
-    for (int i = threadIdx.x; i < cout * 36; i += blockDim.x) sw[i] = wgt[i];
-    for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[cout * 36 + i] = bias ? bias[i] : 0.f;
+constexpr int CIN4_PX = 4;   // consecutive output pixels (along x) per thread: every weight vector read from smem feeds 4 pixels
+
+__global__ void __launch_bounds__(256) k_conv_cin4(const uint2* __restrict__ x, const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                   __half* __restrict__ out, int ld_out, int n, int h, int w, int cout, int act, int groups, int vec) {
+    extern __shared__ float sw[];   // [36][cout_pad] + bias[cout_pad], cout_pad = groups * vec
+    const int cpad = groups * vec;
+    for (int i = threadIdx.x; i < 36 * cpad; i += blockDim.x) { const int k = i / cpad, co = i % cpad; sw[i] = co < cout ? wgt[co * 36 + k] : 0.f; }
+    for (int i = threadIdx.x; i < cpad; i += blockDim.x) sw[36 * cpad + i] = (bias && i < cout) ? bias[i] : 0.f;
     __syncthreads();
-    const long long npix = (long long)n * h * w;
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const int xx = (int)(pix % w); const int yy = (int)((pix / w) % h); const long long img = pix / ((long long)w * h);
-    float patch[36];
+    const int wq = (w + CIN4_PX - 1) / CIN4_PX;                // pixel quads per row
+    const long long nquads = (long long)n * h * wq;
+    const int qpb = blockDim.x / groups;                       // quads per block
+    const int g = threadIdx.x % groups, ql = threadIdx.x / groups;
+    if (ql >= qpb) return;
+    for (long long quad = (long long)blockIdx.x * qpb + ql; quad < nquads; quad += (long long)gridDim.x * qpb) {
+        const int xq0 = (int)(quad % wq) * CIN4_PX; const long long rowi = quad / wq; const int yy = (int)(rowi % h); const long long img = rowi / h;
+        float in[3][CIN4_PX + 2][4];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int y = yy + t / 3 - 1, xq = xx + t % 3 - 1;
-        if (y >= 0 && y < h && xq >= 0 && xq < w) {
-            uint2 u = __ldg(x + (img * h + y) * w + xq);
-            float2 a = __half22float2(*reinterpret_cast<__half2*>(&u.x)), b = __half22float2(*reinterpret_cast<__half2*>(&u.y));
-            patch[4 * t] = a.x; patch[4 * t + 1] = a.y; patch[4 * t + 2] = b.x; patch[4 * t + 3] = b.y;
-        } else { patch[4 * t] = patch[4 * t + 1] = patch[4 * t + 2] = patch[4 * t + 3] = 0.f; }
-    }
-    __half* o = out + pix * ld_out;
-    if (ld_out & 7) {   // narrow outputs (e.g. 4 channels): 64-bit stores
-        for (int co = 0; co < ld_out; co += 4) {
-            float acc[4];
+        for (int ky = 0; ky < 3; ++ky) {
+            const int y = yy + ky - 1;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float s = 0.f;
-                if (co + j < cout) {
-                    const float* wr = sw + (co + j) * 36;
-                    s = sw[cout * 36 + co + j];
-#pragma unroll
-                    for (int k = 0; k < 36; ++k) s = fmaf(patch[k], wr[k], s);
-                    if (act == FIE_ACT_SILU) s = silu_f(s);
+            for (int cx = 0; cx < CIN4_PX + 2; ++cx) {
+                const int xx = xq0 + cx - 1;
+                float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+                if (y >= 0 && y < h && xx >= 0 && xx < w) {
+                    const uint2 u = __ldg(x + (img * h + y) * w + xx);
+                    a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)); b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
                 }
-                acc[j] = s;
+                in[ky][cx][0] = a.x; in[ky][cx][1] = a.y; in[ky][cx][2] = b.x; in[ky][cx][3] = b.y;
             }
-            uint2 u; __half2* hh = reinterpret_cast<__half2*>(&u);
-            hh[0] = __floats2half2_rn(acc[0], acc[1]); hh[1] = __floats2half2_rn(acc[2], acc[3]);
-            *reinterpret_cast<uint2*>(o + co) = u;
         }
-        return;
-    }
-    for (int co = 0; co < ld_out; co += 8) {
-        float acc[8];
+        float acc[CIN4_PX][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float s = 0.f;
-            if (co + j < cout) {
-                const float* wr = sw + (co + j) * 36;
-                s = sw[cout * 36 + co + j];
+        for (int px = 0; px < CIN4_PX; ++px)
 #pragma unroll
-                for (int k = 0; k < 36; ++k) s = fmaf(patch[k], wr[k], s);
-                if (act == FIE_ACT_SILU) s = silu_f(s);
+            for (int j = 0; j < 8; ++j) acc[px][j] = (j < vec) ? sw[36 * cpad + g * vec + j] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4* wr = reinterpret_cast<const float4*>(sw + (4 * t + c) * cpad + g * vec);
+                const float4 w0 = wr[0];
+                float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (vec == 8) w1 = wr[1];
+#pragma unroll
+                for (int px = 0; px < CIN4_PX; ++px) {
+                    const float v = in[t / 3][px + t % 3][c];
+                    acc[px][0] = fmaf(v, w0.x, acc[px][0]); acc[px][1] = fmaf(v, w0.y, acc[px][1]);
+                    acc[px][2] = fmaf(v, w0.z, acc[px][2]); acc[px][3] = fmaf(v, w0.w, acc[px][3]);
+                    if (vec == 8) {
+                        acc[px][4] = fmaf(v, w1.x, acc[px][4]); acc[px][5] = fmaf(v, w1.y, acc[px][5]);
+                        acc[px][6] = fmaf(v, w1.z, acc[px][6]); acc[px][7] = fmaf(v, w1.w, acc[px][7]);
+                    }
+                }
             }
-            acc[j] = s;
         }
-        uint4 u; __half2* hh = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
-        *reinterpret_cast<uint4*>(o + co) = u;
+        for (int px = 0; px < CIN4_PX; ++px) {
+            if (xq0 + px >= w) break;
+            if (act == FIE_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (j < vec && g * vec + j < cout) acc[px][j] = silu_f(acc[px][j]);
+            }
+            __half* o = out + ((img * h + yy) * w + xq0 + px) * ld_out + g * vec;
+            if (vec == 8) {
+                uint4 u; __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hh[j] = __floats2half2_rn(acc[px][2 * j], acc[px][2 * j + 1]);
+                *reinterpret_cast<uint4*>(o) = u;
+            } else {
+                uint2 u; __half2* hh = reinterpret_cast<__half2*>(&u);
+                hh[0] = __floats2half2_rn(acc[px][0], acc[px][1]); hh[1] = __floats2half2_rn(acc[px][2], acc[px][3]);
+                *reinterpret_cast<uint2*>(o) = u;
+            }
+        }
     }
 }
 
@@ -76,11 +92,17 @@ extern "C" int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float
                                     int n, int h, int w, int cout, int act, void* stream) {
     FIE_REQUIRE(x && wgt && out && n > 0 && h > 0 && w > 0 && cout > 0, "fie_conv3x3_cin4_f16: bad args");
     FIE_REQUIRE(ld_out >= cout && (ld_out % 4) == 0, "fie_conv3x3_cin4_f16: ld_out must be >= cout and a multiple of 4");
-    const size_t smem = (size_t)cout * 37 * sizeof(float);
-    FIE_REQUIRE(smem <= 96 * 1024, "fie_conv3x3_cin4_f16: cout too large");
+    const int vec = (ld_out % 8) == 0 ? 8 : 4;
+    const int groups = ld_out / vec;                 // threads per pixel; channels >= cout are written as zeros
+    FIE_REQUIRE(groups <= 256, "fie_conv3x3_cin4_f16: ld_out too large");
+    const size_t smem = (size_t)37 * groups * vec * sizeof(float);
+    FIE_REQUIRE(smem <= 160 * 1024, "fie_conv3x3_cin4_f16: cout too large");
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_conv_cin4, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
-    const long long npix = (long long)n * h * w;
-    k_conv_cin4<<<(unsigned)((npix + 127) / 128), 128, smem, (cudaStream_t)stream>>>((const uint2*)x, wgt, bias, (__half*)out, ld_out, n, h, w, cout, act);
+    if (!attr) { cudaFuncSetAttribute(k_conv_cin4, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    const long long nquads = (long long)n * h * ((w + CIN4_PX - 1) / CIN4_PX);
+    const int qpb = 256 / groups;
+    long long blocks = (nquads + qpb - 1) / qpb;
+    const long long cap = 148ll * 8; if (blocks > cap) blocks = cap;
+    k_conv_cin4<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>((const uint2*)x, wgt, bias, (__half*)out, ld_out, n, h, w, cout, act, groups, vec);
     return check_launch("fie_conv3x3_cin4_f16");
 }

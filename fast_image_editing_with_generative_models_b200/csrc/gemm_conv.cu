@@ -24,7 +24,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_STAGES = 8;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 192 * 1024;      // pipeline stages
+constexpr int EPI_STAGE_BYTES = 8 * 2048;      // per-epilogue-warp 32x32 fp16 transpose buffers
 
 struct GemmParams {
     CUtensorMap a_maps[4];
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* epi_smem = smem + SMEM_BUDGET;        // [8 warps][32 rows][64 B], 16-byte pieces XOR-swizzled by (row >> 1) & 3
     const int block_n = p.block_n;
     const int b_rows = block_n / CG;                                   // B rows held by this CTA
     const int b_sub_bytes = b_rows * BLOCK_K * 2;
@@ -226,9 +228,11 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
             const int nchunks = (geglu ? half_n : block_n) / 32;
+            const long long m_w0 = m - lane;                       // first row of this warp
             for (int c = cpar; c < ((p.dbg & 4) ? 0 : nchunks); c += 2) {
                 uint32_t r[32];
                 float v[32];
+
                 tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
                 tmem_ld_wait();
                 const int nacc = n_blk * block_n + c * 32;        // accumulator column (B row) of v[0]
@@ -272,20 +276,52 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] *= p.scale;
                 }
-                if (row_ok && nout < p.n_store) {
+                const bool fast = !p.out_f32 && nout + 32 <= p.n_store && (p.ldd & 7) == 0 && (!p.residual || (p.ld_res & 7) == 0);
+                if (fast) {
+                    // Coalesced path: a warp instruction moves 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
+                    uint8_t* stg = epi_smem + (warp - 4) * 2048;
+                    const int own = lane * 64, osw = (lane >> 1) & 3;
+                    if (p.residual) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int rr = (lane >> 2) + 8 * t, pc = lane & 3;
+                            const long long mr = m_w0 + rr;
+                            uint4 u = make_uint4(0, 0, 0, 0);
+                            if (mr < p.M) u = __ldg(reinterpret_cast<const uint4*>(p.residual + mr * p.ld_res + nout) + pc);
+                            *reinterpret_cast<uint4*>(stg + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4)) = u;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int pc = 0; pc < 4; ++pc) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(stg + own + ((pc ^ osw) << 4));
+                            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[8 * pc + 2 * j] += f.x; v[8 * pc + 2 * j + 1] += f.y; }
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                        uint4 u;
+                        __half2 h0 = __floats2half2_rn(v[8 * pc], v[8 * pc + 1]), h1 = __floats2half2_rn(v[8 * pc + 2], v[8 * pc + 3]);
+                        __half2 h2 = __floats2half2_rn(v[8 * pc + 4], v[8 * pc + 5]), h3 = __floats2half2_rn(v[8 * pc + 6], v[8 * pc + 7]);
+                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(stg + own + ((pc ^ osw) << 4)) = u;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int rr = (lane >> 2) + 8 * t, pc = lane & 3;
+                        const long long mr = m_w0 + rr;
+                        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
+                        if (mr < p.M) *(reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.D) + mr * p.ldd + nout) + pc) = u;
+                    }
+                    __syncwarp();
+                } else if (row_ok && nout < p.n_store) {
                     if (p.residual) {
                         const __half* rp = p.residual + m * p.ld_res + nout;
-                        if (nout + 32 <= p.n_store && (p.ld_res & 7) == 0) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + i);
-                                const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[8 * i + 2 * j] += f.x; v[8 * i + 2 * j + 1] += f.y; }
-                            }
-                        } else {
-                            for (int i = 0; i < 32; ++i) if (nout + i < p.n_store) v[i] += __half2float(rp[i]);
-                        }
+                        for (int i = 0; i < 32; ++i) if (nout + i < p.n_store) v[i] += __half2float(rp[i]);
                     }
                     store_chunk(p, m, nout, v);
                 }
@@ -400,15 +436,14 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     p.num_stages = stages;
     int cols = 2 * p.block_n, tc = 32; while (tc < cols) tc <<= 1;
     p.tmem_cols = tc;
-    size_t smem = (size_t)stages * stage_bytes + 1024;
-    // >113 KiB of dynamic smem guarantees one CTA per SM, so a 512-column TMEM allocation can never deadlock
-    if (tc > 256 && smem < 120 * 1024) smem = 120 * 1024;
+    size_t smem = (size_t)SMEM_BUDGET + EPI_STAGE_BYTES + 1024;
+    // (>113 KiB of dynamic smem: one CTA per SM, so a 512-column TMEM allocation can never deadlock)
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_conv<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 2048);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_conv<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gemm_conv): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
         attr_set = true;
     }

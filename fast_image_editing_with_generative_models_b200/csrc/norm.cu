@@ -32,7 +32,20 @@ __global__ void __launch_bounds__(512) k_gn_stats(GNArgs a) {
         const bool first = v < a.c0v;
         const uint4* src = first ? a.x0 + (long long)img * a.hw * a.c0v + v : a.x1 + (long long)img * a.hw * a.c1v + (v - a.c0v);
         const int stride = first ? a.c0v : a.c1v;
-        for (long long r = r0 + rsub; r < r1; r += a.rows_in_flight) {
+        const long long step = a.rows_in_flight;
+        long long r = r0 + rsub;
+        for (; r + 3 * step < r1; r += 4 * step) {          // 4 independent 128-bit loads in flight per thread
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) u[k] = __ldg(src + (r + k * step) * stride);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); s[2 * j] += f.x; q[2 * j] += f.x * f.x; s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y; }
+            }
+        }
+        for (; r < r1; r += step) {
             uint4 u = __ldg(src + r * stride);
             const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -77,20 +90,33 @@ __global__ void __launch_bounds__(512) k_gn_apply(GNArgs a) {
     const uint4* src = first ? a.x0 + (long long)img * a.hw * a.c0v + v : a.x1 + (long long)img * a.hw * a.c1v + (v - a.c0v);
     const int stride = first ? a.c0v : a.c1v;
     uint4* dst = a.out + (long long)img * a.hw * a.cv + v;
-    for (long long r = r0 + rsub; r < r1; r += a.rows_in_flight) {
-        uint4 u = __ldg(src + r * stride), o;
+    // fold the affine transform: y = x * sc + sh
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = rs[j] * ga[j]; sh[j] = be[j] - mu[j] * sc[j]; }
+    auto apply = [&](const uint4& u) -> uint4 {
+        uint4 o;
         const __half2* h = reinterpret_cast<const __half2*>(&u);
         __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float2 f = __half22float2(h[j]);
-            float y0 = (f.x - mu[2 * j]) * rs[2 * j] * ga[2 * j] + be[2 * j];
-            float y1 = (f.y - mu[2 * j + 1]) * rs[2 * j + 1] * ga[2 * j + 1] + be[2 * j + 1];
+            float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]), y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
             if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
             oh[j] = __floats2half2_rn(y0, y1);
         }
-        dst[r * a.cv] = o;
+        return o;
+    };
+    const long long step = a.rows_in_flight;
+    long long r = r0 + rsub;
+    for (; r + 3 * step < r1; r += 4 * step) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) u[k] = __ldg(src + (r + k * step) * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[(r + k * step) * a.cv] = apply(u[k]);
     }
+    for (; r < r1; r += step) dst[r * a.cv] = apply(__ldg(src + r * stride));
 }
 
 // ---- LayerNorm: warp per row, up to 8 vectors (2048 channels) per lane ----
