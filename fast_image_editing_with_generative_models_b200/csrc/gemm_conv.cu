@@ -36,11 +36,13 @@ struct GemmParams {
     int kb_split;     // GEMM: k-blocks taken from a_maps[0]; the rest from a_maps[1]
     int8_t tap_map[12], tap_dh[12], tap_dw[12];
     int OH, OW;
+    int up2, up_a, up_b;   // up2 = 1: rows are INPUT pixels (n,h,w) of a nearest-2x-upsampled conv phase; output pixel (2h+a, 2w+b)
     long long M;
     int N;            // accumulator columns (B rows)
     int block_n;
     int cg;           // 1 or 2 CTAs per tile
     int kps;          // 64-wide K blocks per pipeline stage (1 or 2)
+    int mt;           // 128-row M sub-tiles per CTA (1 or 2)
     int dbg;          // debug/tuning: 1 = skip TMA loads, 2 = skip MMA issue, 4 = skip epilogue math/stores
     int num_m_blocks, num_n_blocks;   // m blocks of 128*cg rows
     int num_stages;
@@ -61,10 +63,19 @@ struct GemmParams {
     int out_f32;
 };
 
+// Output row of accumulator row m (identity, or the strided scatter of one phase of the fused nearest-2x upsample).
+__device__ __forceinline__ long long out_row(const GemmParams& p, long long m) {
+    if (!p.up2) return m;
+    const int pix = p.OH * p.OW;
+    const int n = (int)(m / pix), rem = (int)(m - (long long)n * pix);
+    const int h = rem / p.OW, w = rem - h * p.OW;
+    return ((long long)n * 2 * p.OH + 2 * h + p.up_a) * (2 * p.OW) + 2 * w + p.up_b;
+}
+
 __device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, int n0, const float (&v)[32]) {
     // stores v[0..31] to output row m, columns n0..n0+31 (masked by n_store)
     if (p.out_f32) {
-        float* d = reinterpret_cast<float*>(p.D) + m * p.ldd + n0;
+        float* d = reinterpret_cast<float*>(p.D) + out_row(p, m) * p.ldd + n0;
         if (n0 + 32 <= p.n_store && (p.ldd & 3) == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(d)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -72,7 +83,7 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, in
             for (int i = 0; i < 32; ++i) if (n0 + i < p.n_store) d[i] = v[i];
         }
     } else {
-        __half* d = reinterpret_cast<__half*>(p.D) + m * p.ldd + n0;
+        __half* d = reinterpret_cast<__half*>(p.D) + out_row(p, m) * p.ldd + n0;
         if (n0 + 32 <= p.n_store && (p.ldd & 7) == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -91,7 +102,8 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, in
 
 // CG = 1: one CTA per tile (M = 128).  CG = 2: CTA pair (cta_group::2), tile M = 256, each CTA loads half of B.
 // KPS = 64-wide K blocks per pipeline stage (per producer/consumer mbarrier handshake).
-template <int CG, int KPS>
+// MT = 128-row M sub-tiles per CTA that share every B tile (narrow-N problems: twice the MMA work per handshake).
+template <int CG, int KPS, int MT>
 __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned by the ABI; round up to 1024 for the 128B swizzle
@@ -104,7 +116,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     const int block_n = p.block_n;
     const int b_rows = block_n / CG;                                   // B rows held by this CTA
     const int b_sub_bytes = b_rows * BLOCK_K * 2;
-    const int stage_bytes = KPS * (A_STAGE_BYTES + b_sub_bytes);
+    const int stage_bytes = KPS * (MT * A_STAGE_BYTES + b_sub_bytes);
     const int num_sb = (p.num_kb + KPS - 1) / KPS;                     // pipeline iterations per tile
     const int num_stages = p.num_stages;
     const int num_tiles = p.num_m_blocks * p.num_n_blocks;            // m blocks of 128*CG rows
@@ -133,13 +145,17 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             int stage = 0; uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-                const long long m0 = ((long long)m_blk * CG + cta_rank) * BLOCK_M;
-                int n0i = 0, h0 = 0, w0 = 0;
-                if (p.mode == 1) {
-                    const long long pix = (long long)p.OH * p.OW;
-                    n0i = (int)(m0 / pix);
-                    const int rem = (int)(m0 % pix);
-                    h0 = rem / p.OW; w0 = rem % p.OW;
+                long long m0[MT]; int n0i[MT], h0[MT], w0[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    m0[mt] = (((long long)m_blk * MT + mt) * CG + cta_rank) * BLOCK_M;
+                    n0i[mt] = 0; h0[mt] = 0; w0[mt] = 0;
+                    if (p.mode == 1) {
+                        const long long pix = (long long)p.OH * p.OW;
+                        n0i[mt] = (int)(m0[mt] / pix);
+                        const int rem = (int)(m0[mt] % pix);
+                        h0[mt] = rem / p.OW; w0[mt] = rem % p.OW;
+                    }
                 }
                 for (int sb = 0; sb < num_sb; ++sb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -152,20 +168,23 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
 #pragma unroll
                         for (int sub = 0; sub < KPS; ++sub) {
                             const int kb = sb * KPS + sub;                       // kb >= num_kb: coordinates fall outside -> zero fill
-                            uint8_t* sa = sbase + sub * A_STAGE_BYTES;
-                            uint8_t* sbm = sbase + KPS * A_STAGE_BYTES + sub * b_sub_bytes;
-                            if (p.mode == 0) {
-                                const bool first = kb < p.kb_split;
-                                const CUtensorMap* am = first ? &p.a_maps[0] : &p.a_maps[1];
-                                const int kc = (first ? kb : kb - p.kb_split) * BLOCK_K;
-                                if (CG == 1) tma_load_2d(am, &full_bar[stage], sa, kc, (int)m0); else tma_load_2d_2sm(am, &full_bar[stage], sa, kc, (int)m0);
-                            } else {
-                                int tap = kb / p.kb_per_tap;
-                                int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
-                                if (kb >= p.num_kb) { tap = 0; c0 = p.kb_per_tap * BLOCK_K; }
-                                const CUtensorMap* am = &p.a_maps[p.tap_map[tap]];
-                                if (CG == 1) tma_load_4d(am, &full_bar[stage], sa, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0i);
-                                else tma_load_4d_2sm(am, &full_bar[stage], sa, c0, w0 + p.tap_dw[tap], h0 + p.tap_dh[tap], n0i);
+                            uint8_t* sbm = sbase + KPS * MT * A_STAGE_BYTES + sub * b_sub_bytes;
+#pragma unroll
+                            for (int mt = 0; mt < MT; ++mt) {
+                                uint8_t* sa = sbase + (sub * MT + mt) * A_STAGE_BYTES;
+                                if (p.mode == 0) {
+                                    const bool first = kb < p.kb_split;
+                                    const CUtensorMap* am = first ? &p.a_maps[0] : &p.a_maps[1];
+                                    const int kc = (first ? kb : kb - p.kb_split) * BLOCK_K;
+                                    if (CG == 1) tma_load_2d(am, &full_bar[stage], sa, kc, (int)m0[mt]); else tma_load_2d_2sm(am, &full_bar[stage], sa, kc, (int)m0[mt]);
+                                } else {
+                                    int tap = kb / p.kb_per_tap;
+                                    int c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+                                    if (kb >= p.num_kb) { tap = 0; c0 = p.kb_per_tap * BLOCK_K; }
+                                    const CUtensorMap* am = &p.a_maps[p.tap_map[tap]];
+                                    if (CG == 1) tma_load_4d(am, &full_bar[stage], sa, c0, w0[mt] + p.tap_dw[tap], h0[mt] + p.tap_dh[tap], n0i[mt]);
+                                    else tma_load_4d_2sm(am, &full_bar[stage], sa, c0, w0[mt] + p.tap_dw[tap], h0[mt] + p.tap_dh[tap], n0i[mt]);
+                                }
                             }
                             if (CG == 1) tma_load_2d(&p.b_map, &full_bar[stage], sbm, kb * BLOCK_K, n_blk * block_n);
                             else tma_load_2d_2sm(&p.b_map, &full_bar[stage], sbm, kb * BLOCK_K, n_blk * block_n + (int)cta_rank * b_rows);
@@ -183,7 +202,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             if (CG == 2) mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1); else mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * block_n);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * MT * block_n);
             for (int sb = 0; sb < num_sb; ++sb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
@@ -191,14 +210,17 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                     const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
 #pragma unroll
                     for (int sub = 0; sub < KPS; ++sub) {
-                        const uint64_t adesc = umma_desc_sw128(sbase + sub * A_STAGE_BYTES);
-                        const uint64_t bdesc = umma_desc_sw128(sbase + KPS * A_STAGE_BYTES + sub * b_sub_bytes);
+                        const uint64_t bdesc = umma_desc_sw128(sbase + KPS * MT * A_STAGE_BYTES + sub * b_sub_bytes);
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; ++k) {
-                            if (p.dbg & 2) continue;
-                            const uint32_t acc = (sb | sub | k) ? 1u : 0u;
-                            if (CG == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-                            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t adesc = umma_desc_sw128(sbase + (sub * MT + mt) * A_STAGE_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                if (p.dbg & 2) continue;
+                                const uint32_t acc = (sb | sub | k) ? 1u : 0u;
+                                if (CG == 2) umma_f16_2sm(tmem_d + mt * block_n, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                                else umma_f16(tmem_d + mt * block_n, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                            }
                         }
                     }
                     if (CG == 2) { umma_commit_2sm(&empty_bar[stage]); if (sb == num_sb - 1) umma_commit_2sm(&tmem_full[buf]); }
@@ -220,14 +242,16 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-            const long long m = ((long long)m_blk * CG + cta_rank) * BLOCK_M + row_in_tile;
-            const bool row_ok = m < p.M;
             mbar_wait(&tmem_full[buf], acc_phase);
             tc_fence_after();
-            const uint32_t tacc = tmem_base + lane_addr + (uint32_t)(buf * block_n);
+            const int nchunks = (geglu ? half_n : block_n) / 32;
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+            const long long m = (((long long)m_blk * MT + mt) * CG + cta_rank) * BLOCK_M + row_in_tile;
+            const bool row_ok = m < p.M;
+            const uint32_t tacc = tmem_base + lane_addr + (uint32_t)((buf * MT + mt) * block_n);
             const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
             const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
-            const int nchunks = (geglu ? half_n : block_n) / 32;
             const long long m_w0 = m - lane;                       // first row of this warp
             for (int c = cpar; c < ((p.dbg & 4) ? 0 : nchunks); c += 2) {
                 uint32_t r[32];
@@ -315,7 +339,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                         const int rr = (lane >> 2) + 8 * t, pc = lane & 3;
                         const long long mr = m_w0 + rr;
                         const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
-                        if (mr < p.M) *(reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.D) + mr * p.ldd + nout) + pc) = u;
+                        if (mr < p.M) *(reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.D) + out_row(p, mr) * p.ldd + nout) + pc) = u;
                     }
                     __syncwarp();
                 } else if (row_ok && nout < p.n_store) {
@@ -326,6 +350,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                     store_chunk(p, m, nout, v);
                 }
             }
+            }   // mt
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { if (CG == 2) mbar_arrive_remote(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]); }
@@ -388,25 +413,30 @@ static int g_force_cg = -1;
 static int g_force_bn = 0;
 static int g_dbg = 0;
 static int g_force_kps = 0;
-static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out) {
+static int g_force_mt = 0;
+static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out, int* mt_out) {
     if (g_force_cg < 0) { const char* s = getenv("FIE_GEMM_CG"); g_force_cg = s ? atoi(s) : 0; }
     const int sms = num_sms();
-    double best_cost = 1e30; int best_cg = 2, best_bn = 32;
+    double best_cost = 1e30; int best_cg = 2, best_bn = 32, best_mt = 1;
     for (int cg = 2; cg >= 1; --cg) {
         if (g_force_cg && cg != g_force_cg) continue;
         if (!g_force_cg && cg == 1 && M > BLOCK_M) continue;          // single-CTA form only for one-tile-high problems
-        const long long mblocks = (M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
-        const int slots = sms / cg;
-        for (int bn = 32; bn <= 256; bn += 32) {
-            if (geglu && bn != fie_geglu_block_n(N)) continue;   // GEGLU rows are pre-interleaved per tile by the host
-            if (!geglu && g_force_bn && bn != g_force_bn) continue;
-            const long long tiles = mblocks * ((N + bn - 1) / bn);
-            const long long waves = (tiles + slots - 1) / slots;
-            const double cost = (double)waves * (bn + 290.0) * (cg == 1 ? 0.6 : 1.0);
-            if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && bn > best_bn)) { best_cost = cost; best_cg = cg; best_bn = bn; }
+        for (int mt = 1; mt <= 2; ++mt) {
+            if (g_force_mt && mt != g_force_mt) continue;
+            if (!g_force_mt && mt == 2 && N > 128) continue;     // measured: two M sub-tiles only pay off for N <= 128
+            const long long mblocks = (M + BLOCK_M * cg * mt - 1) / (BLOCK_M * cg * mt);
+            const int slots = sms / cg;
+            for (int bn = 32; bn <= 256 / mt; bn += 32) {       // 2 buffers x mt x bn TMEM columns <= 512
+                if (geglu && bn != fie_geglu_block_n(N)) continue;   // GEGLU rows are pre-interleaved per tile by the host
+                if (!geglu && g_force_bn && bn != g_force_bn) continue;
+                const long long tiles = mblocks * ((N + bn - 1) / bn);
+                const long long waves = (tiles + slots - 1) / slots;
+                const double cost = (double)waves * (mt * bn + 290.0) * (cg == 1 ? 0.6 : 1.0);
+                if (cost < best_cost - 1e-9 || (cost < best_cost + 1e-9 && mt * bn > best_mt * best_bn)) { best_cost = cost; best_cg = cg; best_bn = bn; best_mt = mt; }
+            }
         }
     }
-    *cg_out = best_cg; *bn_out = best_bn;
+    *cg_out = best_cg; *bn_out = best_bn; *mt_out = best_mt;
 }
 
 static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
@@ -427,42 +457,41 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
 static int launch(GemmParams& p, cudaStream_t stream) {
     const int cg = p.cg;
     p.dbg = g_dbg;
+    const int mt = p.mt;
     int kps = (g_force_kps > 0) ? g_force_kps : (p.num_kb >= 4 ? 2 : 1);
-    if (kps == 2 && SMEM_BUDGET / (2 * (A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2)) < 2) kps = 1;
+    if (kps == 2 && SMEM_BUDGET / (2 * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2)) < 2) kps = 1;
     p.kps = kps;
-    const int stage_bytes = kps * (A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2);
+    const int stage_bytes = kps * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2);
     int stages = SMEM_BUDGET / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) stages = 2;
     p.num_stages = stages;
-    int cols = 2 * p.block_n, tc = 32; while (tc < cols) tc <<= 1;
+    int cols = 2 * mt * p.block_n, tc = 32; while (tc < cols) tc <<= 1;
     p.tmem_cols = tc;
     size_t smem = (size_t)SMEM_BUDGET + EPI_STAGE_BYTES + 1024;
     // (>113 KiB of dynamic smem: one CTA per SM, so a 512-column TMEM allocation can never deadlock)
+    typedef void (*KernelFn)(GemmParams);
+    static const KernelFn kernels[2][2][2] = {{{k_gemm_conv<1, 1, 1>, k_gemm_conv<1, 1, 2>}, {k_gemm_conv<1, 2, 1>, k_gemm_conv<1, 2, 2>}},
+                                              {{k_gemm_conv<2, 1, 1>, k_gemm_conv<2, 1, 2>}, {k_gemm_conv<2, 2, 1>, k_gemm_conv<2, 2, 2>}}};
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_conv<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_conv<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gemm_conv): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gemm_conv): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+        }
         attr_set = true;
     }
+    KernelFn fn = kernels[cg - 1][kps - 1][mt - 1];
     const int tiles = p.num_m_blocks * p.num_n_blocks;
-    if (cg == 1) {
-        const int grid = tiles < num_sms() ? tiles : num_sms();
-        if (kps == 2) k_gemm_conv<1, 2><<<grid, 384, smem, stream>>>(p); else k_gemm_conv<1, 1><<<grid, 384, smem, stream>>>(p);
-    } else {
-        const int slots = num_sms() / 2;
-        const int grid = 2 * (tiles < slots ? tiles : slots);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = (kps == 2) ? cudaLaunchKernelEx(&cfg, k_gemm_conv<2, 2>, p) : cudaLaunchKernelEx(&cfg, k_gemm_conv<2, 1>, p);
-        if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_gemm_conv<2>): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
-    }
+    const int slots = num_sms() / cg;
+    const int grid = cg * (tiles < slots ? tiles : slots);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_gemm_conv): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
     return check_launch("k_gemm_conv");
 }
 
@@ -470,7 +499,7 @@ static int launch(GemmParams& p, cudaStream_t stream) {
 
 using namespace fie;
 
-extern "C" void fie_tune_gemm(int force_cg, int force_block_n) { fie::g_force_cg = force_cg & 3; fie::g_force_kps = (force_cg >> 2) & 3; fie::g_dbg = force_cg >> 4; fie::g_force_bn = force_block_n; }
+extern "C" void fie_tune_gemm(int force_cg, int force_block_n) { fie::g_force_cg = force_cg & 3; fie::g_force_kps = (force_cg >> 2) & 3; fie::g_dbg = (force_cg >> 4) & 15; fie::g_force_mt = (force_cg >> 8) & 3; fie::g_force_bn = force_block_n; }
 
 extern "C" int fie_geglu_block_n(int N) { return (N % 256) == 0 ? 256 : ((N % 128) == 0 ? 128 : 64); }
 
@@ -487,8 +516,8 @@ extern "C" int fie_gemm_f16(const void* A, long long lda, const void* A1, long l
     if (rc) return rc;
     const bool geglu = p.act == FIE_ACT_GEGLU;
     p.mode = 0; p.M = M; p.N = N;
-    pick_config(M, N, geglu, &p.cg, &p.block_n);
-    p.num_m_blocks = (int)((M + BLOCK_M * p.cg - 1) / (BLOCK_M * p.cg));
+    pick_config(M, N, geglu, &p.cg, &p.block_n, &p.mt);
+    p.num_m_blocks = (int)((M + BLOCK_M * p.cg * p.mt - 1) / (BLOCK_M * p.cg * p.mt));
     p.num_n_blocks = (N + p.block_n - 1) / p.block_n;
     p.num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     p.kb_per_tap = p.num_kb; p.kb_split = p.num_kb;
@@ -536,8 +565,8 @@ extern "C" int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long l
     if (rc) return rc;
     FIE_REQUIRE(p.act != FIE_ACT_GEGLU, "fie_conv3x3_f16: GEGLU epilogue not supported for conv");
     p.mode = 1; p.M = M; p.N = cout; p.OH = OH; p.OW = OW;
-    pick_config(M, cout, false, &p.cg, &p.block_n);
-    p.num_m_blocks = (int)((M + BLOCK_M * p.cg - 1) / (BLOCK_M * p.cg));
+    pick_config(M, cout, false, &p.cg, &p.block_n, &p.mt);
+    p.num_m_blocks = (int)((M + BLOCK_M * p.cg * p.mt - 1) / (BLOCK_M * p.cg * p.mt));
     p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
     p.kb_per_tap = cin / BLOCK_K;
     p.num_kb = 9 * p.kb_per_tap;
@@ -573,4 +602,55 @@ extern "C" int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long l
     const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(p.block_n / p.cg)};
     if ((rc = make_tmap_f16(&p.b_map, wgt, 2, bdims, bstr, bbox))) return rc;
     return launch(p, (cudaStream_t)stream);
+}
+
+// Nearest-2x upsample fused into the following 3x3 convolution (diffusers Upsample2D: F.interpolate(scale 2, nearest) then
+// conv3x3).  Output pixel (2i+a, 2j+b) only ever sees a 2x2 neighbourhood of the input, with the 3x3 taps that land on the
+// same input pixel pre-summed by the host: four phase convolutions with 2x2 taps = 16/36 of the FLOPs and no upsampled
+// tensor in HBM.  wgt: fp16 [4 phases (a*2+b)][cout][2][2][cin].
+extern "C" int fie_conv_up2x_f16(const void* x, const void* wgt, void* out, long long ldd, int n, int h, int w, int cin, int cout,
+                                 const fie_epilogue* ep, void* stream) {
+    FIE_REQUIRE(x && wgt && out, "fie_conv_up2x_f16: null pointer");
+    FIE_REQUIRE(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "fie_conv_up2x_f16: bad shape");
+    FIE_REQUIRE((cin % BLOCK_K) == 0 && (cout % 32) == 0, "fie_conv_up2x_f16: cin %% 64 and cout %% 32 required");
+    int bw, bh, bn;
+    if (w >= 128) { FIE_REQUIRE((w % 128) == 0, "fie_conv_up2x_f16: width %d must be a multiple of 128", w); bw = 128; bh = 1; bn = 1; }
+    else {
+        FIE_REQUIRE((128 % w) == 0, "fie_conv_up2x_f16: width %d must divide 128", w);
+        bw = w; bh = 128 / w;
+        if (bh <= h) { FIE_REQUIRE((h % bh) == 0, "fie_conv_up2x_f16: height %d not a multiple of %d", h, bh); bn = 1; }
+        else { FIE_REQUIRE((bh % h) == 0, "fie_conv_up2x_f16: height %d must divide %d", h, bh); bn = bh / h; bh = h; }
+    }
+    const long long M = (long long)n * h * w;
+    for (int ph = 0; ph < 4; ++ph) {
+        GemmParams p;
+        memset(&p, 0, sizeof(p));
+        int rc = fill_epilogue(p, ep, M, cout, out, ldd);
+        if (rc) return rc;
+        FIE_REQUIRE(p.act != FIE_ACT_GEGLU && !p.residual && !p.out_f32, "fie_conv_up2x_f16: unsupported epilogue");
+        p.mode = 1; p.M = M; p.N = cout; p.OH = h; p.OW = w;
+        p.up2 = 1; p.up_a = ph >> 1; p.up_b = ph & 1;
+        pick_config(M, cout, false, &p.cg, &p.block_n, &p.mt);
+        p.num_m_blocks = (int)((M + BLOCK_M * p.cg * p.mt - 1) / (BLOCK_M * p.cg * p.mt));
+        p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
+        p.kb_per_tap = cin / BLOCK_K;
+        p.num_kb = 4 * p.kb_per_tap;
+        p.kb_split = p.num_kb;
+        p.n_store = cout;
+        const uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+        const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};
+        if ((rc = make_tmap_f16(&p.a_maps[0], x, 4, dims, strides, box))) return rc;
+        p.a_maps[1] = p.a_maps[0]; p.a_maps[2] = p.a_maps[0]; p.a_maps[3] = p.a_maps[0];
+        for (int t = 0; t < 4; ++t) {   // tap (ty, tx): input row i + ty - 1 + a, column j + tx - 1 + b
+            p.tap_map[t] = 0; p.tap_dh[t] = (int8_t)((t >> 1) - 1 + p.up_a); p.tap_dw[t] = (int8_t)((t & 1) - 1 + p.up_b);
+        }
+        const uint64_t bdims[2] = {(uint64_t)4 * cin, (uint64_t)cout};
+        const uint64_t bstr[1] = {(uint64_t)4 * cin * 2};
+        const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(p.block_n / p.cg)};
+        const uint8_t* wp = (const uint8_t*)wgt + (size_t)ph * cout * 4 * cin * 2;
+        if ((rc = make_tmap_f16(&p.b_map, wp, 2, bdims, bstr, bbox))) return rc;
+        if ((rc = launch(p, (cudaStream_t)stream))) return rc;
+    }
+    return FIE_OK;
 }

@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from .configs import ControlNetConfig, UNetConfig, VAEConfig, skip_channels
-from .weights import fuse_lora, pack_conv3x3, pack_geglu
+from .weights import fuse_lora, pack_conv3x3, pack_conv_up2x, pack_geglu
 
 Tensor = torch.Tensor
 Params = Dict[str, Tensor]
@@ -66,6 +66,10 @@ class _Packer:
             bp[: b.numel()] = b
             b = bp
         return w, b
+
+    def conv_up(self, name: str) -> Tuple[Tensor, Optional[Tensor]]:
+        """Upsample2D conv: phase-decomposed weights for the fused nearest-2x upsample + conv3x3 kernel."""
+        return pack_conv_up2x(self.w(name)), self.b(name)
 
     def conv1(self, name: str) -> Tuple[Tensor, Optional[Tensor]]:
         w = self.w(name)
@@ -260,7 +264,7 @@ class UNet:
                 if len(cfg.up_depths[i]):
                     blk["attn"].append(Transformer2D(pk, f"up_blocks.{i}.attentions.{j}", cout, cfg.up_depths[i][j], g, self.enc.kv_slot))
             if i < len(rev) - 1:
-                blk["up"] = pk.conv3(f"up_blocks.{i}.upsamplers.0.conv")
+                blk["up"] = pk.conv_up(f"up_blocks.{i}.upsamplers.0.conv")
             self.up.append(blk)
         self.norm_out = pk.norm("conv_norm_out")
         self.conv_out = pk.conv3("conv_out", pad_cout_to=32)
@@ -287,7 +291,7 @@ class UNet:
                 if blk["attn"]:
                     h = blk["attn"][j](h, ctx_kv, nctx)
             if blk["up"] is not None:
-                h = ops.conv3x3(ops.upsample2x(h), blk["up"][0], col_bias=blk["up"][1])
+                h = ops.conv_up2x(h, blk["up"][0], col_bias=blk["up"][1])
         h = ops.groupnorm(h, self.norm_out[0], self.norm_out[1], cfg.norm_eps, True, cfg.norm_groups)
         return ops.conv3x3(h, self.conv_out[0], cout_valid=cfg.out_channels, col_bias=self.conv_out[1])
 
@@ -394,7 +398,7 @@ class VAE:
         self.d_up = []
         for i in range(len(ch)):
             res = [Resnet(pk, f"decoder.up_blocks.{i}.resnets.{j}", eps, g) for j in range(cfg.layers_per_block + 1)]
-            us = pk.conv3(f"decoder.up_blocks.{i}.upsamplers.0.conv") if i < len(ch) - 1 else None
+            us = pk.conv_up(f"decoder.up_blocks.{i}.upsamplers.0.conv") if i < len(ch) - 1 else None
             self.d_up.append((res, us))
         self.d_norm = pk.norm("decoder.conv_norm_out")
         self.d_out = pk.conv3("decoder.conv_out", pad_cout_to=32)
@@ -429,7 +433,7 @@ class VAE:
             for r in res:
                 h = r(h)
             if us is not None:
-                h = ops.conv3x3(ops.upsample2x(h), us[0], col_bias=us[1])
+                h = ops.conv_up2x(h, us[0], col_bias=us[1])
         h = ops.groupnorm(h, self.d_norm[0], self.d_norm[1], cfg.norm_eps, True, cfg.norm_groups)
         n, hh, ww, _ = h.shape
         out = torch.empty((n, hh, ww, 4), dtype=torch.float16, device=h.device)

@@ -28,10 +28,10 @@ def _count(n=1):
 class _prof:
     """Context manager: when ops.PROFILE is a list, brackets one C-ABI call with CUDA events on the launch stream."""
 
-    def __init__(self, family: str, work: float, unit: str):
+    def __init__(self, family: str, work: float, unit: str, tag: str = ""):
         self.on = PROFILE is not None
         if self.on:
-            self.family, self.work, self.unit = family, work, unit
+            self.family, self.work, self.unit, self.tag = family, work, unit, tag
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
 
@@ -43,15 +43,17 @@ class _prof:
     def __exit__(self, *a):
         if self.on:
             self.e1.record()
-            PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1))
+            PROFILE.append((self.family, self.work, self.unit, self.e0, self.e1, self.tag))
         return False
 
 
-def profile_summary():
+def profile_summary(by_tag: bool = False):
     """-> {family: dict(calls, ms, work, unit)} from the recorded events (synchronises)."""
     torch.cuda.synchronize()
     out = {}
-    for fam, work, unit, e0, e1 in PROFILE or []:
+    for fam, work, unit, e0, e1, tag in PROFILE or []:
+        if by_tag:
+            fam = f"{fam} {tag}"
         d = out.setdefault(fam, dict(calls=0, ms=0.0, work=0.0, unit=unit))
         d["calls"] += 1
         d["ms"] += e0.elapsed_time(e1)
@@ -169,7 +171,7 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
         c1 = x1.shape[-1]
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), dtype=torch.float16, device=x0.device)
     stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x0.device)
-    with _prof("groupnorm", 4.0 * out.numel(), "B"):
+    with _prof("groupnorm", 4.0 * out.numel(), "B", f"[{n},{hw},{c0}+{c1}]"):
         check(_lib.lib().fie_groupnorm_f16(_p(x0), c0, _p(x1), c1, _p(out), n, hw, groups, _p(gamma), _p(beta), float(eps), int(silu),
                                             _p(stats), _stream()), "fie_groupnorm_f16")
     _count(2)
@@ -181,7 +183,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     c = x.shape[-1]
     rows = x.numel() // c
     out = torch.empty_like(x)
-    with _prof("layernorm", 4.0 * out.numel(), "B"):
+    with _prof("layernorm", 4.0 * out.numel(), "B", f"[{rows},{c}]"):
         check(_lib.lib().fie_layernorm_f16(_p(x), _p(out), rows, c, _p(gamma), _p(beta), float(eps), _stream()), "fie_layernorm_f16")
     _count()
     return out
@@ -218,7 +220,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
         out = torch.empty(tuple(a.shape[:-1]) + (n_out,), dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
     ldd = out.stride(-2) if out.dim() >= 2 else n_out
     ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32)
-    with _prof("gemm", 2.0 * m * n * k, "FLOP"):
+    with _prof("gemm", 2.0 * m * n * k, "FLOP", f"M{m} N{n} K{k} act{act} res{int(residual is not None)} f32{int(out_f32)}"):
         check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")
     _count()
     return out
@@ -235,10 +237,25 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad_mode: int 
     if out is None:
         out = torch.empty((n, h // stride, wd // stride, cv), dtype=torch.float16, device=x.device)
     ep = _epilogue(col_bias, row_bias, rows_per_group, None, residual, scale, act, False)
-    with _prof("conv3x3", 2.0 * n * (h // stride) * (wd // stride) * cv * 9 * cin, "FLOP"):
+    with _prof("conv3x3", 2.0 * n * (h // stride) * (wd // stride) * cv * 9 * cin, "FLOP", f"[{n},{h},{wd},{cin}]->{cv} s{stride}"):
         check(_lib.lib().fie_conv3x3_f16(_p(x), _p(w), _p(out), out.stride(-2), n, h, wd, cin, cout, cv, stride, pad_mode, ctypes.byref(ep), _stream()),
               "fie_conv3x3_f16")
     _count()
+    return out
+
+
+def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused nearest-2x upsample + conv3x3.  x [N,H,W,Cin], w4 packed [4, Cout, 4*Cin] (weights.pack_conv_up2x) -> [N,2H,2W,Cout]."""
+    _req(x, torch.float16, "conv_up2x")
+    n, h, wd, cin = x.shape
+    cout = w4.shape[1]
+    assert w4.shape[0] == 4 and w4.shape[2] == 4 * cin, (w4.shape, cin)
+    if out is None:
+        out = torch.empty((n, 2 * h, 2 * wd, cout), dtype=torch.float16, device=x.device)
+    ep = _epilogue(col_bias)
+    with _prof("conv_up2x", 2.0 * n * 4 * h * wd * cout * 4 * cin, "FLOP", f"[{n},{h},{wd},{cin}]->{cout}"):
+        check(_lib.lib().fie_conv_up2x_f16(_p(x), _p(w4), _p(out), out.stride(-2), n, h, wd, cin, cout, ctypes.byref(ep), _stream()), "fie_conv_up2x_f16")
+    _count(4)
     return out
 
 
@@ -263,7 +280,7 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, hea
             raise _lib.FieError("attention_d64: fp16 CUDA tensors with unit inner stride required")
     if out is None:
         out = torch.empty((b * nq, heads * 64), dtype=torch.float16, device=q.device)
-    with _prof("attention", 4.0 * b * heads * nq * nkv * 64, "FLOP"):
+    with _prof("attention", 4.0 * b * heads * nq * nkv * 64, "FLOP", f"b{b} h{heads} nq{nq} nkv{nkv}"):
         check(_lib.lib().fie_attention_d64_f16(_p(q), q.stride(-2), _p(k), k.stride(-2), _p(v), v.stride(-2), _p(out), out.stride(-2),
                                                 b, heads, nq, nkv, float(scale), _stream()), "fie_attention_d64_f16")
     _count()

@@ -19,6 +19,24 @@ def pack_conv3x3(w: torch.Tensor, pad_cout_to: Optional[int] = None, pad_cin_to:
     return out.reshape(op, 9 * cp).contiguous()
 
 
+def pack_conv_up2x(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> fp16 [4, Cout, 4*Cin]: phase (a, b) weights of nearest-2x-upsample + conv3x3.
+    Output row 2i+a reads input rows {i-1, i} (a = 0) or {i, i+1} (a = 1); the 3x3 taps that fall on the same input row are
+    summed (in fp32): a=0 -> [W0, W1+W2], a=1 -> [W0+W1, W2]; identically for columns.  K order (ty, tx, cin)."""
+    w = w.float()
+    rows = {0: [w[:, :, 0], w[:, :, 1] + w[:, :, 2]], 1: [w[:, :, 0] + w[:, :, 1], w[:, :, 2]]}   # each [Cout, Cin, 3(kw)]
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for ty in (0, 1):
+                r = rows[a][ty]
+                cols = [r[:, :, 0], r[:, :, 1] + r[:, :, 2]] if b == 0 else [r[:, :, 0] + r[:, :, 1], r[:, :, 2]]
+                taps += cols                                   # (ty, tx) order, each [Cout, Cin]
+            out.append(torch.stack(taps, dim=1).reshape(w.shape[0], -1))
+    return torch.stack(out, 0).to(torch.float16).contiguous()
+
+
 def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """GEGLU projection [8C, C] (value rows first, gate rows second) -> rows interleaved per accumulator tile:
     tile j = [value rows j*h..(j+1)*h | gate rows 4C+j*h..], h = fie_geglu_block_n(8C)/2."""

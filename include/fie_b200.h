@@ -113,6 +113,11 @@ int fie_gemm_f16(const void* A, long long lda, const void* A1, long long lda1, i
 int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long long ldd, int n, int h, int w, int cin, int cout,
                     int cout_valid, int stride, int pad_mode, const fie_epilogue* ep, void* stream);
 
+/* Nearest-2x upsample fused with the following 3x3 convolution (diffusers Upsample2D).  x: [n,h,w,cin] -> out [n,2h,2w,cout].
+ * wgt: fp16 [4][cout][2][2][cin] phase weights (host pre-sums the 3x3 taps that hit the same input pixel, see weights.py). */
+int fie_conv_up2x_f16(const void* x, const void* wgt, void* out, long long ldd, int n, int h, int w, int cin, int cout,
+                      const fie_epilogue* ep, void* stream);
+
 /* 3x3 convolution with tiny Cin (<= 4, NHWC fp16 with 4 channels), CUDA cores: conv_in of UNet/ControlNet/VAE.
  * wgt: fp32 [cout][3][3][4]; bias fp32 [cout]; out fp16 [n,h,w,ld_out] (channels >= cout are zero-filled up to ld_out). */
 int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float* bias, void* out, int ld_out,

@@ -34,6 +34,7 @@ ops.PROFILE = []
 l0 = ops.LAUNCHES
 out = eng.edit_batch(imgs, pe, pl, noises)
 summ = ops.profile_summary()
+tags = ops.profile_summary(by_tag=True)
 ops.PROFILE = None
 print("launches per edit_batch", ops.LAUNCHES - l0)
 tot = sum(d["ms"] for d in summ.values())
@@ -41,6 +42,10 @@ for fam, d in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
     rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else 0
     print(f"{fam:14s} calls {d['calls']:5d}  {d['ms']:9.2f} ms  {100*d['ms']/tot:5.1f}%  " + (f"{rate/1e12:8.1f} TFLOP/s" if d["unit"] == "FLOP" else f"{rate/1e9:8.1f} GB/s"))
 print("sum of profiled ms", tot)
+print("--- top shapes ---")
+for fam, d in sorted(tags.items(), key=lambda kv: -kv[1]["ms"])[:45]:
+    rate = d["work"] / (d["ms"] * 1e-3)
+    print(f"{d['ms']:8.2f} ms x{d['calls']:4d}  " + (f"{rate/1e12:7.1f} TF/s" if d["unit"] == "FLOP" else f"{rate/1e9:7.1f} GB/s") + f"  {fam}")
 print("img u8 mean/std", float(out.images.float().mean()), float(out.images.float().std()))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({k: {kk: vv for kk, vv in v.items()} for k, v in summ.items()}, open(f"gpurun_out/probe_{a.model}_b{B}.json", "w"), indent=1)

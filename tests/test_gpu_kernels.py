@@ -213,6 +213,20 @@ def test_conv3x3_small_cout_and_epilogue(cuda_dev):
     assert rel_err(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (2, 32, 32, 128, 320), (1, 128, 128, 64, 128), (2, 8, 8, 256, 256), (1, 64, 256, 64, 96)])
+def test_conv_up2x(cuda_dev, n, h, w, cin, cout):
+    """Fused nearest-2x upsample + conv3x3 (Upsample2D) vs F.interpolate + F.conv2d."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv_up2x
+    x = _rand((n, h, w, cin), cuda_dev, 70).half()
+    wt = (_rand((cout, cin, 3, 3), cuda_dev, 71) / math.sqrt(9 * cin)).half()
+    bias = _rand((cout,), cuda_dev, 72)
+    out = ops.conv_up2x(x, pack_conv_up2x(wt), col_bias=bias)
+    ref = F.conv2d(F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest"), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 3e-3, rel_err(out, ref)     # phase weights are fp32 sums rounded once to fp16
+
+
 def test_conv3x3_cin4(cuda_dev):
     ops = _ops()
     n, h, w, cout = 2, 40, 56, 320
