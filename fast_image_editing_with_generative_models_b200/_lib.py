@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfie_b200.so")
+LIB_PATH = os.environ.get("FIE_LIB") or os.path.join(_HERE, "libfie_b200.so")   # FIE_LIB: experiment builds only
 
 c_void_p, c_int, c_ll, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
 
@@ -29,6 +29,7 @@ SIGNATURES = {
     "fie_canny_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "fie_canny_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "fie_preprocess_u8_to_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "fie_preprocess_u8_to_f16_pad8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "fie_postprocess_f16_to_u8": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fie_add_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "fie_silu_f16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
@@ -39,9 +40,11 @@ SIGNATURES = {
     "fie_layernorm_f16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "fie_geglu_block_n": (c_int, [c_int]),
     "fie_tune_gemm": (None, [c_int, c_int]),
+    "fie_gemm_trace": (None, [c_void_p]),
     "fie_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv3x3_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv_up2x_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
+    "fie_conv3x3_c8_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv3x3_cin4_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fie_attention_d64_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "fie_vae_sample_add_noise": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_float, c_float, c_float, c_void_p]),

@@ -28,6 +28,26 @@ __global__ void __launch_bounds__(256) k_pre(const uint8_t* __restrict__ in, __h
     }
 }
 
+// Same conversion into the zero-padded 8-channel layout [n][h+2][w+8][8] the tensor-core conv_in reads (real pixel (y, x) at
+// (y+1, x+1)); one thread writes one 16-byte padded pixel, borders and channels 3..7 as zeros.
+__global__ void __launch_bounds__(256) k_pre_pad8(const uint8_t* __restrict__ in, uint4* __restrict__ out, int n, int h, int w, int normalize) {
+    const int wp = w + 8, hp = h + 2;
+    const long long total = (long long)n * hp * wp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % wp) - 1; const long long t = i / wp; const int yy = (int)(t % hp) - 1; const long long img = t / hp;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (xx >= 0 && xx < w && yy >= 0 && yy < h) {
+            const uint8_t* px = in + ((img * h + yy) * w + xx) * 3;
+            float v[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { float x = (float)px[c] / 255.0f; v[c] = normalize ? 2.0f * x - 1.0f : x; }
+            __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], 0.0f);
+            u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        }
+        out[i] = u;
+    }
+}
+
 // ---- VaeImageProcessor.postprocess: clamp(x/2+0.5,0,1) -> round(x*255) -> u8 ----
 __global__ void __launch_bounds__(256) k_post(const __half* __restrict__ in, int ld, uint8_t* __restrict__ out, long long npix) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
@@ -165,6 +185,12 @@ extern "C" int fie_preprocess_u8_to_f16(const void* img, void* out, int n, int h
     long long npix = (long long)n * h * w;
     k_pre<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img, (__half*)out, npix, c_out, normalize);
     return check_launch("fie_preprocess_u8_to_f16");
+}
+extern "C" int fie_preprocess_u8_to_f16_pad8(const void* img, void* out, int n, int h, int w, int normalize, void* stream) {
+    FIE_REQUIRE(img && out && n > 0 && h > 0 && w > 0, "fie_preprocess_u8_to_f16_pad8: bad args");
+    const long long total = (long long)n * (h + 2) * (w + 8);
+    k_pre_pad8<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img, (uint4*)out, n, h, w, normalize);
+    return check_launch("fie_preprocess_u8_to_f16_pad8");
 }
 extern "C" int fie_postprocess_f16_to_u8(const void* x, int ld, void* out, int n, int h, int w, void* stream) {
     FIE_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && ld >= 3, "fie_postprocess_f16_to_u8: bad args");

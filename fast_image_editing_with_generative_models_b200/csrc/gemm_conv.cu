@@ -15,17 +15,29 @@
 // Epilogue: 4 warps read TMEM (tcgen05.ld 32x32b), fuse bias / time-embedding broadcast / SiLU / GEGLU /
 //           scale / residual, and store fp16 (or fp32) rows.
 //
-// Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-11 epilogue.
+// Warp roles (384 threads): w0-7 epilogue, w8 TMA producer, w9 MMA issuer, w10 TMEM allocator, w11 idle.
 #include "tc_common.cuh"
 
+#ifndef FIE_GEMM_SETMAXNREG
+#define FIE_GEMM_SETMAXNREG 1
+#endif
+
 namespace fie {
+
+// Warp roles.  The epilogue warps get the LOW warp ids: the SM's warp scheduler favours higher ids among ready warps, and the
+// single-thread TMA producer / MMA issuer must never wait behind eight ALU-busy epilogue warps.
+#ifndef FIE_GEMM_ROLES_HIGH
+#define FIE_GEMM_ROLES_HIGH 1
+#endif
+constexpr int W_EPI0 = FIE_GEMM_ROLES_HIGH ? 0 : 4;        // first of the 8 epilogue warps
+constexpr int W_PROD = FIE_GEMM_ROLES_HIGH ? 8 : 0, W_MMA = W_PROD + 1, W_ALLOC = W_PROD + 2;
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 192 * 1024;      // pipeline stages
-constexpr int EPI_STAGE_BYTES = 8 * 2048;      // per-epilogue-warp 32x32 fp16 transpose buffers
+constexpr int EPI_STAGE_BYTES = 8 * 1024;      // per-epilogue-warp bias staging (8 slots x 32 fp32)
 
 struct GemmParams {
     CUtensorMap a_maps[4];
@@ -44,6 +56,7 @@ struct GemmParams {
     int kps;          // 64-wide K blocks per pipeline stage (1 or 2)
     int mt;           // 128-row M sub-tiles per CTA (1 or 2)
     int dbg;          // debug/tuning: 1 = skip TMA loads, 2 = skip MMA issue, 4 = skip epilogue math/stores
+    long long* trace; // debug: per-CTA wait-time accounting [grid][8] (see fie_gemm_trace), or NULL
     int num_m_blocks, num_n_blocks;   // m blocks of 128*cg rows
     int num_stages;
     int tmem_cols;
@@ -100,10 +113,49 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, in
     }
 }
 
+// Out-of-line generic epilogue for one 32-column chunk of one accumulator row per thread: partial chunks at the N edge,
+// fp32 output, unaligned leading dimensions.  Rare; kept out of the hot loop on purpose.
+__device__ __noinline__ void epi_slow_chunk(const GemmParams& p, uint32_t taddr, uint32_t taddr_gate, int ngate, long long m, bool row_ok,
+                                            int nacc, int nout, float mb, const float* rb) {
+    uint32_t r[32];
+    float v[32];
+    tmem_ld_32x32(taddr, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + mb;
+    if (p.col_bias) for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(p.col_bias + nacc + i);
+    if (rb) for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(rb + nacc + i);
+    if (p.act == FIE_ACT_GEGLU) {
+        tmem_ld_32x32(taddr_gate, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float gate = __uint_as_float(r[i]);
+            if (p.col_bias && ngate + i < p.N) gate += __ldg(p.col_bias + ngate + i);
+            v[i] *= gelu_erf_f(gate);
+        }
+    } else if (p.act == FIE_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+    if (row_ok && nout < p.n_store) {
+        if (p.residual) {
+            const __half* rp = p.residual + m * p.ld_res + nout;
+            for (int i = 0; i < 32; ++i) if (nout + i < p.n_store) v[i] += __half2float(rp[i]);
+        }
+        store_chunk(p, m, nout, v);
+    }
+}
+
+// Debug accounting: clock cycles a role spends blocked on a barrier (only when a trace buffer is installed).
+#define FIE_TIMED(acc, stmt) do { if (p.trace) { const long long t0_ = clock64(); stmt; (acc) += clock64() - t0_; } else { stmt; } } while (0)
+
 // CG = 1: one CTA per tile (M = 128).  CG = 2: CTA pair (cta_group::2), tile M = 256, each CTA loads half of B.
 // KPS = 64-wide K blocks per pipeline stage (per producer/consumer mbarrier handshake).
 // MT = 128-row M sub-tiles per CTA that share every B tile (narrow-N problems: twice the MMA work per handshake).
-template <int CG, int KPS, int MT>
+template <int CG, int KPS, int MT, int GEGLU>
 __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned by the ABI; round up to 1024 for the 128B swizzle
@@ -112,7 +164,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* epi_smem = smem + SMEM_BUDGET;        // [8 warps][32 rows][64 B], 16-byte pieces XOR-swizzled by (row >> 1) & 3
+    uint8_t* epi_smem = smem + SMEM_BUDGET;        // [8 epilogue warps][8 bias slots][32 fp32]
     const int block_n = p.block_n;
     const int b_rows = block_n / CG;                                   // B rows held by this CTA
     const int b_sub_bytes = b_rows * BLOCK_K * 2;
@@ -124,22 +176,30 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     const bool leader = cta_rank == 0;
     const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_PROD && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
         tma_prefetch_desc(&p.b_map);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8 * CG); }
         mbar_fence_init();
     }
-    if (warp == 2) { if (CG == 2) tmem_alloc_2sm(&tmem_base_slot, (uint32_t)p.tmem_cols); else tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols); }
+    if (warp == W_ALLOC) { if (CG == 2) tmem_alloc_2sm(&tmem_base_slot, (uint32_t)p.tmem_cols); else tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols); }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    long long tr_wait = 0, tr_wait2 = 0;
+    const long long tr_start = p.trace ? clock64() : 0;
 
-    if (warp == 0) {
+    // Register re-partition (384 threads x 168 at launch): the producer / MMA / allocator warpgroup keeps 56 registers per
+    // thread, the two epilogue warpgroups get 224 so that the epilogue math has the ILP to stay off the critical path.
+    if (warp >= W_PROD && warp < W_PROD + 4) {
+#if FIE_GEMM_SETMAXNREG
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+#endif
+    if (warp == W_PROD) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -158,7 +218,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                     }
                 }
                 for (int sb = 0; sb < num_sb; ++sb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    FIE_TIMED(tr_wait, mbar_wait(&empty_bar[stage], phase ^ 1));
                     uint8_t* sbase = smem + (size_t)stage * stage_bytes;
                     if (p.dbg & 1) {
                         if (CG == 1 || leader) mbar_arrive(&full_bar[stage]);
@@ -193,18 +253,19 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.trace) { p.trace[blockIdx.x * 8 + 0] = tr_wait; p.trace[blockIdx.x * 8 + 1] = clock64() - tr_start; }
         }
-    } else if (warp == 1 && leader) {
+    } else if (warp == W_MMA && leader) {
         // ===================== MMA issuer (leader CTA of the pair) =====================
         const uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, block_n);
         int stage = 0; uint32_t phase = 0; int it = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-            if (CG == 2) mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1); else mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+            FIE_TIMED(tr_wait2, if (CG == 2) mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1); else mbar_wait(&tmem_empty[buf], acc_phase ^ 1));
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * MT * block_n);
             for (int sb = 0; sb < num_sb; ++sb) {
-                mbar_wait(&full_bar[stage], phase);
+                FIE_TIMED(tr_wait, mbar_wait(&full_bar[stage], phase));
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -230,135 +291,184 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+        if (p.trace && lane == 0) { p.trace[blockIdx.x * 8 + 2] = tr_wait; p.trace[blockIdx.x * 8 + 3] = tr_wait2; p.trace[blockIdx.x * 8 + 4] = clock64() - tr_start; }
+    }
+    } else {
+#if FIE_GEMM_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+#endif
         // ===================== Epilogue: 8 warps, two per TMEM lane quadrant (even / odd 32-column chunks) =====================
+        // Work item = one 32-row x 32-column chunk of the accumulator; a thread owns one row of it (TMEM lane == row), i.e.
+        // 64 contiguous bytes of fp16 output, moved as two 256-bit global accesses (full 32-byte sectors, no shared-memory
+        // transpose: the main loop already saturates the shared-memory bandwidth with TMA writes + MMA operand reads).
+        // The hot path (fp16 output, full chunk, 32-byte aligned rows) is straight-line code; everything else goes through
+        // the out-of-line epi_slow_chunk.
         const int ew = warp & 3;                       // TMEM lane quadrant accessible to this warp
-        const int cpar = (warp - 4) >> 2;              // 0: even chunks, 1: odd chunks
-        const int row_in_tile = ew * 32 + lane;
+        const int cpar = (warp - W_EPI0) >> 2;              // 0: even chunks, 1: odd chunks
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-        const bool geglu = p.act == FIE_ACT_GEGLU;
-        const int half_n = block_n >> 1;
+        const int ncols_tile = GEGLU ? (block_n >> 1) : block_n;      // output columns per tile
+        const int nchunks = ncols_tile / 32;
+        const bool fast_cfg = !p.out_f32 && (p.ldd & 15) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 31) == 0 &&
+                              (!p.residual || ((p.ld_res & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0)) &&
+                              (!p.row_bias || (p.rows_per_group & 31) == 0);
+        const bool res_fast = fast_cfg && p.residual != nullptr;
+        auto chunk_fast = [&](int n_blk_, int c_) -> bool {
+            return fast_cfg && n_blk_ * ncols_tile + c_ * 32 + 32 <= p.n_store && n_blk_ * block_n + (GEGLU ? (block_n >> 1) : 0) + c_ * 32 + 32 <= p.N;
+        };
+        auto row_of = [&](int tile_, int mt_) -> long long {
+            return (((long long)(tile_ / p.num_n_blocks) * MT + mt_) * CG + cta_rank) * BLOCK_M + ew * 32 + lane;
+        };
+        // Residual prefetch: this thread's 64 bytes of the NEXT item's residual block are requested before the current item
+        // is processed (across tiles: before the wait on the accumulator), so the L2 latency is off the critical path.
+        uint32_t pre0[8], pre1[8], prf0[8], prf1[8];     // residual of item +1 and of item +2
+        auto issue_res = [&](int tile_, int mt_, int c_, uint32_t (&d0)[8], uint32_t (&d1)[8]) {
+            if (tile_ >= num_tiles || c_ >= nchunks || !chunk_fast(tile_ % p.num_n_blocks, c_)) return;
+            const long long m_ = row_of(tile_, mt_);
+            if (m_ < p.M) {
+                const __half* rp = p.residual + m_ * p.ld_res + (tile_ % p.num_n_blocks) * ncols_tile + c_ * 32;
+                ldg256(rp, d0); ldg256(rp + 16, d1);
+            }
+        };
+        auto next_item = [&](int& tile_, int& mt_, int& c_) {       // order in which this warp visits its chunks
+            if (c_ + 2 < nchunks) c_ += 2;
+            else if (mt_ + 1 < MT) { ++mt_; c_ = cpar; }
+            else { tile_ += tile_step; mt_ = 0; c_ = cpar; }
+        };
+        // Bias staging.  With ~210 KB of shared memory the L1 is tiny, so every bias load is an L2 round trip; instead of paying
+        // it per chunk, lane i fetches element i of each of this warp's chunks for the NEXT (tile, mt) group into registers
+        // while the current group is processed, then parks them in the warp's private staging area, where the hot loop reads
+        // them back as broadcast 128-bit shared loads.  Slots 0-3: value columns (col_bias + row_bias), 4-7: GEGLU gate columns.
+        const uint32_t bias_s = smem_u32(epi_smem) + (uint32_t)(warp - W_EPI0) * 1024u;
+        float nb_col[4], nb_row[4], nb_gate[4];
+        auto bias_issue = [&](int tile_, int mt_) {
+            if (!fast_cfg || tile_ >= num_tiles) return;
+            const int n_blk_ = tile_ % p.num_n_blocks;
+            const long long mw_ = row_of(tile_, mt_) - lane;
+            const float* rbp = (p.row_bias && mw_ < p.M) ? p.row_bias + (mw_ / p.rows_per_group) * p.ld_row_bias : nullptr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n_ = n_blk_ * block_n + (cpar + 2 * j) * 32 + lane;
+                const bool in = cpar + 2 * j < nchunks && n_ < p.N;
+                nb_col[j] = (p.col_bias && in) ? __ldg(p.col_bias + n_) : 0.0f;
+                nb_row[j] = (rbp && in) ? __ldg(rbp + n_) : 0.0f;
+                if (GEGLU) nb_gate[j] = (p.col_bias && in && n_ + (block_n >> 1) < p.N) ? __ldg(p.col_bias + n_ + (block_n >> 1)) : 0.0f;
+            }
+        };
+        auto bias_commit = [&]() {
+            if (!fast_cfg) return;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + j * 128 + lane * 4), "f"(nb_col[j] + nb_row[j]) : "memory");
+                if (GEGLU) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (4 + j) * 128 + lane * 4), "f"(nb_gate[j]) : "memory");
+            }
+            __syncwarp();
+        };
+        bias_issue(first_tile, 0);
+        if (res_fast) {
+            int t_ = first_tile, m_ = 0, c_ = cpar;
+            issue_res(t_, m_, c_, pre0, pre1);
+            next_item(t_, m_, c_);
+            issue_res(t_, m_, c_, prf0, prf1);
+        }
         int it = 0;
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-            const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
-            mbar_wait(&tmem_full[buf], acc_phase);
+            const int n_blk = tile % p.num_n_blocks;
+            FIE_TIMED(tr_wait, mbar_wait(&tmem_full[buf], acc_phase));
             tc_fence_after();
-            const int nchunks = (geglu ? half_n : block_n) / 32;
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
-            const long long m = (((long long)m_blk * MT + mt) * CG + cta_rank) * BLOCK_M + row_in_tile;
-            const bool row_ok = m < p.M;
-            const uint32_t tacc = tmem_base + lane_addr + (uint32_t)((buf * MT + mt) * block_n);
-            const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
-            const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
-            const long long m_w0 = m - lane;                       // first row of this warp
-            for (int c = cpar; c < ((p.dbg & 4) ? 0 : nchunks); c += 2) {
-                uint32_t r[32];
-                float v[32];
-
-                tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
-                tmem_ld_wait();
-                const int nacc = n_blk * block_n + c * 32;        // accumulator column (B row) of v[0]
-                const bool full = nacc + 32 <= p.N;
+                const long long m = row_of(tile, mt);
+                const bool row_ok = m < p.M;
+                const uint32_t tacc = tmem_base + lane_addr + (uint32_t)((buf * MT + mt) * block_n);
+                const float mb = (p.m_bias && row_ok) ? p.m_bias[m] : 0.0f;
+                const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
+                __half* orow = reinterpret_cast<__half*>(p.D) + out_row(p, row_ok ? m : 0) * p.ldd;
+                bias_commit();                                         // this group's biases -> staging; then fetch the next group's
+                if (mt + 1 < MT) bias_issue(tile, mt + 1); else bias_issue(tile + tile_step, 0);
+#pragma unroll 1
+                for (int c = cpar; c < ((p.dbg & 4) ? 0 : nchunks); c += 2) {
+                    const int nacc = n_blk * block_n + c * 32;        // accumulator column (B row) of element 0
+                    const int nout = n_blk * ncols_tile + c * 32;     // output column of element 0
+                    uint32_t res0[8], res1[8];
+                    if (res_fast) {                                   // advance the prefetch queue on EVERY item (fast or not)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + mb;
-                if (p.col_bias) {
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.col_bias + nacc) + i); v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w; }
-                    } else {
-                        for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(p.col_bias + nacc + i);
+                        for (int i = 0; i < 8; ++i) { res0[i] = pre0[i]; res1[i] = pre1[i]; pre0[i] = prf0[i]; pre1[i] = prf1[i]; }
+                        int t_ = tile, m_ = mt, c_ = c;
+                        next_item(t_, m_, c_); next_item(t_, m_, c_);
+                        issue_res(t_, m_, c_, prf0, prf1);
                     }
-                }
-                if (rb) {
-                    if (full && ((p.ld_row_bias | nacc) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.row_bias) & 15) == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { const float4 b4 = __ldg(reinterpret_cast<const float4*>(rb + nacc) + i); v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w; }
-                    } else {
-                        for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(rb + nacc + i);
+                    if (!chunk_fast(n_blk, c)) {
+                        epi_slow_chunk(p, tacc + (uint32_t)(c * 32), GEGLU ? tacc + (uint32_t)((block_n >> 1) + c * 32) : 0u, GEGLU ? nacc + (block_n >> 1) : 0,
+                                       m, row_ok, nacc, nout, mb, rb);
+                        continue;
                     }
-                }
-                int nout = nacc;
-                if (geglu) {
-                    uint32_t g[32];
-                    tmem_ld_32x32(tacc + (uint32_t)(half_n + c * 32), g);
-                    tmem_ld_wait();
-                    const int ng = nacc + half_n;
+                    const uint32_t bslot = bias_s + (uint32_t)(((c - cpar) >> 1) * 128);
+                    float v[32];
+                    if (GEGLU) {
+                        uint32_t r[32], g[32];
+                        tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
+                        tmem_ld_32x32(tacc + (uint32_t)((block_n >> 1) + c * 32), g);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        float gate = __uint_as_float(g[i]);
-                        if (p.col_bias && ng + i < p.N) gate += __ldg(p.col_bias + ng + i);
-                        v[i] *= gelu_erf_f(gate);
-                    }
-                    nout = n_blk * half_n + c * 32;
-                } else if (p.act == FIE_ACT_SILU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-                }
-                if (p.scale != 1.0f) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-                }
-                const bool fast = !p.out_f32 && nout + 32 <= p.n_store && (p.ldd & 7) == 0 && (!p.residual || (p.ld_res & 7) == 0);
-                if (fast) {
-                    // Coalesced path: a warp instruction moves 8 rows x 64 contiguous bytes instead of 32 rows x 16 bytes.
-                    uint8_t* stg = epi_smem + (warp - 4) * 2048;
-                    const int own = lane * 64, osw = (lane >> 1) & 3;
-                    if (p.residual) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const int rr = (lane >> 2) + 8 * t, pc = lane & 3;
-                            const long long mr = m_w0 + rr;
-                            uint4 u = make_uint4(0, 0, 0, 0);
-                            if (mr < p.M) u = __ldg(reinterpret_cast<const uint4*>(p.residual + mr * p.ld_res + nout) + pc);
-                            *reinterpret_cast<uint4*>(stg + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4)) = u;
+                        for (int i = 0; i < 8; ++i) {
+                            const uint4 bv = lds128(bslot + i * 16), bg = lds128(bslot + 512 + i * 16);
+                            v[4 * i] = (__uint_as_float(r[4 * i]) + __uint_as_float(bv.x)) * gelu_erf_f(__uint_as_float(g[4 * i]) + __uint_as_float(bg.x));
+                            v[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) + __uint_as_float(bv.y)) * gelu_erf_f(__uint_as_float(g[4 * i + 1]) + __uint_as_float(bg.y));
+                            v[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) + __uint_as_float(bv.z)) * gelu_erf_f(__uint_as_float(g[4 * i + 2]) + __uint_as_float(bg.z));
+                            v[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) + __uint_as_float(bv.w)) * gelu_erf_f(__uint_as_float(g[4 * i + 3]) + __uint_as_float(bg.w));
                         }
-                        __syncwarp();
+                    } else {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tacc + (uint32_t)(c * 32), r);
+                        tmem_ld_wait();
 #pragma unroll
-                        for (int pc = 0; pc < 4; ++pc) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(stg + own + ((pc ^ osw) << 4));
-                            const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); v[8 * pc + 2 * j] += f.x; v[8 * pc + 2 * j + 1] += f.y; }
+                        for (int i = 0; i < 8; ++i) {
+                            const uint4 bv = lds128(bslot + i * 16);
+                            v[4 * i] = __uint_as_float(r[4 * i]) + __uint_as_float(bv.x); v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + __uint_as_float(bv.y);
+                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + __uint_as_float(bv.z); v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + __uint_as_float(bv.w);
                         }
-                        __syncwarp();
-                    }
+                        if (p.act == FIE_ACT_SILU) {
 #pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
-                        uint4 u;
-                        __half2 h0 = __floats2half2_rn(v[8 * pc], v[8 * pc + 1]), h1 = __floats2half2_rn(v[8 * pc + 2], v[8 * pc + 3]);
-                        __half2 h2 = __floats2half2_rn(v[8 * pc + 4], v[8 * pc + 5]), h3 = __floats2half2_rn(v[8 * pc + 6], v[8 * pc + 7]);
-                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(stg + own + ((pc ^ osw) << 4)) = u;
+                            for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+                        }
                     }
-                    __syncwarp();
+                    if (p.m_bias) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int rr = (lane >> 2) + 8 * t, pc = lane & 3;
-                        const long long mr = m_w0 + rr;
-                        const uint4 u = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((pc ^ ((rr >> 1) & 3)) << 4));
-                        if (mr < p.M) *(reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.D) + out_row(p, mr) * p.ldd + nout) + pc) = u;
+                        for (int i = 0; i < 32; ++i) v[i] += mb;        // (GEGLU with a per-row bias is not a supported combination)
                     }
-                    __syncwarp();
-                } else if (row_ok && nout < p.n_store) {
-                    if (p.residual) {
-                        const __half* rp = p.residual + m * p.ld_res + nout;
-                        for (int i = 0; i < 32; ++i) if (nout + i < p.n_store) v[i] += __half2float(rp[i]);
+                    if (p.scale != 1.0f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] *= p.scale;
                     }
-                    store_chunk(p, m, nout, v);
+                    if (res_fast && row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&res0[i])); v[2 * i] += f.x; v[2 * i + 1] += f.y;
+                            f = __half22float2(*reinterpret_cast<const __half2*>(&res1[i])); v[16 + 2 * i] += f.x; v[16 + 2 * i + 1] += f.y;
+                        }
+                    }
+                    if (row_ok) {
+                        uint32_t o0[8], o1[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); o0[i] = *reinterpret_cast<uint32_t*>(&h);
+                            h = __floats2half2_rn(v[16 + 2 * i], v[16 + 2 * i + 1]); o1[i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        stg256(orow + nout, o0); stg256(orow + nout + 16, o1);
+                    }
                 }
-            }
             }   // mt
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (CG == 2) mbar_arrive_remote(&tmem_empty[buf], 0); else mbar_arrive(&tmem_empty[buf]); }
+            if (lane == 0) { if (CG == 2) mbar_arrive_remote_relaxed(&tmem_empty[buf], 0); else mbar_arrive_relaxed(&tmem_empty[buf]); }
         }
+        if (p.trace && warp == W_EPI0 && lane == 0) { p.trace[blockIdx.x * 8 + 5] = tr_wait; p.trace[blockIdx.x * 8 + 6] = clock64() - tr_start; }
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's MMAs read this CTA's shared memory until the very end
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         tc_fence_after();
         if (CG == 2) tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
@@ -414,6 +524,7 @@ static int g_force_bn = 0;
 static int g_dbg = 0;
 static int g_force_kps = 0;
 static int g_force_mt = 0;
+static long long* g_trace = nullptr;
 static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out, int* mt_out) {
     if (g_force_cg < 0) { const char* s = getenv("FIE_GEMM_CG"); g_force_cg = s ? atoi(s) : 0; }
     const int sms = num_sms();
@@ -457,6 +568,7 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
 static int launch(GemmParams& p, cudaStream_t stream) {
     const int cg = p.cg;
     p.dbg = g_dbg;
+    p.trace = g_trace;
     const int mt = p.mt;
     int kps = (g_force_kps > 0) ? g_force_kps : (p.num_kb >= 4 ? 2 : 1);
     if (kps == 2 && SMEM_BUDGET / (2 * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2)) < 2) kps = 1;
@@ -470,17 +582,19 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     size_t smem = (size_t)SMEM_BUDGET + EPI_STAGE_BYTES + 1024;
     // (>113 KiB of dynamic smem: one CTA per SM, so a 512-column TMEM allocation can never deadlock)
     typedef void (*KernelFn)(GemmParams);
-    static const KernelFn kernels[2][2][2] = {{{k_gemm_conv<1, 1, 1>, k_gemm_conv<1, 1, 2>}, {k_gemm_conv<1, 2, 1>, k_gemm_conv<1, 2, 2>}},
-                                              {{k_gemm_conv<2, 1, 1>, k_gemm_conv<2, 1, 2>}, {k_gemm_conv<2, 2, 1>, k_gemm_conv<2, 2, 2>}}};
+#define FIE_K(cg, kps, mt) {k_gemm_conv<cg, kps, mt, 0>, k_gemm_conv<cg, kps, mt, 1>}
+    static const KernelFn kernels[2][2][2][2] = {{{FIE_K(1, 1, 1), FIE_K(1, 1, 2)}, {FIE_K(1, 2, 1), FIE_K(1, 2, 2)}},
+                                                 {{FIE_K(2, 1, 1), FIE_K(2, 1, 2)}, {FIE_K(2, 2, 1), FIE_K(2, 2, 2)}}};
+#undef FIE_K
     static bool attr_set = false;
     if (!attr_set) {
-        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) {
-            cudaError_t e = cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
+        for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) for (int d = 0; d < 2; ++d) {
+            cudaError_t e = cudaFuncSetAttribute(kernels[a][b][c][d], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gemm_conv): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
         }
         attr_set = true;
     }
-    KernelFn fn = kernels[cg - 1][kps - 1][mt - 1];
+    KernelFn fn = kernels[cg - 1][kps - 1][mt - 1][p.act == FIE_ACT_GEGLU ? 1 : 0];
     const int tiles = p.num_m_blocks * p.num_n_blocks;
     const int slots = num_sms() / cg;
     const int grid = cg * (tiles < slots ? tiles : slots);
@@ -500,6 +614,11 @@ static int launch(GemmParams& p, cudaStream_t stream) {
 using namespace fie;
 
 extern "C" void fie_tune_gemm(int force_cg, int force_block_n) { fie::g_force_cg = force_cg & 3; fie::g_force_kps = (force_cg >> 2) & 3; fie::g_dbg = (force_cg >> 4) & 15; fie::g_force_mt = (force_cg >> 8) & 3; fie::g_force_bn = force_block_n; }
+
+// Debug: install (or clear, with NULL) a device buffer of 8 x int64 per CTA that the next GEMM launches fill with
+// [0] producer cycles blocked on "empty", [1] producer total, [2] MMA issuer blocked on "full", [3] on the accumulator buffer,
+// [4] issuer total, [5] epilogue warp 4 blocked on "accumulator full", [6] epilogue total.
+extern "C" void fie_gemm_trace(long long* device_buf) { fie::g_trace = device_buf; }
 
 extern "C" int fie_geglu_block_n(int N) { return (N % 256) == 0 ? 256 : ((N % 128) == 0 ? 128 : 64); }
 
@@ -653,4 +772,49 @@ extern "C" int fie_conv_up2x_f16(const void* x, const void* wgt, void* out, long
         if ((rc = launch(p, (cudaStream_t)stream))) return rc;
     }
     return FIE_OK;
+}
+
+// 3x3 convolution of an image-like input with <= 8 channels (conv_in of the VAE encoder and of the ControlNet conditioning
+// embedding at full resolution) on the tensor cores.  The input is stored zero-padded as xp[n][h+2][w+8][8] fp16 (real pixel
+// (y, x) at (y+1, x+1); see fie_preprocess_u8_to_f16_pad8), so the 3 pixels x 8 channels one kernel row needs for output pixel x are
+// 24 contiguous fp16 starting at padded pixel x.  The A operand is an OVERLAPPING TMA view: dimension 0 = 64 contiguous fp16
+// (8 padded pixels, of which the first 3 carry non-zero weights), dimension 1 = start pixel with a 16-byte stride.  K = 3 kernel
+// rows x 64, so the generic implicit-GEMM kernel runs unchanged with 3 "taps" of one K block each.
+// wgt: fp16 [cout][3][64], element (kh, kw*8 + c) = w[co][c][kh][kw] (zeros elsewhere).
+extern "C" int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, long long ldd, int n, int h, int w, int cout,
+                                  int cout_valid, const fie_epilogue* ep, void* stream) {
+    FIE_REQUIRE(xp && wgt && out, "fie_conv3x3_c8_f16: null pointer");
+    FIE_REQUIRE(n > 0 && h > 0 && w > 0 && cout > 0 && (cout % 32) == 0, "fie_conv3x3_c8_f16: bad shape (cout must be a multiple of 32)");
+    int bw, bh, bn;
+    if (w >= 128) { FIE_REQUIRE((w % 128) == 0, "fie_conv3x3_c8_f16: width %d must be a multiple of 128", w); bw = 128; bh = 1; bn = 1; }
+    else {
+        FIE_REQUIRE((128 % w) == 0, "fie_conv3x3_c8_f16: width %d must divide 128", w);
+        bw = w; bh = 128 / w;
+        if (bh <= h) { FIE_REQUIRE((h % bh) == 0, "fie_conv3x3_c8_f16: height %d not a multiple of %d", h, bh); bn = 1; }
+        else { FIE_REQUIRE((bh % h) == 0, "fie_conv3x3_c8_f16: height %d must divide %d", h, bh); bn = bh / h; bh = h; }
+    }
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    const long long M = (long long)n * h * w;
+    int rc = fill_epilogue(p, ep, M, cout, out, ldd);
+    if (rc) return rc;
+    FIE_REQUIRE(p.act != FIE_ACT_GEGLU, "fie_conv3x3_c8_f16: GEGLU epilogue not supported for conv");
+    p.mode = 1; p.M = M; p.N = cout; p.OH = h; p.OW = w;
+    pick_config(M, cout, false, &p.cg, &p.block_n, &p.mt);
+    p.num_m_blocks = (int)((M + BLOCK_M * p.cg * p.mt - 1) / (BLOCK_M * p.cg * p.mt));
+    p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
+    p.kb_per_tap = 1; p.num_kb = 3; p.kb_split = 3;
+    p.n_store = cout_valid > 0 ? cout_valid : cout;
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    const uint64_t wp = (uint64_t)w + 8, hp = (uint64_t)h + 2;
+    const uint64_t dims[4] = {BLOCK_K, (uint64_t)w, hp, (uint64_t)n};
+    const uint64_t strides[3] = {16, wp * 16, hp * wp * 16};
+    if ((rc = make_tmap_f16(&p.a_maps[0], xp, 4, dims, strides, box))) return rc;
+    p.a_maps[1] = p.a_maps[0]; p.a_maps[2] = p.a_maps[0]; p.a_maps[3] = p.a_maps[0];
+    for (int t = 0; t < 3; ++t) { p.tap_map[t] = 0; p.tap_dh[t] = (int8_t)t; p.tap_dw[t] = 0; }   // padded row y + kh, padded pixel x
+    const uint64_t bdims[2] = {(uint64_t)3 * BLOCK_K, (uint64_t)cout};
+    const uint64_t bstr[1] = {(uint64_t)3 * BLOCK_K * 2};
+    const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(p.block_n / p.cg)};
+    if ((rc = make_tmap_f16(&p.b_map, wgt, 2, bdims, bstr, bbox))) return rc;
+    return launch(p, (cudaStream_t)stream);
 }

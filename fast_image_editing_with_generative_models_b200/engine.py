@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from .configs import ControlNetConfig, UNetConfig, VAEConfig, skip_channels
-from .weights import fuse_lora, pack_conv3x3, pack_conv_up2x, pack_geglu
+from .weights import fuse_lora, pack_conv3x3, pack_conv3x3_c8, pack_conv_up2x, pack_geglu
 
 Tensor = torch.Tensor
 Params = Dict[str, Tensor]
@@ -81,6 +81,16 @@ class _Packer:
         out = torch.zeros((w.shape[0], 3, 3, 4), dtype=torch.float32, device=self.dev)
         out[..., : w.shape[1]] = w.permute(0, 2, 3, 1)
         return out.contiguous(), self.b(name)
+
+    def c8(self, name: str, pad_cout_to=None) -> Tuple[Tensor, Optional[Tensor]]:
+        """[Cout, Cin<=8, 3, 3] -> fp16 [Cout_p, 192] for the tensor-core conv_in on a zero-padded 8-channel image."""
+        w = pack_conv3x3_c8(self.w(name), pad_cout_to)
+        b = self.b(name)
+        if b is not None and pad_cout_to and pad_cout_to > b.numel():
+            bp = torch.zeros(pad_cout_to, dtype=torch.float32, device=self.dev)
+            bp[: b.numel()] = b
+            b = bp
+        return w, b
 
     def norm(self, name: str) -> Tuple[Tensor, Tensor]:
         return self.p[self.prefix + name + ".weight"].to(self.dev, torch.float32).contiguous(), self.b(name)
@@ -303,7 +313,7 @@ class ControlNet:
         self.enc = _EncoderPart(pk, cfg.unet)
         cc = list(cfg.cond_channels)
         pads = [_pad64(c) for c in cc]
-        self.cond_in = pk.cin4("controlnet_cond_embedding.conv_in")
+        self.cond_in = pk.c8("controlnet_cond_embedding.conv_in", pads[0])
         self.cond_blocks = []
         for i in range(len(cc) - 1):
             self.cond_blocks.append((pk.conv3(f"controlnet_cond_embedding.blocks.{2 * i}", pads[i], pads[i]), 1))
@@ -318,9 +328,9 @@ class ControlNet:
     def prepare_prompt(self, ctx, text_embeds, time_ids):
         return self.enc.prepare_prompt(ctx, text_embeds, time_ids)
 
-    def cond_embedding(self, cond4: Tensor) -> Tensor:
-        """cond4: [N,H,W,4] fp16 in {0,1} (3 real channels).  Step-invariant: computed once per image."""
-        h = ops.conv3x3_cin4(cond4, self.cond_in[0], self.cond_in[1], self.cond_c0, ld_out=self.cond_pad0, act=ops.ACT_SILU)
+    def cond_embedding(self, cond_p8: Tensor) -> Tensor:
+        """cond_p8: zero-padded [N,H+2,W+8,8] fp16 control image in {0,1} (ops.preprocess_pad8).  Step-invariant: once per image."""
+        h = ops.conv3x3_c8(cond_p8, self.cond_in[0], col_bias=self.cond_in[1], act=ops.ACT_SILU)   # padded channels: silu(0) = 0
         for (w, b), stride in self.cond_blocks:
             h = ops.conv3x3(h, w, stride=stride, pad_mode=0, col_bias=b, act=ops.ACT_SILU)
         return ops.conv3x3(h, self.cond_out[0], col_bias=self.cond_out[1])
@@ -376,7 +386,7 @@ class VAE:
         ch = list(cfg.block_out_channels)
         L = cfg.latent_channels
         # ---- encoder ----
-        self.e_in = pk.cin4("encoder.conv_in")
+        self.e_in = pk.c8("encoder.conv_in")
         self.e_down = []
         for i in range(len(ch)):
             res = [Resnet(pk, f"encoder.down_blocks.{i}.resnets.{j}", eps, g) for j in range(cfg.layers_per_block)]
@@ -403,10 +413,10 @@ class VAE:
         self.d_norm = pk.norm("decoder.conv_norm_out")
         self.d_out = pk.conv3("decoder.conv_out", pad_cout_to=32)
 
-    def encode_moments(self, x4: Tensor) -> Tensor:
-        """x4 [N,H,W,4] fp16 in [-1,1] (3 real channels) -> moments [N,H/8,W/8,2L] fp16."""
+    def encode_moments(self, xp8: Tensor) -> Tensor:
+        """xp8: zero-padded [N,H+2,W+8,8] fp16 image in [-1,1] (ops.preprocess_pad8) -> moments [N,H/8,W/8,2L] fp16."""
         cfg = self.cfg
-        h = ops.conv3x3_cin4(x4, self.e_in[0], self.e_in[1], cfg.block_out_channels[0])
+        h = ops.conv3x3_c8(xp8, self.e_in[0], col_bias=self.e_in[1])
         for res, ds in self.e_down:
             for r in res:
                 h = r(h)

@@ -102,6 +102,16 @@ def preprocess(img_u8: torch.Tensor, c_out: int = 4, normalize: bool = True) -> 
     return out
 
 
+def preprocess_pad8(img_u8: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """uint8 [N,H,W,3] -> fp16 zero-padded [N,H+2,W+8,8] (input layout of :func:`conv3x3_c8`)."""
+    _req(img_u8, torch.uint8, "preprocess_pad8")
+    n, h, w, _ = img_u8.shape
+    out = torch.empty((n, h + 2, w + 8, 8), dtype=torch.float16, device=img_u8.device)
+    check(_lib.lib().fie_preprocess_u8_to_f16_pad8(_p(img_u8), _p(out), n, h, w, int(normalize), _stream()), "fie_preprocess_u8_to_f16_pad8")
+    _count()
+    return out
+
+
 def postprocess(x: torch.Tensor) -> torch.Tensor:
     """fp16 [N,H,W,C>=3] -> uint8 [N,H,W,3]."""
     _req(x, torch.float16, "postprocess")
@@ -256,6 +266,23 @@ def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional
     with _prof("conv_up2x", 2.0 * n * 4 * h * wd * cout * 4 * cin, "FLOP", f"[{n},{h},{wd},{cin}]->{cout}"):
         check(_lib.lib().fie_conv_up2x_f16(_p(x), _p(w4), _p(out), out.stride(-2), n, h, wd, cin, cout, ctypes.byref(ep), _stream()), "fie_conv_up2x_f16")
     _count(4)
+    return out
+
+
+def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] = None, col_bias=None, act=ACT_NONE) -> torch.Tensor:
+    """Tensor-core conv_in.  xp: zero-padded [N,H+2,W+8,8] fp16 (:func:`preprocess_pad8`), w: [Cout, 192] (weights.pack_conv3x3_c8)
+    -> [N,H,W,cout_valid]."""
+    _req(xp, torch.float16, "conv3x3_c8")
+    n, hp, wp, c = xp.shape
+    assert c == 8 and w.shape[1] == 192, (xp.shape, w.shape)
+    h, wd = hp - 2, wp - 8
+    cout = w.shape[0]
+    cv = cout if cout_valid is None else cout_valid
+    out = torch.empty((n, h, wd, cv), dtype=torch.float16, device=xp.device)
+    ep = _epilogue(col_bias, act=act)
+    with _prof("conv_in_c8", 2.0 * out.numel() + 2.0 * xp.numel(), "B", f"[{n},{h},{wd},8]->{cv}"):
+        check(_lib.lib().fie_conv3x3_c8_f16(_p(xp), _p(w), _p(out), out.stride(-2), n, h, wd, cout, cv, ctypes.byref(ep), _stream()), "fie_conv3x3_c8_f16")
+    _count()
     return out
 
 

@@ -53,11 +53,11 @@ class EditEngine:
         nz = [n.to(dev, torch.float16).permute(0, 2, 3, 1).contiguous() for n in noises]
         # ---- Canny control image + conditioning embedding (step-invariant) ----
         edges3 = ops.canny(images_u8, canny_low, canny_high, out_channels=3)
-        cond_emb = self.cn.cond_embedding(ops.preprocess(edges3, 4, normalize=False))
+        cond_emb = self.cn.cond_embedding(ops.preprocess_pad8(edges3, normalize=False))
         if do_cfg:
             cond_emb = torch.cat([cond_emb, cond_emb], 0)
         # ---- VAE encode -> posterior sample -> scale -> add_noise ----
-        moments = self.vae.encode_moments(ops.preprocess(images_u8, 4, normalize=True))
+        moments = self.vae.encode_moments(ops.preprocess_pad8(images_u8, normalize=True))
         sa, s1 = sched.add_noise_coeffs(timesteps[0]) if timesteps else (1.0, 0.0)
         x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)
         # ---- prompt conditioning (step-invariant): rows [neg]*B + [pos]*B as diffusers ----

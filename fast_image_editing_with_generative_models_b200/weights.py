@@ -19,6 +19,17 @@ def pack_conv3x3(w: torch.Tensor, pad_cout_to: Optional[int] = None, pad_cin_to:
     return out.reshape(op, 9 * cp).contiguous()
 
 
+def pack_conv3x3_c8(w: torch.Tensor, pad_cout_to: Optional[int] = None) -> torch.Tensor:
+    """[Cout, Cin<=8, 3, 3] -> fp16 [Cout_p, 3*64] for the tensor-core conv_in (fie_conv3x3_c8_f16): per kernel row kh a 64-wide
+    K block whose element kw*8 + c is w[co, c, kh, kw]; the other 40 positions (padded pixels 3..7 of the window) are zero."""
+    cout, cin = w.shape[:2]
+    assert cin <= 8
+    op = pad_cout_to or cout
+    out = torch.zeros((op, 3, 8, 8), dtype=torch.float16, device=w.device)        # [co][kh][pixel][channel]
+    out[:cout, :, :3, :cin] = w.permute(0, 2, 3, 1).to(torch.float16)
+    return out.reshape(op, 3 * 64).contiguous()
+
+
 def pack_conv_up2x(w: torch.Tensor) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> fp16 [4, Cout, 4*Cin]: phase (a, b) weights of nearest-2x-upsample + conv3x3.
     Output row 2i+a reads input rows {i-1, i} (a = 0) or {i, i+1} (a = 1); the 3x3 taps that fall on the same input row are

@@ -44,6 +44,9 @@ int fie_canny_u8(const void* img, void* edges, int n, int h, int w, int in_chann
  *      at reference src/pipeline.py:261-272 ---- */
 /* uint8 [n,h,w,3] -> fp16 [n,h,w,c_out] (c_out >= 3, extra channels zero): x/127.5-1 (normalize=1) or x/255 */
 int fie_preprocess_u8_to_f16(const void* img_u8, void* out_f16, int n, int h, int w, int c_out, int normalize, void* stream);
+/* uint8 [n,h,w,3] -> fp16 [n,h+2,w+8,8]: the same conversion written into the zero-padded 8-channel layout read by
+ * fie_conv3x3_c8_f16 (real pixel (y,x) at (y+1,x+1); borders and channels 3..7 are zero) */
+int fie_preprocess_u8_to_f16_pad8(const void* img_u8, void* out_f16, int n, int h, int w, int normalize, void* stream);
 /* fp16 [n,h,w,ld] (first 3 channels) -> uint8 [n,h,w,3]: round(clamp(x/2+0.5,0,1)*255) */
 int fie_postprocess_f16_to_u8(const void* x_f16, int ld, void* out_u8, int n, int h, int w, void* stream);
 
@@ -99,6 +102,10 @@ int fie_geglu_block_n(int N);
  * fie_conv3x3_f16.  Not needed in production. */
 void fie_tune_gemm(int force_cg, int force_block_n);
 
+/* Debug hook: device buffer of 8 x int64 per CTA that subsequent GEMM/conv launches fill with per-role wait-cycle
+ * accounting (see gemm_conv.cu); NULL switches it off.  Not needed in production. */
+void fie_gemm_trace(long long* device_buf);
+
 /* A: fp16 [M, K] with row stride lda (elements, multiple of 8); optional second source A1 supplies
  * K columns [k_split, K) (k_split multiple of 64) — a virtual torch.cat along K.
  * B: fp16 [N, K] row-major (ldb = K).  D: [M, N_out] row stride ldd. */
@@ -122,6 +129,12 @@ int fie_conv_up2x_f16(const void* x, const void* wgt, void* out, long long ldd, 
  * wgt: fp32 [cout][3][3][4]; bias fp32 [cout]; out fp16 [n,h,w,ld_out] (channels >= cout are zero-filled up to ld_out). */
 int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float* bias, void* out, int ld_out,
                          int n, int h, int w, int cout, int act, void* stream);
+
+/* 3x3 convolution (pad 1) of an image-like input with <= 8 channels on the tensor cores: conv_in of the VAE encoder and of
+ * the ControlNet conditioning embedding at full resolution.  xp: fp16 zero-padded [n,h+2,w+8,8] (fie_preprocess_u8_to_f16_pad8);
+ * wgt: fp16 [cout][3][64] with element (kh, kw*8 + c) = w[co][c][kh][kw], zeros elsewhere; out: [n,h,w,cout_valid..] rows of ldd. */
+int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, long long ldd, int n, int h, int w, int cout,
+                       int cout_valid, const fie_epilogue* ep, void* stream);
 
 /* ---- Flash attention, head_dim 64 (tcgen05): replaces F.scaled_dot_product_attention in AttnProcessor2_0 ----
  * q: fp16 rows [b*nq, ldq] (head h at columns h*64..), k/v: [b*nkv, ldk/ldv], out: [b*nq, ldo]. No mask. */

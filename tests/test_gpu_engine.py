@@ -38,8 +38,7 @@ def test_vae_encode_decode_tiny(cuda_dev):
     ucfg, up, ccfg, cp, vcfg, vp, _ = _models(cuda_dev)
     vae = VAE(vp, vcfg, cuda_dev)
     img = torch.from_numpy(np.stack([synthetic_image(s, 256, 256) for s in range(2)])).to(cuda_dev)
-    x4 = ops.preprocess(img, 4, True)
-    mom = vae.encode_moments(x4)
+    mom = vae.encode_moments(ops.preprocess_pad8(img, True))
     vp32 = O.to_dtype(vp, torch.float32, cuda_dev)
     ref = O.vae_encode_moments(vp32, vcfg, O.preprocess_image(img, torch.float32))
     err = float((_nchw(mom).float() - ref).abs().max())
@@ -69,9 +68,9 @@ def test_unet_controlnet_tiny(cuda_dev, mid_depth, lora):
     t = 499.0
     ps_cn = cn.prepare_prompt(ctx, te, tids)
     ps_un = unet.prepare_prompt(ctx, te, tids)
-    cond4 = torch.zeros((B, 8 * h, 8 * h, 4), dtype=torch.float16, device=cuda_dev)
-    cond4[..., :3] = _nhwc(cond)
-    cemb = cn.cond_embedding(cond4)
+    cond_p8 = torch.zeros((B, 8 * h + 2, 8 * h + 8, 8), dtype=torch.float16, device=cuda_dev)   # layout of ops.preprocess_pad8
+    cond_p8[:, 1:-1, 1:8 * h + 1, :3] = _nhwc(cond)
+    cemb = cn.cond_embedding(cond_p8)
     down, mid = cn.forward(_nhwc(x), t, ps_cn, cemb, 0.5)
     eps = unet.forward(_nhwc(x), t, ps_un, down, mid)
     # oracle, fp32 on the GPU

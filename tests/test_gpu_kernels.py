@@ -155,6 +155,32 @@ def test_gemm_epilogues(cuda_dev):
     assert rel_err(out, big[:, k:2 * k].float() @ w.float().t()) < 2e-3
 
 
+@pytest.mark.parametrize("force_bn", [0, 224, 160, 96])
+def test_gemm_epilogue_persistent_ragged(cuda_dev, force_bn):
+    """Many tiles per CTA, ragged M, N that leaves empty / partial accumulator chunks in the last tile column, bias + residual:
+    exercises the epilogue's cross-item prefetch queues (residual, staged biases) across fast and slow chunks."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200 import _lib
+    m, n, k = 45000, 624, 256
+    a = _rand((m, k), cuda_dev, 33).half()
+    w = (_rand((n, k), cuda_dev, 34) / math.sqrt(k)).half()
+    bias = _rand((n,), cuda_dev, 35)
+    res = _rand((m, n), cuda_dev, 36).half()
+    rowb = _rand((m // 1000, n), cuda_dev, 37)
+    ref = a.float() @ w.float().t() + bias
+    _lib.lib().fie_tune_gemm(0, force_bn)
+    try:
+        out = ops.gemm(a, w, col_bias=bias, residual=res)
+        out2 = ops.gemm(a, w, col_bias=bias, row_bias=rowb, rows_per_group=1000)
+        out3 = ops.gemm(a[:, :k], w, col_bias=bias, row_bias=rowb[:, :n], rows_per_group=1024, residual=res, scale=0.25)
+    finally:
+        _lib.lib().fie_tune_gemm(0, 0)
+    assert rel_err(out, ref + res.float()) < 2e-3
+    assert rel_err(out2, ref + rowb.repeat_interleave(1000, dim=0)) < 2e-3
+    g = torch.arange(m, device=cuda_dev) // 1024
+    assert rel_err(out3, (ref + rowb[g]) * 0.25 + res.float()) < 2e-3
+
+
 @pytest.mark.parametrize("m,c", [(256, 64), (1024, 640), (300, 128)])
 def test_gemm_geglu(cuda_dev, m, c):
     ops = _ops()
@@ -239,6 +265,25 @@ def test_conv3x3_cin4(cuda_dev):
     out = ops.conv3x3_cin4(x, wt[:16].permute(0, 2, 3, 1).contiguous(), bias[:16], 16, ld_out=64, act=ops.ACT_SILU)
     ref = F.silu(F.conv2d(x.permute(0, 3, 1, 2).float(), wt[:16], bias[:16], padding=1)).permute(0, 2, 3, 1)
     assert rel_err(out[..., :16], ref) < 2e-3 and float(out[..., 16:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,h,w,cout,silu", [(2, 128, 128, 128, False), (1, 256, 256, 64, True), (2, 64, 32, 96, False), (1, 1024, 1024, 128, False)])
+def test_conv3x3_c8_image_input(cuda_dev, n, h, w, cout, silu):
+    """Tensor-core conv_in on the zero-padded 8-channel image layout (overlapping TMA view) vs F.conv2d on the u8->fp16 image."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3_c8
+    img = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(53)).to(cuda_dev)
+    xp = ops.preprocess_pad8(img, True)
+    x = (2.0 * (img.float() / 255.0) - 1.0).half()
+    assert xp.shape == (n, h + 2, w + 8, 8)
+    assert torch.equal(xp[:, 1:h + 1, 1:w + 1, :3], x) and float(xp[..., 3:].abs().max()) == 0.0
+    assert float(xp[:, 0].abs().max()) == 0.0 and float(xp[:, -1].abs().max()) == 0.0 and float(xp[:, :, 0].abs().max()) == 0.0 and float(xp[:, :, w + 1:].abs().max()) == 0.0
+    wt = _rand((cout, 3, 3, 3), cuda_dev, 54) / 5
+    bias = _rand((cout,), cuda_dev, 55)
+    out = ops.conv3x3_c8(xp, pack_conv3x3_c8(wt), col_bias=bias, act=ops.ACT_SILU if silu else ops.ACT_NONE)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.half().float(), bias, padding=1)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
 
 
 # ------------------------------------------------------------------ attention
