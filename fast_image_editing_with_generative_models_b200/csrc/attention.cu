@@ -14,6 +14,7 @@
 // The two warpgroups ping-pong: while one does its softmax the tensor core serves the other (FlashAttention-4 style).
 // Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 softmax(q=0), w8-11 softmax(q=1).
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace fie {
 
@@ -44,7 +45,8 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     uint64_t* s_full = bars + 7;             // [2]
     uint64_t* p_full = bars + 9;             // [2]
     uint64_t* o_full = bars + 11;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* s_free = bars + 13;            // [2]  S_q has been read into registers: the next Q K^T may overwrite it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("fie: attention smem base misaligned\n"); __trap(); }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < ATT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        for (int q = 0; q < ATT_QT; ++q) { mbar_init(&s_full[q], 1); mbar_init(&p_full[q], 128); mbar_init(&o_full[q], 1); }
+        for (int q = 0; q < ATT_QT; ++q) { mbar_init(&s_full[q], 1); mbar_init(&p_full[q], 128); mbar_init(&o_full[q], 1); mbar_init(&s_free[q], 128); }
         mbar_fence_init();
     }
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.v_map); }
@@ -98,6 +100,16 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
         int s = 0; uint32_t ph = 0;                 // stage / phase of tile j
         for (int j = 0; j < n_tiles; ++j) {
             int sn = s + 1; uint32_t phn = ph; if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
+            // S_q(j+1) = Q_q K_{j+1}^T is issued as soon as the softmax warps hold S_q(j) in registers, i.e. while they are
+            // still exponentiating it: the next scores are ready when P_q(j) is, and the softmax never waits on the tensor pipe.
+            if (j + 1 < n_tiles) {
+                mbar_wait(&kv_full[sn], phn);
+                for (int q = 0; q < ATT_QT; ++q) {
+                    mbar_wait(&s_free[q], (uint32_t)(j & 1));
+                    tc_fence_after();
+                    issue_qk(q, sn);
+                }
+            }
             for (int q = 0; q < ATT_QT; ++q) {
                 mbar_wait(&p_full[q], (uint32_t)(j & 1));
                 tc_fence_after();
@@ -113,10 +125,6 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
                     if (q == ATT_QT - 1) umma_commit(&kv_empty[s]);
                 }
                 __syncwarp();
-                if (j + 1 < n_tiles) {
-                    if (q == 0) { mbar_wait(&kv_full[sn], phn); tc_fence_after(); }
-                    issue_qk(q, sn);
-                }
             }
             s = sn; ph = phn;
         }
@@ -132,7 +140,9 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
         uint8_t* prow = sP + q * 32768 + row * 128;
         const int sw = row & 7;
         // exp2 of one 64-column half -> fp16 -> swizzled smem; returns the row sum of the half
-        auto exp_store = [&](const uint32_t (&r)[64], int hf, float mneg, int kv_left, bool full_tile) -> float {
+        // exp2 of one 64-column half -> fp16 -> swizzled smem; returns the row sum of the half.  FULL: no column masking.
+        auto exp_store = [&](const uint32_t (&r)[64], int hf, float mneg, int kv_left, auto full_c) -> float {
+            constexpr bool FULL = decltype(full_c)::value;
             float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
             uint8_t* base = prow + hf * 16384;
 #pragma unroll
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
                     const int c = u * 8 + 2 * i;
                     float p0 = ex2_approx(fmaf(__uint_as_float(r[c]), sl2, mneg));
                     float p1 = ex2_approx(fmaf(__uint_as_float(r[c + 1]), sl2, mneg));
-                    if (!full_tile) { if (hf * 64 + c >= kv_left) p0 = 0.f; if (hf * 64 + c + 1 >= kv_left) p1 = 0.f; }
+                    if (!FULL) { if (hf * 64 + c >= kv_left) p0 = 0.f; if (hf * 64 + c + 1 >= kv_left) p1 = 0.f; }
                     if (i & 1) { ps2 += p0; ps3 += p1; } else { ps0 += p0; ps1 += p1; }
                     __half2 h = __floats2half2_rn(p0, p1);
                     pk[i] = *reinterpret_cast<uint32_t*>(&h);
@@ -182,14 +192,18 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
             tmem_ld_32x64(tS + 64, rb);
             tmem_ld_wait();
             mx = fmaxf(mx, half_max(rb, 1, kv_left, full_tile));
-            const float alpha = ex2_approx((m_run - mx) * sl2);      // first tile: exp2(-inf) = 0
-            m_run = mx;
+            // Lazy rescale: the running reference max only moves when a row max grew by more than 2^8 in the exponent
+            // domain (or on the first tile); until then P = exp2((s - m_run) * scale) <= 256 still fits fp16 and the final
+            // O / l is exact because both were accumulated against the same reference.
+            const bool move = (j == 0) || ((mx - m_run) * sl2 > 8.0f);
+            const float alpha = move ? ex2_approx((m_run - mx) * sl2) : 1.0f;      // first tile: exp2(-inf) = 0
+            if (move) m_run = mx;
             if (j > 0) {
                 // P_q and O_q are free once PV(q, j-1) has completed; O_q lives in TMEM and is rescaled only when the
-                // running max of some row of this warp moved (rare after the first few tiles)
+                // reference max of some row of this warp moved (rare after the first tile)
                 mbar_wait(&o_full[q], (uint32_t)((j - 1) & 1));
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                if (__any_sync(0xffffffffu, move)) {
                     uint32_t ro[64];
                     tmem_ld_32x64(tO, ro);
                     tmem_ld_wait();
@@ -199,13 +213,16 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
                     tmem_st_wait();
                 }
             }
-            const float mneg = -mx * sl2;
-            float psum = exp_store(rb, 1, mneg, kv_left, full_tile);
+            const float mneg = -m_run * sl2;
+            float psum;
+            if (full_tile) psum = exp_store(rb, 1, mneg, kv_left, std::true_type{}); else psum = exp_store(rb, 1, mneg, kv_left, std::false_type{});
             {
                 uint32_t ra[64];
                 tmem_ld_32x64(tS, ra);
                 tmem_ld_wait();
-                psum += exp_store(ra, 0, mneg, kv_left, full_tile);
+                tc_fence_before();
+                mbar_arrive(&s_free[q]);                  // S_q is in registers: Q_q K_{j+1}^T may be issued now
+                if (full_tile) psum += exp_store(ra, 0, mneg, kv_left, std::true_type{}); else psum += exp_store(ra, 0, mneg, kv_left, std::false_type{});
             }
             l_run = l_run * alpha + psum;
             fence_proxy_async_smem();
