@@ -35,14 +35,22 @@ constexpr int W_PROD = FIE_GEMM_ROLES_HIGH ? 8 : 0, W_MMA = W_PROD + 1, W_ALLOC 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int SMEM_BUDGET = 192 * 1024;      // pipeline stages
+// Halo mode (stride-1 3x3 convolutions whose output rows are >= 128 pixels wide): per 64-channel chunk the producer loads
+// the three input rows h-1, h, h+1 of a 128-pixel output segment ONCE as 130-pixel slabs (130 x 128 B, padded to 17 KiB so
+// every slab base stays 1024-byte aligned) and the 9 filter taps read them through shifted shared-memory descriptors
+// (start address + kw * 128 B): a third of the L2 -> SM traffic of loading 9 shifted A tiles.
+constexpr int HALO_PX = BLOCK_M + 2;
+constexpr int HALO_SLAB_BYTES = 17 * 1024;
+constexpr int HALO_SET_BYTES = 3 * HALO_SLAB_BYTES;
+constexpr int HALO_A_BYTES = 2 * HALO_SET_BYTES;     // double-buffered slab sets; the B ring takes the rest of SMEM_BUDGET
 constexpr int EPI_STAGE_BYTES = 8 * 1024;      // per-epilogue-warp bias staging (8 slots x 32 fp32)
 
 struct GemmParams {
     CUtensorMap a_maps[4];
     CUtensorMap b_map;
-    int mode;         // 0 = GEMM, 1 = CONV
+    int mode;         // 0 = GEMM, 1 = CONV (one shifted A tile per tap), 2 = CONV halo (A slabs shared by the 9 taps)
     int num_kb;       // K blocks of 64
     int kb_per_tap;   // CONV: cin/64
     int kb_split;     // GEMM: k-blocks taken from a_maps[0]; the rest from a_maps[1]
@@ -160,10 +168,10 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned by the ABI; round up to 1024 for the 128B swizzle
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[2], tmem_empty[2];
+    __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full[2], tmem_empty[2], a_full[2], a_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     uint8_t* epi_smem = smem + SMEM_BUDGET;        // [8 epilogue warps][8 bias slots][32 fp32]
     const int block_n = p.block_n;
     const int b_rows = block_n / CG;                                   // B rows held by this CTA
@@ -182,7 +190,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     }
     if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8 * CG); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8 * CG); mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
         mbar_fence_init();
     }
     if (warp == W_ALLOC) { if (CG == 2) tmem_alloc_2sm(&tmem_base_slot, (uint32_t)p.tmem_cols); else tmem_alloc(&tmem_base_slot, (uint32_t)p.tmem_cols); }
@@ -201,7 +209,42 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
 #endif
     if (warp == W_PROD) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        const bool prod_lane = elect_one_sync();
+        if (prod_lane && p.mode == 2) {
+            // ---- halo convolution: slab sets (per 64-channel chunk) + a ring of per-tap B tiles ----
+            int stage = 0; uint32_t phase = 0; int ab = 0; uint32_t aph = 0;
+            uint8_t* smem_b = smem + HALO_A_BYTES;
+            const int num_cc = p.kb_per_tap, tps = p.kps;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+                const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
+                const long long m0 = ((long long)m_blk * CG + cta_rank) * BLOCK_M;
+                const long long pix = (long long)p.OH * p.OW;
+                const int n0i = (int)(m0 / pix), rem = (int)(m0 % pix), h0 = rem / p.OW, w0 = rem % p.OW;
+                for (int cc = 0; cc < num_cc; ++cc) {
+                    FIE_TIMED(tr_wait, mbar_wait(&a_empty[ab], aph ^ 1));
+                    if (CG == 1 || leader) mbar_arrive_expect_tx(&a_full[ab], (uint32_t)(CG * 3 * HALO_PX * BLOCK_K * 2));
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        uint8_t* dst = smem + ab * HALO_SET_BYTES + r * HALO_SLAB_BYTES;
+                        if (CG == 1) tma_load_4d(&p.a_maps[0], &a_full[ab], dst, cc * BLOCK_K, w0 - 1, h0 + r - 1, n0i);
+                        else tma_load_4d_2sm(&p.a_maps[0], &a_full[ab], dst, cc * BLOCK_K, w0 - 1, h0 + r - 1, n0i);
+                    }
+                    ab ^= 1; if (ab == 0) aph ^= 1;
+                    for (int tap0 = 0; tap0 < 9; tap0 += tps) {          // one ring stage = tps taps (a whole kernel row when it fits)
+                        FIE_TIMED(tr_wait, mbar_wait(&empty_bar[stage], phase ^ 1));
+                        if (CG == 1 || leader) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(CG * tps * b_sub_bytes));
+                        for (int t = 0; t < tps; ++t) {
+                            const int kcol = ((tap0 + t) * num_cc + cc) * BLOCK_K;
+                            uint8_t* dst = smem_b + (size_t)(stage * tps + t) * b_sub_bytes;
+                            if (CG == 1) tma_load_2d(&p.b_map, &full_bar[stage], dst, kcol, n_blk * block_n);
+                            else tma_load_2d_2sm(&p.b_map, &full_bar[stage], dst, kcol, n_blk * block_n + (int)cta_rank * b_rows);
+                        }
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            if (p.trace) { p.trace[blockIdx.x * 8 + 0] = tr_wait; p.trace[blockIdx.x * 8 + 1] = clock64() - tr_start; }
+        } else if (prod_lane) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile / p.num_n_blocks, n_blk = tile % p.num_n_blocks;
@@ -259,6 +302,46 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
         // ===================== MMA issuer (leader CTA of the pair) =====================
         const uint32_t idesc = umma_idesc_f16(BLOCK_M * CG, block_n);
         int stage = 0; uint32_t phase = 0; int it = 0;
+        if (p.mode == 2) {
+            int ab = 0; uint32_t aph = 0;
+            const int num_cc = p.kb_per_tap, tps = p.kps;
+            const uint32_t smem_a = smem_u32(smem), smem_b = smem_a + HALO_A_BYTES;
+            for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+                const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+                FIE_TIMED(tr_wait2, if (CG == 2) mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1); else mbar_wait(&tmem_empty[buf], acc_phase ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * block_n);
+                for (int cc = 0; cc < num_cc; ++cc) {
+                    FIE_TIMED(tr_wait, mbar_wait(&a_full[ab], aph));
+                    for (int tap0 = 0; tap0 < 9; tap0 += tps) {
+                        FIE_TIMED(tr_wait, mbar_wait(&full_bar[stage], phase));
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            for (int t = 0; t < tps; ++t) {
+                                const int tap = tap0 + t, kh = tap / 3, kw = tap - 3 * kh;
+                                const uint64_t bdesc = umma_desc_sw128(smem_b + (uint32_t)((stage * tps + t) * b_sub_bytes));
+                                // rows kw .. kw+127 of slab kh: start address shifted by kw pixels (128 B each).  Measured on B200: the 128B
+                                // swizzle is a function of the shared-memory ADDRESS bits, so the descriptor's base-offset field stays 0.
+                                const uint64_t adesc = umma_desc_sw128(smem_a + (uint32_t)(ab * HALO_SET_BYTES + kh * HALO_SLAB_BYTES + kw * 128));
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                                    if (p.dbg & 2) continue;
+                                    const uint32_t acc = (cc | tap | k) ? 1u : 0u;
+                                    if (CG == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                                    else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+                                }
+                            }
+                            const bool last_tap = tap0 + tps == 9, last = last_tap && cc == num_cc - 1;
+                            if (CG == 2) { umma_commit_2sm(&empty_bar[stage]); if (last_tap) umma_commit_2sm(&a_empty[ab]); if (last) umma_commit_2sm(&tmem_full[buf]); }
+                            else { umma_commit(&empty_bar[stage]); if (last_tap) umma_commit(&a_empty[ab]); if (last) umma_commit(&tmem_full[buf]); }
+                        }
+                        __syncwarp();
+                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                    }
+                    ab ^= 1; if (ab == 0) aph ^= 1;
+                }
+            }
+        } else
         for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
             const int buf = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
             FIE_TIMED(tr_wait2, if (CG == 2) mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1); else mbar_wait(&tmem_empty[buf], acc_phase ^ 1));
@@ -267,7 +350,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             for (int sb = 0; sb < num_sb; ++sb) {
                 FIE_TIMED(tr_wait, mbar_wait(&full_bar[stage], phase));
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
 #pragma unroll
                     for (int sub = 0; sub < KPS; ++sub) {
@@ -291,7 +374,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         }
-        if (p.trace && lane == 0) { p.trace[blockIdx.x * 8 + 2] = tr_wait; p.trace[blockIdx.x * 8 + 3] = tr_wait2; p.trace[blockIdx.x * 8 + 4] = clock64() - tr_start; }
+        if (p.trace && elect_one_sync()) { p.trace[blockIdx.x * 8 + 2] = tr_wait; p.trace[blockIdx.x * 8 + 3] = tr_wait2; p.trace[blockIdx.x * 8 + 4] = clock64() - tr_start; }
     }
     } else {
 #if FIE_GEMM_SETMAXNREG
@@ -525,15 +608,17 @@ static int g_dbg = 0;
 static int g_force_kps = 0;
 static int g_force_mt = 0;
 static long long* g_trace = nullptr;
-static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out, int* mt_out) {
+static int g_halo = -1;             // FIE_CONV_HALO=0 disables the halo convolution path
+static int g_halo_max_cout = 640;   // wider outputs reuse each A tile enough for the per-tap form to win
+static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out, int* mt_out, int max_mt = 2) {
     if (g_force_cg < 0) { const char* s = getenv("FIE_GEMM_CG"); g_force_cg = s ? atoi(s) : 0; }
     const int sms = num_sms();
     double best_cost = 1e30; int best_cg = 2, best_bn = 32, best_mt = 1;
     for (int cg = 2; cg >= 1; --cg) {
         if (g_force_cg && cg != g_force_cg) continue;
         if (!g_force_cg && cg == 1 && M > BLOCK_M) continue;          // single-CTA form only for one-tile-high problems
-        for (int mt = 1; mt <= 2; ++mt) {
-            if (g_force_mt && mt != g_force_mt) continue;
+        for (int mt = 1; mt <= max_mt; ++mt) {
+            if (g_force_mt && mt != g_force_mt && max_mt > 1) continue;
             if (!g_force_mt && mt == 2 && N > 128) continue;     // measured: two M sub-tiles only pay off for N <= 128
             const long long mblocks = (M + BLOCK_M * cg * mt - 1) / (BLOCK_M * cg * mt);
             const int slots = sms / cg;
@@ -572,9 +657,11 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     const int mt = p.mt;
     int kps = (g_force_kps > 0) ? g_force_kps : (p.num_kb >= 4 ? 2 : 1);
     if (kps == 2 && SMEM_BUDGET / (2 * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2)) < 2) kps = 1;
-    p.kps = kps;
-    const int stage_bytes = kps * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2);
-    int stages = SMEM_BUDGET / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES;
+    int halo_tps = 1;                              // halo: ring stage = B tiles of 3 taps (one kernel row) when two such stages fit, else 1 tap
+    if (p.mode == 2) { kps = 1; if (2 * 3 * (p.block_n / cg) * BLOCK_K * 2 <= SMEM_BUDGET - HALO_A_BYTES) halo_tps = 3; if (g_force_kps == 1) halo_tps = 1; }
+    p.kps = p.mode == 2 ? halo_tps : kps;
+    const int stage_bytes = p.mode == 2 ? halo_tps * (p.block_n / cg) * BLOCK_K * 2 : kps * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2);
+    int stages = (p.mode == 2 ? SMEM_BUDGET - HALO_A_BYTES : SMEM_BUDGET) / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) stages = 2;
     p.num_stages = stages;
     int cols = 2 * mt * p.block_n, tc = 32; while (tc < cols) tc <<= 1;
@@ -612,6 +699,8 @@ static int launch(GemmParams& p, cudaStream_t stream) {
 }  // namespace fie
 
 using namespace fie;
+
+extern "C" void fie_tune_conv_halo(int enable, int max_cout) { fie::g_halo = enable; if (max_cout > 0) fie::g_halo_max_cout = max_cout; }
 
 extern "C" void fie_tune_gemm(int force_cg, int force_block_n) { fie::g_force_cg = force_cg & 3; fie::g_force_kps = (force_cg >> 2) & 3; fie::g_dbg = (force_cg >> 4) & 15; fie::g_force_mt = (force_cg >> 8) & 3; fie::g_force_bn = force_block_n; }
 
@@ -683,15 +772,17 @@ extern "C" int fie_conv3x3_f16(const void* x, const void* wgt, void* out, long l
     int rc = fill_epilogue(p, ep, M, cout, out, ldd);
     if (rc) return rc;
     FIE_REQUIRE(p.act != FIE_ACT_GEGLU, "fie_conv3x3_f16: GEGLU epilogue not supported for conv");
-    p.mode = 1; p.M = M; p.N = cout; p.OH = OH; p.OW = OW;
-    pick_config(M, cout, false, &p.cg, &p.block_n, &p.mt);
+    if (g_halo < 0) { const char* e = getenv("FIE_CONV_HALO"); g_halo = e ? atoi(e) : 1; }
+    const bool halo = g_halo > 0 && stride == 1 && (OW % BLOCK_M) == 0 && cout <= g_halo_max_cout;
+    p.mode = halo ? 2 : 1; p.M = M; p.N = cout; p.OH = OH; p.OW = OW;
+    pick_config(M, cout, false, &p.cg, &p.block_n, &p.mt, halo ? 1 : 2);
     p.num_m_blocks = (int)((M + BLOCK_M * p.cg * p.mt - 1) / (BLOCK_M * p.cg * p.mt));
     p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
     p.kb_per_tap = cin / BLOCK_K;
     p.num_kb = 9 * p.kb_per_tap;
     p.kb_split = p.num_kb;
     p.n_store = cout_valid > 0 ? cout_valid : cout;
-    const uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    const uint32_t box[4] = {BLOCK_K, (uint32_t)(halo ? HALO_PX : bw), (uint32_t)(halo ? 1 : bh), (uint32_t)(halo ? 1 : bn)};
     if (stride == 1) {
         const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w, (uint64_t)h, (uint64_t)n};
         const uint64_t strides[3] = {(uint64_t)cin * 2, (uint64_t)w * cin * 2, (uint64_t)h * w * cin * 2};

@@ -93,6 +93,16 @@ __device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* m, uint64_t* 
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+// One elected lane of a fully converged warp (elect.sync).  Together with a shuffle-broadcast warp index this keeps the
+// TMA / MMA issue loops in uniform control flow, so their descriptors live in uniform registers instead of being moved
+// there (R2UR + vote loops) before every tcgen05.mma / cp.async.bulk.tensor.
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---------------- clusters ----------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

@@ -102,6 +102,10 @@ int fie_geglu_block_n(int N);
  * fie_conv3x3_f16.  Not needed in production. */
 void fie_tune_gemm(int force_cg, int force_block_n);
 
+/* Tuning / test hook: enable (1) / disable (0) the halo form of the stride-1 3x3 convolution (input rows loaded once per channel
+ * chunk and shared by the 9 taps) and set the widest cout it is used for (0 = keep).  Not needed in production. */
+void fie_tune_conv_halo(int enable, int max_cout);
+
 /* Debug hook: device buffer of 8 x int64 per CTA that subsequent GEMM/conv launches fill with per-role wait-cycle
  * accounting (see gemm_conv.cu); NULL switches it off.  Not needed in production. */
 void fie_gemm_trace(long long* device_buf);

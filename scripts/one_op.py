@@ -9,6 +9,8 @@ import torch
 from fast_image_editing_with_generative_models_b200 import _lib, ops
 from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
 dev = torch.device("cuda:0")
+if os.environ.get("FIE_DBG"): _lib.lib().fie_tune_gemm(int(os.environ["FIE_DBG"]) << 4, 0)      # 1 noTMA, 2 noMMA, 4 noEpilogue
+if os.environ.get("FIE_HALO_MAX"): _lib.lib().fie_tune_conv_halo(1, int(os.environ["FIE_HALO_MAX"]))
 kind = sys.argv[1]
 args = sys.argv[2:]
 iters = 3

@@ -217,6 +217,32 @@ def test_conv3x3(cuda_dev, n, h, w, cin, cout, stride, pad_mode):
     assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 40, 256, 192, 160), (1, 128, 128, 320, 320), (3, 17, 384, 64, 32), (1, 512, 512, 128, 128)])
+def test_conv3x3_halo_vs_per_tap(cuda_dev, n, h, w, cin, cout):
+    """Stride-1 convs with >= 128-pixel rows use the halo form (input rows loaded once, taps read through shifted smem
+    descriptors); it must agree with the per-tap form bit-for-bit up to accumulation order, and with F.conv2d."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200 import _lib
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
+    x = _rand((n, h, w, cin), cuda_dev, 56).half()
+    wt = (_rand((cout, cin, 3, 3), cuda_dev, 57) / math.sqrt(9 * cin)).half()
+    bias = _rand((cout,), cuda_dev, 58)
+    res = _rand((n, h, w, cout), cuda_dev, 59).half()
+    wp = pack_conv3x3(wt)
+    L = _lib.lib()
+    try:
+        L.fie_tune_conv_halo(1, 4096)
+        out_h = ops.conv3x3(x, wp, col_bias=bias, residual=res)
+        L.fie_tune_conv_halo(0, 0)
+        out_t = ops.conv3x3(x, wp, col_bias=bias, residual=res)
+    finally:
+        L.fie_tune_conv_halo(1, 640)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    assert rel_err(out_t, ref) < 2e-3, rel_err(out_t, ref)
+    assert rel_err(out_h, ref) < 2e-3, rel_err(out_h, ref)
+    assert float((out_h.float() - out_t.float()).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
 def test_conv3x3_small_cout_and_epilogue(cuda_dev):
     ops = _ops()
     from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
