@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--model", default="sdxl", choices=["sdxl", "ssd-1b"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the ~2500 kernels of an edit eagerly instead of replaying one CUDA graph")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family breakdown JSON here")
     return ap.parse_args()
 
@@ -154,6 +155,7 @@ def main():
 
     state = model_zoo.synthetic_state(a.model)
     eng = model_zoo.build_engine(state, dev)
+    eng.use_graphs = not a.no_graph      # one CUDA graph per edit (the product default of FastEditor); --no-graph = eager launches
     ucfg = eng.unet.cfg
     pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
     idx0 = rank * B
@@ -230,9 +232,10 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kernel timed inside a long step)" if peaks else "fallback (B200_PROFILING.md sustained ~1400)"
-    tc_ms = sum(fam[k]["ms"] for k in ("gemm", "conv3x3") if k in fam)
-    tc_flop = sum(fam[k]["work"] for k in ("gemm", "conv3x3") if k in fam)
-    tc_calls = sum(fam[k]["calls"] for k in ("gemm", "conv3x3") if k in fam)
+    TC = ("gemm", "conv3x3", "conv_up2x")        # every launch of k_gemm_conv with a FLOP count (conv_up2x = 4 phase launches per call)
+    tc_ms = sum(fam[k]["ms"] for k in TC if k in fam)
+    tc_flop = sum(fam[k]["work"] for k in TC if k in fam)
+    tc_calls = sum(fam[k]["calls"] * (4 if k == "conv_up2x" else 1) for k in TC if k in fam)
     total_ms = sum(d["ms"] for d in fam.values())
     achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     roofline = {"kernel": "k_gemm_conv (tcgen05 GEMM / implicit-GEMM conv3x3)", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
@@ -259,7 +262,7 @@ def main():
                 "dtype": "f16", "data": "synthetic",
                 "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world, "strength": 0.5, "executed_steps": 2,
                            "cfg": 1.5, "parallelism": f"dp{world} (independent images, NCCL all-gather of uint8 outputs)",
-                           "weights": "seeded random-init of the named architectures", "l2": "inputs larger than L2 (5 GB weights + GB-scale activations per step)"},
+                           "weights": "seeded random-init of the named architectures", "launch": "eager" if a.no_graph else "cuda-graph replay of the whole edit", "l2": "inputs larger than L2 (5 GB weights + GB-scale activations per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "image_roofline": {"tflop_per_image": TFLOP_PER_IMAGE[a.model], "achieved_tflops_per_gpu": value / world * TFLOP_PER_IMAGE[a.model],
                                    "frac_of_peak": value / world * TFLOP_PER_IMAGE[a.model] / peak_tf},

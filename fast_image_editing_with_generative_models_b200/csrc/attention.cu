@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("fie: attention smem base misaligned\n"); __trap(); }
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int qt0 = blockIdx.x * ATT_QT, head = blockIdx.y, b = blockIdx.z;
     const int n_tiles = (p.nkv + ATT_BN - 1) / ATT_BN;
 
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(q_full, ATT_QT * ATT_TILE_BYTES);
             for (int q = 0; q < ATT_QT; ++q) tma_load_3d(&p.q_map, q_full, sQ + q * ATT_TILE_BYTES, head * ATT_D, (qt0 + q) * ATT_BM, b);
             int s = 0; uint32_t ph = 0;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
         const uint32_t idesc_pv = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);   // B (= V) is MN-major
         const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
         auto issue_qk = [&](int q, int s) {        // S_q = Q_q K_s^T
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 const uint64_t ad = umma_desc_sw128(aQ + q * ATT_TILE_BYTES), bd = umma_desc_sw128(aKV + s * 2 * ATT_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k) umma_f16(tmem + q * 128, ad + 2 * k, bd + 2 * k, idesc_qk, k ? 1u : 0u);
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
             for (int q = 0; q < ATT_QT; ++q) {
                 mbar_wait(&p_full[q], (uint32_t)(j & 1));
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one_sync()) {
                     const uint32_t aV = aKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < ATT_BN / 16; ++k) {

@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * MT * block_n);
             for (int sb = 0; sb < num_sb; ++sb) {
                 FIE_TIMED(tr_wait, mbar_wait(&full_bar[stage], phase));
+                if (p.trace && it == 0 && sb == 0 && lane == 0) p.trace[blockIdx.x * 8 + 7] = clock64() - tr_start;   // prologue + first TMA round trip
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t sbase = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         const int ncols_tile = GEGLU ? (block_n >> 1) : block_n;      // output columns per tile
         const int nchunks = ncols_tile / 32;
-        const bool fast_cfg = !p.out_f32 && (p.ldd & 15) == 0 && (reinterpret_cast<uintptr_t>(p.D) & 31) == 0 &&
+        const bool fast_cfg = (p.out_f32 ? ((p.ldd & 7) == 0 && !p.residual) : (p.ldd & 15) == 0) && (reinterpret_cast<uintptr_t>(p.D) & 31) == 0 &&
                               (!p.residual || ((p.ld_res & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0)) &&
                               (!p.row_bias || (p.rows_per_group & 31) == 0);
         const bool res_fast = fast_cfg && p.residual != nullptr;
@@ -532,7 +533,18 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                             f = __half22float2(*reinterpret_cast<const __half2*>(&res1[i])); v[16 + 2 * i] += f.x; v[16 + 2 * i + 1] += f.y;
                         }
                     }
-                    if (row_ok) {
+                    if (p.out_f32) {
+                        if (row_ok) {                                   // fp32 output (attention scores): 128 B per row and chunk
+                            float* of = reinterpret_cast<float*>(p.D) + out_row(p, m) * p.ldd + nout;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                uint32_t o[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(v[8 * i + j]);
+                                stg256(of + 8 * i, o);
+                            }
+                        }
+                    } else if (row_ok) {
                         uint32_t o0[8], o1[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -871,7 +883,7 @@ extern "C" int fie_conv_up2x_f16(const void* x, const void* wgt, void* out, long
 // 24 contiguous fp16 starting at padded pixel x.  The A operand is an OVERLAPPING TMA view: dimension 0 = 64 contiguous fp16
 // (8 padded pixels, of which the first 3 carry non-zero weights), dimension 1 = start pixel with a 16-byte stride.  K = 3 kernel
 // rows x 64, so the generic implicit-GEMM kernel runs unchanged with 3 "taps" of one K block each.
-// wgt: fp16 [cout][3][64], element (kh, kw*8 + c) = w[co][c][kh][kw] (zeros elsewhere).
+// wgt: fp16 [cout][3][2][64]: per kernel row a hi and a lo block (w = hi + lo to ~2^-22), element kw*8 + c = w[co][c][kh][kw].
 extern "C" int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, long long ldd, int n, int h, int w, int cout,
                                   int cout_valid, const fie_epilogue* ep, void* stream) {
     FIE_REQUIRE(xp && wgt && out, "fie_conv3x3_c8_f16: null pointer");
@@ -894,7 +906,7 @@ extern "C" int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, lo
     pick_config(M, cout, false, &p.cg, &p.block_n, &p.mt);
     p.num_m_blocks = (int)((M + BLOCK_M * p.cg * p.mt - 1) / (BLOCK_M * p.cg * p.mt));
     p.num_n_blocks = (cout + p.block_n - 1) / p.block_n;
-    p.kb_per_tap = 1; p.num_kb = 3; p.kb_split = 3;
+    p.kb_per_tap = 1; p.num_kb = 6; p.kb_split = 6;     // 3 kernel rows x (hi, lo) weight parts, each one 64-wide K block on the same A window
     p.n_store = cout_valid > 0 ? cout_valid : cout;
     const uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
     const uint64_t wp = (uint64_t)w + 8, hp = (uint64_t)h + 2;
@@ -902,9 +914,9 @@ extern "C" int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, lo
     const uint64_t strides[3] = {16, wp * 16, hp * wp * 16};
     if ((rc = make_tmap_f16(&p.a_maps[0], xp, 4, dims, strides, box))) return rc;
     p.a_maps[1] = p.a_maps[0]; p.a_maps[2] = p.a_maps[0]; p.a_maps[3] = p.a_maps[0];
-    for (int t = 0; t < 3; ++t) { p.tap_map[t] = 0; p.tap_dh[t] = (int8_t)t; p.tap_dw[t] = 0; }   // padded row y + kh, padded pixel x
-    const uint64_t bdims[2] = {(uint64_t)3 * BLOCK_K, (uint64_t)cout};
-    const uint64_t bstr[1] = {(uint64_t)3 * BLOCK_K * 2};
+    for (int t = 0; t < 6; ++t) { p.tap_map[t] = 0; p.tap_dh[t] = (int8_t)(t >> 1); p.tap_dw[t] = 0; }   // padded row y + kh, padded pixel x
+    const uint64_t bdims[2] = {(uint64_t)6 * BLOCK_K, (uint64_t)cout};
+    const uint64_t bstr[1] = {(uint64_t)6 * BLOCK_K * 2};
     const uint32_t bbox[2] = {BLOCK_K, (uint32_t)(p.block_n / p.cg)};
     if ((rc = make_tmap_f16(&p.b_map, wgt, 2, bdims, bstr, bbox))) return rc;
     return launch(p, (cudaStream_t)stream);

@@ -77,6 +77,7 @@ class FastEditor:
             self._say("[FastEditor] Generating seeded synthetic weights (no checkpoints available offline)...")
             state = model_zoo.synthetic_state(model_name, use_full_controlnet, tiny)
         self._engine = model_zoo.build_engine(state, device)
+        self._engine.use_graphs = True      # every edit has the same shapes: replay it as one CUDA graph after the first call
         self.controlnet = self._engine.cn
         self.pipe = _PipeShim(self._engine)
         self._prompt_encoder = prompt_encoder

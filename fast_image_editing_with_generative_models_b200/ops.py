@@ -270,11 +270,11 @@ def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional
 
 
 def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] = None, col_bias=None, act=ACT_NONE) -> torch.Tensor:
-    """Tensor-core conv_in.  xp: zero-padded [N,H+2,W+8,8] fp16 (:func:`preprocess_pad8`), w: [Cout, 192] (weights.pack_conv3x3_c8)
+    """Tensor-core conv_in.  xp: zero-padded [N,H+2,W+8,8] fp16 (:func:`preprocess_pad8`), w: [Cout, 384] (weights.pack_conv3x3_c8)
     -> [N,H,W,cout_valid]."""
     _req(xp, torch.float16, "conv3x3_c8")
     n, hp, wp, c = xp.shape
-    assert c == 8 and w.shape[1] == 192, (xp.shape, w.shape)
+    assert c == 8 and w.shape[1] == 384, (xp.shape, w.shape)
     h, wd = hp - 2, wp - 8
     cout = w.shape[0]
     cv = cout if cout_valid is None else cout_valid

@@ -36,21 +36,70 @@ class EditEngine:
             self.cn = ControlNet(cn_params, cn_cfg, self.dev)
             self.vae = VAE(vae_params, vae_cfg, self.dev)
         self.sched = LCMSchedule()
+        self.use_graphs = False           # opt-in: replay each edit as one CUDA graph (see edit_batch)
+        self._graphs: Dict = {}
 
     @torch.no_grad()
     def edit_batch(self, images_u8: Tensor, prompt_embeds: Tensor, pooled: Tensor, noises: Sequence[Tensor], strength: float = 0.5,
                    num_inference_steps: int = 4, guidance_scale: float = 1.5, controlnet_conditioning_scale: float = 0.5,
-                   canny_low: int = 100, canny_high: int = 200, return_latents: bool = False, return_extras: bool = False) -> EditOutput:
+                   canny_low: int = 100, canny_high: int = 200, return_latents: bool = False, return_extras: bool = False,
+                   use_graph: Optional[bool] = None) -> EditOutput:
         """images_u8: uint8 [B,H,W,3] (CUDA, H and W multiples of 8; 1024 for the reference path).
         prompt_embeds [2,77,D] / pooled [2,P] (row 0 negative, row 1 positive; shared by the batch) or per image
-        [B,2,77,D] / [B,2,P].  noises: [xi, n, z1, ...] each [B,4,h,w] (reference RNG order)."""
+        [B,2,77,D] / [B,2,P].  noises: [xi, n, z1, ...] each [B,4,h,w] (reference RNG order).
+
+        ``use_graph`` (default: ``self.use_graphs``): replay the whole edit — ~2500 kernel launches — as ONE CUDA graph
+        captured on first use for this (shapes, schedule) key; inputs are copied into the graph's static buffers and the
+        returned tensors are the graph's static outputs (valid until the next call with the same key)."""
         dev = self.dev
+        nz = [n.to(dev, torch.float16).permute(0, 2, 3, 1).contiguous() for n in noises]
+        pe = prompt_embeds.to(dev, torch.float16)
+        pl = pooled.to(dev, torch.float16)
+        images_u8 = images_u8.to(dev)
+        args = dict(strength=strength, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
+                    controlnet_conditioning_scale=controlnet_conditioning_scale, canny_low=canny_low, canny_high=canny_high)
+        graph = self.use_graphs if use_graph is None else use_graph
+        if not graph or return_extras or ops.PROFILE is not None:
+            return self._edit_core(images_u8, pe, pl, nz, return_latents=return_latents, return_extras=return_extras, **args)
+        key = (tuple(images_u8.shape), tuple(pe.shape), tuple(pl.shape), len(nz), tuple(sorted(args.items())))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(key, images_u8, pe, pl, nz, args)
+        g["img"].copy_(images_u8); g["pe"].copy_(pe); g["pl"].copy_(pl)
+        for d, s_ in zip(g["nz"], nz):
+            d.copy_(s_)
+        g["graph"].replay()
+        ops.LAUNCHES += g["launches"]
+        out = g["out"]
+        return EditOutput(images=out.images, edges=out.edges, latents=out.latents if return_latents else None)
+
+    def _capture(self, key, images_u8, pe, pl, nz, args):
+        """Warm up eagerly (first-use attribute setup, allocator pools), then record one edit into a CUDA graph."""
+        st = dict(img=images_u8.clone(), pe=pe.clone(), pl=pl.clone(), nz=[n.clone() for n in nz])
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            self._edit_core(st["img"], st["pe"], st["pl"], st["nz"], return_latents=True, **args)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES
+        with torch.cuda.graph(graph):
+            out = self._edit_core(st["img"], st["pe"], st["pl"], st["nz"], return_latents=True, **args)
+        st.update(graph=graph, out=out, launches=ops.LAUNCHES - l0)
+        ops.LAUNCHES = l0                         # capture records launches, it does not execute them
+        self._graphs[key] = st
+        return st
+
+    def _edit_core(self, images_u8: Tensor, pe: Tensor, pl: Tensor, nz: List[Tensor], strength: float = 0.5,
+                   num_inference_steps: int = 4, guidance_scale: float = 1.5, controlnet_conditioning_scale: float = 0.5,
+                   canny_low: int = 100, canny_high: int = 200, return_latents: bool = False, return_extras: bool = False) -> EditOutput:
+        """The edit itself; every tensor is already on the device (fp16, noises NHWC) — nothing here touches the host."""
         B, H, W, _ = images_u8.shape
         sched = self.sched
         timesteps, begin = sched.img2img_timesteps(num_inference_steps, strength)
         do_cfg = guidance_scale > 1
         nrow = 2 if do_cfg else 1
-        nz = [n.to(dev, torch.float16).permute(0, 2, 3, 1).contiguous() for n in noises]
         # ---- Canny control image + conditioning embedding (step-invariant) ----
         edges3 = ops.canny(images_u8, canny_low, canny_high, out_channels=3)
         cond_emb = self.cn.cond_embedding(ops.preprocess_pad8(edges3, normalize=False))
@@ -61,8 +110,6 @@ class EditEngine:
         sa, s1 = sched.add_noise_coeffs(timesteps[0]) if timesteps else (1.0, 0.0)
         x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)
         # ---- prompt conditioning (step-invariant): rows [neg]*B + [pos]*B as diffusers ----
-        pe = prompt_embeds.to(dev, torch.float16)
-        pl = pooled.to(dev, torch.float16)
         if pe.dim() == 3:
             pe, pl = pe[None].expand(B, -1, -1, -1), pl[None].expand(B, -1, -1)
         rows = [0, 1] if do_cfg else [1]

@@ -20,14 +20,19 @@ def pack_conv3x3(w: torch.Tensor, pad_cout_to: Optional[int] = None, pad_cin_to:
 
 
 def pack_conv3x3_c8(w: torch.Tensor, pad_cout_to: Optional[int] = None) -> torch.Tensor:
-    """[Cout, Cin<=8, 3, 3] -> fp16 [Cout_p, 3*64] for the tensor-core conv_in (fie_conv3x3_c8_f16): per kernel row kh a 64-wide
-    K block whose element kw*8 + c is w[co, c, kh, kw]; the other 40 positions (padded pixels 3..7 of the window) are zero."""
+    """[Cout, Cin<=8, 3, 3] -> fp16 [Cout_p, 3*2*64] for the tensor-core conv_in (fie_conv3x3_c8_f16): per kernel row kh two
+    64-wide K blocks (hi, lo) whose element kw*8 + c is w[co, c, kh, kw]; the other 40 positions (padded pixels 3..7 of the
+    window) are zero.  hi = fp16(w), lo = fp16(w - hi): the fp32 conv_in weights survive the fp16 tensor-core path to ~2^-22."""
     cout, cin = w.shape[:2]
     assert cin <= 8
     op = pad_cout_to or cout
-    out = torch.zeros((op, 3, 8, 8), dtype=torch.float16, device=w.device)        # [co][kh][pixel][channel]
-    out[:cout, :, :3, :cin] = w.permute(0, 2, 3, 1).to(torch.float16)
-    return out.reshape(op, 3 * 64).contiguous()
+    w32 = w.float().permute(0, 2, 3, 1)                                            # [co][kh][kw][c]
+    hi = w32.to(torch.float16)
+    lo = (w32 - hi.float()).to(torch.float16)
+    out = torch.zeros((op, 3, 2, 8, 8), dtype=torch.float16, device=w.device)     # [co][kh][hi|lo][pixel][channel]
+    out[:cout, :, 0, :3, :cin] = hi
+    out[:cout, :, 1, :3, :cin] = lo
+    return out.reshape(op, 3 * 2 * 64).contiguous()
 
 
 def pack_conv_up2x(w: torch.Tensor) -> torch.Tensor:

@@ -136,7 +136,8 @@ int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float* bias, voi
 
 /* 3x3 convolution (pad 1) of an image-like input with <= 8 channels on the tensor cores: conv_in of the VAE encoder and of
  * the ControlNet conditioning embedding at full resolution.  xp: fp16 zero-padded [n,h+2,w+8,8] (fie_preprocess_u8_to_f16_pad8);
- * wgt: fp16 [cout][3][64] with element (kh, kw*8 + c) = w[co][c][kh][kw], zeros elsewhere; out: [n,h,w,cout_valid..] rows of ldd. */
+ * wgt: fp16 [cout][3][2][64]: per kernel row a hi block and a lo block (w = hi + lo keeps the fp32 weights to ~2^-22), element
+ * kw*8 + c = w[co][c][kh][kw], zeros elsewhere; out: [n,h,w,cout_valid..] rows of ldd. */
 int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, long long ldd, int n, int h, int w, int cout,
                        int cout_valid, const fie_epilogue* ep, void* stream);
 

@@ -307,9 +307,9 @@ def test_conv3x3_c8_image_input(cuda_dev, n, h, w, cout, silu):
     wt = _rand((cout, 3, 3, 3), cuda_dev, 54) / 5
     bias = _rand((cout,), cuda_dev, 55)
     out = ops.conv3x3_c8(xp, pack_conv3x3_c8(wt), col_bias=bias, act=ops.ACT_SILU if silu else ops.ACT_NONE)
-    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.half().float(), bias, padding=1)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt, bias, padding=1)        # fp32 weights: the kernel carries them as hi + lo fp16
     ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
-    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+    assert rel_err(out, ref) < 1e-3, rel_err(out, ref)
 
 
 # ------------------------------------------------------------------ attention
