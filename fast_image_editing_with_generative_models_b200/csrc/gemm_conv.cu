@@ -82,6 +82,9 @@ struct GemmParams {
     float scale;
     int act;
     int out_f32;
+    unsigned long long* gn_stats;   // optional GroupNorm statistics of the output [images][groups][2], 2^-20 fixed point
+    int gn_cpg, gn_groups;          // channels per group (divides 32), groups
+    long long gn_rows;              // rows per image
 };
 
 // Output row of accumulator row m (identity, or the strided scatter of one phase of the fused nearest-2x upsample).
@@ -119,6 +122,38 @@ __device__ __forceinline__ void store_chunk(const GemmParams& p, long long m, in
             for (int i = 0; i < 32; ++i) if (n0 + i < p.n_store) d[i] = __float2half_rn(v[i]);
         }
     }
+}
+
+// GroupNorm statistics of one 32 x 32 output chunk (thread = row, v = its 32 fp32 outputs): per-thread partial sums of the NG
+// = 32 / cpg groups the chunk covers and a halving butterfly over the 32 rows of the warp (NG + log2 stages shuffles instead of
+// 5 per value).  The warp keeps adding into per-chunk-slot registers across its tiles and only flushes them with 64-bit
+// fixed-point atomics when the (image, tile column) changes: integer accumulation keeps the result independent of the order in
+// which warps finish, and the number of atomics independent of the problem size.
+template <int NG>
+__device__ __forceinline__ void gn_stats_chunk(const float (&v)[32], bool row_ok, int lane, float& s_out, float& q_out) {
+    constexpr int CPG = 32 / NG;
+    float s[NG], q[NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int i = 0; i < CPG; ++i) { const float x = row_ok ? v[j * CPG + i] : 0.f; a += x; b = fmaf(x, x, b); }
+        s[j] = a; q[j] = b;
+    }
+    int n = NG, off = 16;
+#pragma unroll
+    for (; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            const float ss = upper ? s[j] : s[j + n / 2], sq = upper ? q[j] : q[j + n / 2];
+            const float rs = __shfl_xor_sync(0xffffffffu, ss, off), rq = __shfl_xor_sync(0xffffffffu, sq, off);
+            s[j] = (upper ? s[j + n / 2] : s[j]) + rs; q[j] = (upper ? q[j + n / 2] : q[j]) + rq;
+        }
+    }
+#pragma unroll
+    for (; off > 0; off >>= 1) { s[0] += __shfl_xor_sync(0xffffffffu, s[0], off); q[0] += __shfl_xor_sync(0xffffffffu, q[0], off); }
+    s_out += s[0]; q_out += q[0];       // every lane of a group class now holds that group's total over the warp's 32 rows
 }
 
 // Out-of-line generic epilogue for one 32-column chunk of one accumulator row per thread: partial chunks at the N edge,
@@ -448,6 +483,26 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             }
             __syncwarp();
         };
+        // GroupNorm statistics of the output (optional): per chunk slot, accumulated over this warp's tiles
+        float gn_s[4] = {0.f, 0.f, 0.f, 0.f}, gn_q[4] = {0.f, 0.f, 0.f, 0.f};
+        long long gn_key = -1;                                   // image * num_n_blocks + n_blk of the accumulated sums
+        auto gn_flush = [&]() {
+            if (gn_key < 0) return;
+            const int ng = 32 / p.gn_cpg, stages = ng == 8 ? 3 : ng == 4 ? 2 : ng == 2 ? 1 : 0;
+            if ((lane & ((32 >> stages) - 1)) == 0) {
+                unsigned long long* st = p.gn_stats + (gn_key / p.num_n_blocks) * (2 * p.gn_groups);
+                const int nb = (int)(gn_key % p.num_n_blocks);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (cpar + 2 * j >= nchunks) break;
+                    const int g = (nb * ncols_tile + (cpar + 2 * j) * 32) / p.gn_cpg + (stages ? (lane >> (5 - stages)) : 0);
+                    atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn(gn_s[j] * 1048576.0f));
+                    atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn(gn_q[j] * 1048576.0f));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { gn_s[j] = 0.f; gn_q[j] = 0.f; }
+        };
         bias_issue(first_tile, 0);
         if (res_fast) {
             int t_ = first_tile, m_ = 0, c_ = cpar;
@@ -533,6 +588,21 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                             f = __half22float2(*reinterpret_cast<const __half2*>(&res1[i])); v[16 + 2 * i] += f.x; v[16 + 2 * i + 1] += f.y;
                         }
                     }
+                    if (p.gn_stats) {                                   // GroupNorm statistics of the (fp16-rounded) output for the consumer
+                        const long long key = ((m - lane) / p.gn_rows) * p.num_n_blocks + n_blk;
+                        if (key != gn_key) { gn_flush(); gn_key = key; }
+                        float vr[32];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { const float2 f = __half22float2(__floats2half2_rn(v[2 * i], v[2 * i + 1])); vr[2 * i] = f.x; vr[2 * i + 1] = f.y; }
+                        const int slot = (c - cpar) >> 1;
+                        float ds = 0.f, dq = 0.f;
+                        if (p.gn_cpg == 4) gn_stats_chunk<8>(vr, row_ok, lane, ds, dq);
+                        else if (p.gn_cpg == 8) gn_stats_chunk<4>(vr, row_ok, lane, ds, dq);
+                        else if (p.gn_cpg == 16) gn_stats_chunk<2>(vr, row_ok, lane, ds, dq);
+                        else gn_stats_chunk<1>(vr, row_ok, lane, ds, dq);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (j == slot) { gn_s[j] += ds; gn_q[j] += dq; }
+                    }
                     if (p.out_f32) {
                         if (row_ok) {                                   // fp32 output (attention scores): 128 B per row and chunk
                             float* of = reinterpret_cast<float*>(p.D) + out_row(p, m) * p.ldd + nout;
@@ -559,6 +629,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             __syncwarp();
             if (lane == 0) { if (CG == 2) mbar_arrive_remote_relaxed(&tmem_empty[buf], 0); else mbar_arrive_relaxed(&tmem_empty[buf]); }
         }
+        if (p.gn_stats) gn_flush();
         if (p.trace && warp == W_EPI0 && lane == 0) { p.trace[blockIdx.x * 8 + 5] = tr_wait; p.trace[blockIdx.x * 8 + 6] = clock64() - tr_start; }
     }
     tc_fence_before();
@@ -648,7 +719,7 @@ static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out
 }
 
 static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
-    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0};
+    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0, nullptr, 0, 0};
     if (!ep) ep = &kDefault;
     p.D = D; p.ldd = ldd;
     p.col_bias = ep->col_bias; p.row_bias = ep->row_bias; p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
@@ -658,6 +729,18 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
     FIE_REQUIRE(p.act >= 0 && p.act <= 2, "epilogue: bad act %d", p.act);
     FIE_REQUIRE(!(p.act == FIE_ACT_GEGLU && (N % 64)), "GEGLU needs N %% 64 == 0");
     FIE_REQUIRE(!(p.residual && p.ld_res <= 0), "epilogue: residual needs ld_res");
+    p.gn_stats = (unsigned long long*)ep->gn_stats; p.gn_groups = ep->gn_groups; p.gn_rows = ep->gn_rows_per_image; p.gn_cpg = 0;
+    if (p.gn_stats) {
+        const int n_out = p.act == FIE_ACT_GEGLU ? N / 2 : N;
+        FIE_REQUIRE(p.gn_groups > 0 && (n_out % p.gn_groups) == 0, "epilogue: gn_groups must divide the output channels");
+        p.gn_cpg = n_out / p.gn_groups;
+        FIE_REQUIRE(p.gn_cpg <= 32 && (32 % p.gn_cpg) == 0 && p.gn_cpg >= 4, "epilogue: fused GroupNorm statistics need channels/group in {4, 8, 16, 32} (got %d)", p.gn_cpg);
+        FIE_REQUIRE(p.gn_rows > 0 && (p.gn_rows % 32) == 0, "epilogue: gn_rows_per_image must be a positive multiple of 32");
+        FIE_REQUIRE(!p.out_f32 && (n_out % 32) == 0 && (ldd % 16) == 0 && (reinterpret_cast<uintptr_t>(D) & 31) == 0 &&
+                    (!p.residual || ((p.ld_res % 16) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0)) &&
+                    (!p.row_bias || (p.rows_per_group % 32) == 0),
+                    "epilogue: fused GroupNorm statistics need the fast epilogue path (fp16 output, N %% 32 == 0, 32-byte aligned rows)");
+    }
     (void)M;
     return FIE_OK;
 }

@@ -1,7 +1,8 @@
 // GroupNorm(+SiLU) and LayerNorm on NHWC / token-major fp16 activations (memory-bound).
-//   GroupNorm: pass 1 accumulates per-(image, group) sum / sum-of-squares (fp32, 128-bit loads, warp-shuffle +
-//   shared-memory reduction, one atomicAdd pair per CTA and group); pass 2 applies (x-mean)*rstd*gamma+beta (+SiLU)
-//   and writes fp16.  An optional second source realises the torch.cat([h, skip]) of the UNet up blocks so the
+//   GroupNorm: pass 1 accumulates per-(image, group) sum / sum-of-squares (fp32 per thread, then 2^-20 fixed-point
+//   64-bit integer atomics in shared and global memory: integer addition is associative, so the statistics - and with
+//   them the whole edit - are bit-reproducible run to run); pass 2 applies (x-mean)*rstd*gamma+beta (+SiLU) and writes
+//   fp16.  Pass 1 is skipped when the producing GEMM / convolution already accumulated the statistics in its epilogue.  An optional second source realises the torch.cat([h, skip]) of the UNet up blocks so the
 //   concatenated tensor is only ever written once, already normalised.
 //   LayerNorm: one warp per row, row kept in registers, two-pass mean / variance in fp32.
 // Replaces F.group_norm / F.silu / F.layer_norm in diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock.
@@ -9,19 +10,23 @@
 
 namespace fie {
 
+// 2^-20 fixed point in a 64-bit two's-complement integer: exact, order-independent accumulation (|sum| < 2^43).
+__device__ __forceinline__ unsigned long long gn_fix(float v) { return (unsigned long long)__float2ll_rn(v * 1048576.0f); }
+__device__ __forceinline__ float gn_unfix(unsigned long long v) { return (float)((double)(long long)v * (1.0 / 1048576.0)); }
+
 struct GNArgs {
     const uint4* x0; const uint4* x1; uint4* out;
     int c0v, c1v, cv;          // channel vectors (8 fp16) per source / total
     long long hw; int groups; int cpg;   // channels per group
-    const float* gamma; const float* beta; float eps; int silu; float* stats;
+    const float* gamma; const float* beta; float eps; int silu; unsigned long long* stats;
     int rows_per_cta; int rows_in_flight;
 };
 
 __global__ void __launch_bounds__(512) k_gn_stats(GNArgs a) {
-    __shared__ float gs[64], gq[64];
+    __shared__ unsigned long long gs[64], gq[64];
     const int img = blockIdx.y;
     const int v = threadIdx.x % a.cv, rsub = threadIdx.x / a.cv;
-    for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) { if (i < a.groups) gs[i] = 0.f; else gq[i - a.groups] = 0.f; }
+    for (int i = threadIdx.x; i < 2 * a.groups; i += blockDim.x) { if (i < a.groups) gs[i] = 0ull; else gq[i - a.groups] = 0ull; }
     __syncthreads();
     float s[8], q[8];
 #pragma unroll
@@ -57,10 +62,10 @@ __global__ void __launch_bounds__(512) k_gn_stats(GNArgs a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { ts += s[j]; tq += q[j]; }
             int g = (v * 8) / a.cpg;
-            atomicAdd(&gs[g], ts); atomicAdd(&gq[g], tq);
+            atomicAdd(&gs[g], gn_fix(ts)); atomicAdd(&gq[g], gn_fix(tq));
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { int g = (v * 8 + j) / a.cpg; atomicAdd(&gs[g], s[j]); atomicAdd(&gq[g], q[j]); }
+            for (int j = 0; j < 8; ++j) { int g = (v * 8 + j) / a.cpg; atomicAdd(&gs[g], gn_fix(s[j])); atomicAdd(&gq[g], gn_fix(q[j])); }
         }
     }
     __syncthreads();
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(512) k_gn_apply(GNArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int c = v * 8 + j, g = c / a.cpg;
-        float sum = a.stats[((long long)img * a.groups + g) * 2], sq = a.stats[((long long)img * a.groups + g) * 2 + 1];
+        const float sum = gn_unfix(a.stats[((long long)img * a.groups + g) * 2]), sq = gn_unfix(a.stats[((long long)img * a.groups + g) * 2 + 1]);
         float mean = sum * inv_cnt, var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
         mu[j] = mean; rs[j] = rsqrtf(var + a.eps);
         ga[j] = __ldg(a.gamma + c); be[j] = __ldg(a.beta + c);
@@ -119,52 +124,63 @@ __global__ void __launch_bounds__(512) k_gn_apply(GNArgs a) {
     for (; r < r1; r += step) dst[r * a.cv] = apply(__ldg(src + r * stride));
 }
 
-// ---- LayerNorm: warp per row, up to 8 vectors (2048 channels) per lane ----
+// ---- LayerNorm: a warp owns a strided set of rows; gamma / beta live in shared memory (one global read per CTA instead of
+// four 128-bit loads per data vector and row), and the next row is already in flight while the current one is reduced ----
 template <int MAXV>
 __global__ void __launch_bounds__(256) k_layernorm(const uint4* __restrict__ x, uint4* __restrict__ out, long long rows, int cv,
                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+    extern __shared__ float4 gb[];                        // [2 * cv] gamma (two float4 per vector), then [2 * cv] beta
+    for (int i = threadIdx.x; i < 2 * cv; i += blockDim.x) {
+        gb[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        gb[2 * cv + i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const uint4* src = x + row * cv;
-    float vals[MAXV][8];
-    float sum = 0.f;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const float c = (float)(cv * 8), inv_c = 1.0f / c;
+    uint4 cur[MAXV], nxt[MAXV];
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int v = lane + i * 32;
-        if (v < cv) {
-            uint4 u = __ldg(src + v);
-            const __half2* h = reinterpret_cast<const __half2*>(&u);
+    for (int i = 0; i < MAXV; ++i) { const int v = lane + i * 32; cur[i] = (row < rows && v < cv) ? __ldg(x + row * cv + v) : make_uint4(0, 0, 0, 0); }
+    for (; row < rows; row += wstride) {
+        const long long rn = row + wstride;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) { const int v = lane + i * 32; nxt[i] = (rn < rows && v < cv) ? __ldg(x + rn * cv + v) : make_uint4(0, 0, 0, 0); }
+        float vals[MAXV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const __half2* h = reinterpret_cast<const __half2*>(&cur[i]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) { float2 f = __half22float2(h[j]); vals[i][2 * j] = f.x; vals[i][2 * j + 1] = f.y; sum += f.x + f.y; }
         }
-    }
-    const float c = (float)(cv * 8);
-    const float mean = warp_sum(sum) / c;
-    float sq = 0.f;
+        const float mean = warp_sum(sum) * inv_c;          // lanes beyond cv contributed zeros
+        float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        if (lane + i * 32 < cv) {
+        for (int i = 0; i < MAXV; ++i) {
+            if (lane + i * 32 < cv) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { float d = vals[i][j] - mean; sq += d * d; }
+                for (int j = 0; j < 8; ++j) { float d = vals[i][j] - mean; sq += d * d; }
+            }
         }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / c + eps);
-    uint4* dst = out + row * cv;
+        const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+        uint4* dst = out + row * cv;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        int v = lane + i * 32;
-        if (v < cv) {
-            float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + v * 2), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + v * 2 + 1);
-            float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + v * 2), b1 = __ldg(reinterpret_cast<const float4*>(beta) + v * 2 + 1);
-            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint4 o; __half2* oh = reinterpret_cast<__half2*>(&o);
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = lane + i * 32;
+            if (v < cv) {
+                const float4 g0 = gb[2 * v], g1 = gb[2 * v + 1], b0 = gb[2 * cv + 2 * v], b1 = gb[2 * cv + 2 * v + 1];
+                const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint4 o; __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                oh[j] = __floats2half2_rn((vals[i][2 * j] - mean) * rstd * g[2 * j] + b[2 * j], (vals[i][2 * j + 1] - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
-            dst[v] = o;
+                for (int j = 0; j < 4; ++j)
+                    oh[j] = __floats2half2_rn((vals[i][2 * j] - mean) * rstd * g[2 * j] + b[2 * j], (vals[i][2 * j + 1] - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
+                dst[v] = o;
+            }
         }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) cur[i] = nxt[i];
     }
 }
 
@@ -172,7 +188,7 @@ __global__ void __launch_bounds__(256) k_layernorm(const uint4* __restrict__ x, 
 using namespace fie;
 
 extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, void* out, int n, long long hw, int groups,
-                                 const float* gamma, const float* beta, float eps, int fuse_silu, float* stats_ws, void* stream_) {
+                                 const float* gamma, const float* beta, float eps, int fuse_silu, void* stats_ws, int stats_ready, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FIE_REQUIRE(x0 && out && gamma && beta && stats_ws, "fie_groupnorm_f16: null pointer");
     if (!x1) c1 = 0;
@@ -183,7 +199,8 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
     GNArgs a;
     a.x0 = (const uint4*)x0; a.x1 = (const uint4*)x1; a.out = (uint4*)out;
     a.c0v = c0 / 8; a.c1v = c1 / 8; a.cv = c / 8; a.hw = hw; a.groups = groups; a.cpg = c / groups;
-    a.gamma = gamma; a.beta = beta; a.eps = eps; a.silu = fuse_silu; a.stats = stats_ws;
+    a.gamma = gamma; a.beta = beta; a.eps = eps; a.silu = fuse_silu; a.stats = (unsigned long long*)stats_ws;
+    FIE_REQUIRE(!(stats_ready && c1), "fie_groupnorm_f16: producer statistics cannot cover a concatenated second source");
     a.rows_in_flight = 512 / a.cv; if (a.rows_in_flight < 1) a.rows_in_flight = 1;
     const int threads = ((a.cv * a.rows_in_flight + 31) / 32) * 32;
     // enough CTAs to cover the machine a few times, at least rows_in_flight*4 rows each
@@ -192,9 +209,11 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
     if (rows_per_cta < (long long)a.rows_in_flight * 4) rows_per_cta = (long long)a.rows_in_flight * 4;
     a.rows_per_cta = (int)rows_per_cta;
     dim3 grid((unsigned)((hw + rows_per_cta - 1) / rows_per_cta), n);
-    cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(float) * 2 * groups * n, stream);
-    if (e != cudaSuccess) { set_error("fie_groupnorm_f16: memset: %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
-    k_gn_stats<<<grid, threads, 0, stream>>>(a);
+    if (!stats_ready) {
+        cudaError_t e = cudaMemsetAsync(stats_ws, 0, sizeof(unsigned long long) * 2 * groups * n, stream);
+        if (e != cudaSuccess) { set_error("fie_groupnorm_f16: memset: %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+        k_gn_stats<<<grid, threads, 0, stream>>>(a);
+    }
     k_gn_apply<<<grid, threads, 0, stream>>>(a);
     return check_launch("fie_groupnorm_f16");
 }
@@ -202,9 +221,14 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
 extern "C" int fie_layernorm_f16(const void* x, void* out, long long rows, int c, const float* gamma, const float* beta, float eps, void* stream) {
     FIE_REQUIRE(x && out && gamma && beta && rows > 0 && c > 0 && (c % 8) == 0 && c <= 2048, "fie_layernorm_f16: c must be a multiple of 8, <= 2048");
     const int cv = c / 8;
-    const unsigned grid = (unsigned)((rows + 7) / 8);
-    if (cv <= 64) k_layernorm<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
-    else if (cv <= 160) k_layernorm<5><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
-    else k_layernorm<8><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
+    FIE_REQUIRE(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0, "fie_layernorm_f16: gamma / beta must be 16-byte aligned");
+    long long blocks = (rows + 7) / 8;
+    const long long cap = 148ll * 2;                      // two resident CTAs per SM (128 registers x 256 threads); each warp strides over its rows
+    if (blocks > cap) blocks = cap;
+    const unsigned grid = (unsigned)blocks;
+    const size_t smem = (size_t)4 * cv * sizeof(float4);
+    if (cv <= 64) k_layernorm<2><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
+    else if (cv <= 160) k_layernorm<5><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
+    else k_layernorm<8><<<grid, 256, smem, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, rows, cv, gamma, beta, eps);
     return check_launch("fie_layernorm_f16");
 }

@@ -106,6 +106,7 @@ class Resnet:
 
     def __init__(self, pk: _Packer, pre: str, eps: float, groups: int, temb_slot: Optional[List] = None):
         self.eps, self.groups = eps, groups
+        self.out_gn = 0       # > 0: conv2 also accumulates the GroupNorm statistics of the block output for its consumer
         self.n1 = pk.norm(pre + ".norm1")
         self.n2 = pk.norm(pre + ".norm2")
         self.w1, b1 = pk.conv3(pre + ".conv1")
@@ -125,16 +126,16 @@ class Resnet:
         hcur = ops.groupnorm(x, self.n1[0], self.n1[1], self.eps, True, self.groups, skip)
         if self.temb_off is not None:
             rb = temb_all[:, self.temb_off:self.temb_off + self.cout]
-            hcur = ops.conv3x3(hcur, self.w1, row_bias=rb, rows_per_group=h * w)
+            hcur = ops.conv3x3(hcur, self.w1, row_bias=rb, rows_per_group=h * w, gn_groups=self.groups)
         else:
-            hcur = ops.conv3x3(hcur, self.w1, col_bias=self.b1)
+            hcur = ops.conv3x3(hcur, self.w1, col_bias=self.b1, gn_groups=self.groups)
         hcur = ops.groupnorm(hcur, self.n2[0], self.n2[1], self.eps, True, self.groups)
         if self.sc is not None:
             res = ops.gemm(x, self.sc[0], a1=skip, col_bias=self.sc[1])
         else:
             assert skip is None
             res = x
-        return ops.conv3x3(hcur, self.w2, col_bias=self.b2, residual=res)
+        return ops.conv3x3(hcur, self.w2, col_bias=self.b2, residual=res, gn_groups=self.out_gn)
 
 
 class TransformerBlock:
@@ -375,7 +376,7 @@ class _VAEAttention:
                 p = ops.softmax_rows(s, scale)
                 ops.gemm(p, vt, out=o[r0:r1])
             ops.gemm(o, self.o[0], col_bias=self.o[1], residual=xr[i], out=out[i])
-        return out.view(n, hh, ww, c)
+        return out.view(n, hh, ww, c)       # (per-image GEMMs: the statistics of this output are left to the GroupNorm kernel)
 
 
 class VAE:
@@ -412,16 +413,23 @@ class VAE:
             self.d_up.append((res, us))
         self.d_norm = pk.norm("decoder.conv_norm_out")
         self.d_out = pk.conv3("decoder.conv_out", pad_cout_to=32)
+        # every block output of the VAE is consumed by a GroupNorm: let the producing epilogue accumulate its statistics
+        for res, _ in self.e_down + self.d_up:
+            for r in res:
+                r.out_gn = g
+        for blk in (self.e_mid, self.d_mid):
+            blk[0].out_gn = g; blk[2].out_gn = g
+        self.gn_groups = g
 
     def encode_moments(self, xp8: Tensor) -> Tensor:
         """xp8: zero-padded [N,H+2,W+8,8] fp16 image in [-1,1] (ops.preprocess_pad8) -> moments [N,H/8,W/8,2L] fp16."""
         cfg = self.cfg
-        h = ops.conv3x3_c8(xp8, self.e_in[0], col_bias=self.e_in[1])
+        h = ops.conv3x3_c8(xp8, self.e_in[0], col_bias=self.e_in[1], gn_groups=self.gn_groups)
         for res, ds in self.e_down:
             for r in res:
                 h = r(h)
             if ds is not None:
-                h = ops.conv3x3(h, ds[0], stride=2, pad_mode=1, col_bias=ds[1])
+                h = ops.conv3x3(h, ds[0], stride=2, pad_mode=1, col_bias=ds[1], gn_groups=self.gn_groups)
         h = self.e_mid[0](h)
         h = self.e_mid[1](h)
         h = self.e_mid[2](h)
@@ -443,7 +451,7 @@ class VAE:
             for r in res:
                 h = r(h)
             if us is not None:
-                h = ops.conv_up2x(h, us[0], col_bias=us[1])
+                h = ops.conv_up2x(h, us[0], col_bias=us[1], gn_groups=self.gn_groups)
         h = ops.groupnorm(h, self.d_norm[0], self.d_norm[1], cfg.norm_eps, True, cfg.norm_groups)
         n, hh, ww, _ = h.shape
         out = torch.empty((n, hh, ww, 4), dtype=torch.float16, device=h.device)

@@ -168,9 +168,30 @@ def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
     return out
 
 
+def _gn_stats_ok(n_out: int, groups: int, rows_per_image: int, ldd: int) -> bool:
+    """Can the GEMM epilogue accumulate the GroupNorm statistics of its output? (see fie_epilogue.gn_stats)"""
+    if groups <= 0 or n_out % groups or n_out % 32 or ldd % 16 or rows_per_image % 32:
+        return False
+    cpg = n_out // groups
+    return cpg in GN_FUSE_CPG
+
+
+# Channels-per-group for which the producing epilogue accumulates the GroupNorm statistics.  Measured on B200 (SDXL VAE, batch 8):
+# the extra epilogue work costs more than the saved statistics pass for 4 and 8 channels per group (narrow-N convolutions are
+# epilogue-sensitive), and wins for 16 and 32; the kernel supports {4, 8, 16, 32}.
+GN_FUSE_CPG = (16, 32)
+
+
+def _gn_stats_alloc(out: torch.Tensor, n_img: int, groups: int) -> torch.Tensor:
+    st = torch.zeros((n_img, groups, 2), dtype=torch.int64, device=out.device)
+    out._gn_stats = (st, groups)          # picked up by groupnorm() on this very tensor object
+    return st
+
+
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, groups: int = 32,
               x1: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x0 [N,H,W,C0] (+ optional concatenated x1 [N,H,W,C1]) -> [N,H,W,C0+C1] normalised (+SiLU)."""
+    """x0 [N,H,W,C0] (+ optional concatenated x1 [N,H,W,C1]) -> [N,H,W,C0+C1] normalised (+SiLU).  If x0 was produced by a
+    GEMM / conv call with ``gn_groups=groups``, its statistics already exist and only the apply pass runs."""
     _req(x0, torch.float16, "groupnorm")
     n = x0.shape[0]
     c0 = x0.shape[-1]
@@ -180,11 +201,13 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
         _req(x1, torch.float16, "groupnorm")
         c1 = x1.shape[-1]
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), dtype=torch.float16, device=x0.device)
-    stats = torch.empty((n, groups, 2), dtype=torch.float32, device=x0.device)
-    with _prof("groupnorm", 4.0 * out.numel(), "B", f"[{n},{hw},{c0}+{c1}]"):
+    pre = getattr(x0, "_gn_stats", None) if x1 is None else None
+    ready = pre is not None and pre[1] == groups and pre[0].shape[0] == n
+    stats = pre[0] if ready else torch.empty((n, groups, 2), dtype=torch.int64, device=x0.device)
+    with _prof("groupnorm", 4.0 * out.numel(), "B", f"[{n},{hw},{c0}+{c1}]" + (" fused-stats" if ready else "")):
         check(_lib.lib().fie_groupnorm_f16(_p(x0), c0, _p(x1), c1, _p(out), n, hw, groups, _p(gamma), _p(beta), float(eps), int(silu),
-                                            _p(stats), _stream()), "fie_groupnorm_f16")
-    _count(2)
+                                            _p(stats), int(ready), _stream()), "fie_groupnorm_f16")
+    _count(1 if ready else 2)
     return out
 
 
@@ -199,18 +222,21 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False):
+def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False, gn=None):
     ep = Epilogue()
     ep.col_bias = _p(col_bias); ep.row_bias = _p(row_bias); ep.rows_per_group = int(rows_per_group)
     ep.ld_row_bias = row_bias.stride(-2) if (row_bias is not None and row_bias.dim() >= 2) else 0
     ep.m_bias = _p(m_bias)
     ep.residual = _p(residual); ep.ld_res = residual.stride(-2) if residual is not None else 0
     ep.scale = float(scale); ep.act = int(act); ep.out_f32 = int(out_f32)
+    if gn is not None:                      # (stats tensor, groups, rows per image)
+        ep.gn_stats = _p(gn[0]); ep.gn_groups = int(gn[1]); ep.gn_rows_per_image = int(gn[2])
     return ep
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, n_valid: Optional[int] = None,
-         col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False) -> torch.Tensor:
+         col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False,
+         gn_groups: int = 0, gn_rows: int = 0) -> torch.Tensor:
     """D = epilogue(A @ W^T).  a: [..., K] fp16 rows (row stride may exceed K), w: [N, K] fp16; optional a1 continues K."""
     if a.dtype != torch.float16 or w.dtype != torch.float16 or not a.is_cuda:
         raise _lib.FieError("gemm: fp16 CUDA tensors required")
@@ -229,7 +255,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
     if out is None:
         out = torch.empty(tuple(a.shape[:-1]) + (n_out,), dtype=torch.float32 if out_f32 else torch.float16, device=a.device)
     ldd = out.stride(-2) if out.dim() >= 2 else n_out
-    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32)
+    gn = None
+    if gn_groups and gn_rows and not out_f32 and m % gn_rows == 0 and _gn_stats_ok(n_out, gn_groups, gn_rows, ldd):
+        gn = (_gn_stats_alloc(out, m // gn_rows, gn_groups), gn_groups, gn_rows)
+    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32, gn)
     with _prof("gemm", 2.0 * m * n * k, "FLOP", f"M{m} N{n} K{k} act{act} res{int(residual is not None)} f32{int(out_f32)}"):
         check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")
     _count()
@@ -237,7 +266,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad_mode: int = 0, cout_valid: Optional[int] = None,
-            out: Optional[torch.Tensor] = None, col_bias=None, row_bias=None, rows_per_group=1, residual=None, scale=1.0, act=ACT_NONE) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, col_bias=None, row_bias=None, rows_per_group=1, residual=None, scale=1.0, act=ACT_NONE,
+            gn_groups: int = 0) -> torch.Tensor:
     """x [N,H,W,Cin] fp16, w packed [Cout, 9*Cin] fp16 -> [N,H/stride,W/stride,cout_valid]."""
     _req(x, torch.float16, "conv3x3")
     n, h, wd, cin = x.shape
@@ -246,7 +276,11 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad_mode: int 
     cv = cout if cout_valid is None else cout_valid
     if out is None:
         out = torch.empty((n, h // stride, wd // stride, cv), dtype=torch.float16, device=x.device)
-    ep = _epilogue(col_bias, row_bias, rows_per_group, None, residual, scale, act, False)
+    gn = None
+    ohw = (h // stride) * (wd // stride)
+    if gn_groups and cv == cout and _gn_stats_ok(cout, gn_groups, ohw, out.stride(-2)):
+        gn = (_gn_stats_alloc(out, n, gn_groups), gn_groups, ohw)
+    ep = _epilogue(col_bias, row_bias, rows_per_group, None, residual, scale, act, False, gn)
     with _prof("conv3x3", 2.0 * n * (h // stride) * (wd // stride) * cv * 9 * cin, "FLOP", f"[{n},{h},{wd},{cin}]->{cv} s{stride}"):
         check(_lib.lib().fie_conv3x3_f16(_p(x), _p(w), _p(out), out.stride(-2), n, h, wd, cin, cout, cv, stride, pad_mode, ctypes.byref(ep), _stream()),
               "fie_conv3x3_f16")
@@ -254,7 +288,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, stride: int = 1, pad_mode: int 
     return out
 
 
-def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional[torch.Tensor] = None, gn_groups: int = 0) -> torch.Tensor:
     """Fused nearest-2x upsample + conv3x3.  x [N,H,W,Cin], w4 packed [4, Cout, 4*Cin] (weights.pack_conv_up2x) -> [N,2H,2W,Cout]."""
     _req(x, torch.float16, "conv_up2x")
     n, h, wd, cin = x.shape
@@ -262,14 +296,17 @@ def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional
     assert w4.shape[0] == 4 and w4.shape[2] == 4 * cin, (w4.shape, cin)
     if out is None:
         out = torch.empty((n, 2 * h, 2 * wd, cout), dtype=torch.float16, device=x.device)
-    ep = _epilogue(col_bias)
+    gn = None
+    if gn_groups and _gn_stats_ok(cout, gn_groups, h * wd, out.stride(-2)):
+        gn = (_gn_stats_alloc(out, n, gn_groups), gn_groups, h * wd)       # rows of each phase launch are INPUT pixels: h*w per image
+    ep = _epilogue(col_bias, gn=gn)
     with _prof("conv_up2x", 2.0 * n * 4 * h * wd * cout * 4 * cin, "FLOP", f"[{n},{h},{wd},{cin}]->{cout}"):
         check(_lib.lib().fie_conv_up2x_f16(_p(x), _p(w4), _p(out), out.stride(-2), n, h, wd, cin, cout, ctypes.byref(ep), _stream()), "fie_conv_up2x_f16")
     _count(4)
     return out
 
 
-def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] = None, col_bias=None, act=ACT_NONE) -> torch.Tensor:
+def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] = None, col_bias=None, act=ACT_NONE, gn_groups: int = 0) -> torch.Tensor:
     """Tensor-core conv_in.  xp: zero-padded [N,H+2,W+8,8] fp16 (:func:`preprocess_pad8`), w: [Cout, 384] (weights.pack_conv3x3_c8)
     -> [N,H,W,cout_valid]."""
     _req(xp, torch.float16, "conv3x3_c8")
@@ -279,7 +316,10 @@ def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] =
     cout = w.shape[0]
     cv = cout if cout_valid is None else cout_valid
     out = torch.empty((n, h, wd, cv), dtype=torch.float16, device=xp.device)
-    ep = _epilogue(col_bias, act=act)
+    gn = None
+    if gn_groups and cv == cout and _gn_stats_ok(cout, gn_groups, h * wd, out.stride(-2)):
+        gn = (_gn_stats_alloc(out, n, gn_groups), gn_groups, h * wd)
+    ep = _epilogue(col_bias, act=act, gn=gn)
     with _prof("conv_in_c8", 2.0 * out.numel() + 2.0 * xp.numel(), "B", f"[{n},{h},{wd},8]->{cv}"):
         check(_lib.lib().fie_conv3x3_c8_f16(_p(xp), _p(w), _p(out), out.stride(-2), n, h, wd, cout, cv, ctypes.byref(ep), _stream()), "fie_conv3x3_c8_f16")
     _count()

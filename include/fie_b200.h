@@ -66,9 +66,11 @@ int fie_softmax_rows_f32_to_f16(const void* s_f32, long long ld_in, void* p_f16,
 
 /* ---- GroupNorm(+SiLU), NHWC fp16: replaces F.group_norm (+F.silu) in ResnetBlock2D / Transformer2DModel ----
  * x0: [n, hw, c0]; optional x1: [n, hw, c1] is the channel-concatenated second source (torch.cat of the skip
- * connection in the up blocks); out: [n, hw, c0+c1].  stats_ws: fp32 [n, groups, 2] scratch. */
+ * connection in the up blocks); out: [n, hw, c0+c1].  stats_ws: int64 [n, groups, 2] (sum, sum of squares in 2^-20 fixed
+ * point: integer atomics make the statistics bit-reproducible).  stats_ready = 1: stats_ws was already filled by the producing
+ * GEMM / convolution (fie_epilogue.gn_stats) and the statistics pass is skipped (single source only). */
 int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, void* out, int n, long long hw, int groups,
-                      const float* gamma, const float* beta, float eps, int fuse_silu, float* stats_ws, void* stream);
+                      const float* gamma, const float* beta, float eps, int fuse_silu, void* stats_ws, int stats_ready, void* stream);
 
 /* ---- LayerNorm over the last dim, fp16 rows: replaces F.layer_norm in BasicTransformerBlock ---- */
 int fie_layernorm_f16(const void* x, void* out, long long rows, int c, const float* gamma, const float* beta,
@@ -92,6 +94,13 @@ typedef struct {
     float scale;             /* applied before the residual add */
     int act;                 /* FIE_ACT_* ; GEGLU: B rows interleaved per tile (value half | gate half), N_out = N/2 */
     int out_f32;             /* 1: D is fp32, else fp16 */
+    /* Optional GroupNorm statistics of the OUTPUT, accumulated by the epilogue so that the following fie_groupnorm_f16 can
+     * skip its statistics pass (stats_ready = 1): int64 [images][gn_groups][2] (sum, sum of squares; 2^-20 fixed point),
+     * zeroed by the caller.  Requires channels-per-group = N_out / gn_groups dividing 32, gn_rows_per_image % 32 == 0 and a
+     * launch that stays on the fast epilogue path (fp16 output, N_out % 32 == 0, 32-byte aligned rows); else FIE_ERR_INVALID. */
+    void* gn_stats;          /* or NULL */
+    int gn_groups;
+    long long gn_rows_per_image;
 } fie_epilogue;
 
 /* Accumulator tile width used for a GEGLU projection with N = 8C weight rows.  The host packs those rows per tile as

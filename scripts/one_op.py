@@ -33,11 +33,19 @@ elif kind == "attn":
     q = torch.randn((b * nq, heads * 64), device=dev).half(); k = torch.randn((b * nkv, heads * 64), device=dev).half(); v = torch.randn((b * nkv, heads * 64), device=dev).half()
     fn = lambda: ops.attention_d64(q, k, v, b, heads, nq, nkv)
     work = 4.0 * b * heads * nq * nkv * 64
+elif kind == "ln":
+    pass
 elif kind == "gn":
     n, hw, c = map(int, args[:3])
     x = torch.randn((n, hw, c), device=dev).half(); g = torch.ones(c, device=dev); bt = torch.zeros(c, device=dev)
     fn = lambda: ops.groupnorm(x, g, bt, 1e-5, True, 32)
     work = 4.0 * n * hw * c
+if kind == "ln":
+    rows, c = map(int, args[:2])
+    x = torch.randn((rows, c), device=dev).half(); g = torch.ones(c, device=dev); bt = torch.zeros(c, device=dev)
+    fn = lambda: ops.layernorm(x, g, bt)
+    work = 4.0 * rows * c
+    iters = 20
 for _ in range(2): fn()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

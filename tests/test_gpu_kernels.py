@@ -243,6 +243,48 @@ def test_conv3x3_halo_vs_per_tap(cuda_dev, n, h, w, cin, cout):
     assert float((out_h.float() - out_t.float()).abs().max()) <= 2e-2 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,groups", [(2, 64, 64, 128, 128, 32), (1, 128, 128, 64, 256, 32), (3, 32, 32, 128, 512, 32), (2, 16, 16, 64, 64, 16)])
+def test_conv_epilogue_groupnorm_statistics(cuda_dev, n, h, w, cin, cout, groups):
+    """GroupNorm statistics accumulated by the producing convolution's epilogue (fixed-point integer atomics) equal the
+    statistics kernel's, and the GroupNorm that consumes them matches F.group_norm; both are bit-reproducible."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
+    monkey_cpg, ops.GN_FUSE_CPG = ops.GN_FUSE_CPG, (4, 8, 16, 32)        # exercise every supported group width
+    try:
+        _check_conv_gn_stats(ops, pack_conv3x3, cuda_dev, n, h, w, cin, cout, groups)
+    finally:
+        ops.GN_FUSE_CPG = monkey_cpg
+
+
+def _check_conv_gn_stats(ops, pack_conv3x3, cuda_dev, n, h, w, cin, cout, groups):
+    x = _rand((n, h, w, cin), cuda_dev, 70).half()
+    wt = (_rand((cout, cin, 3, 3), cuda_dev, 71) / math.sqrt(9 * cin)).half()
+    bias = _rand((cout,), cuda_dev, 72)
+    res = _rand((n, h, w, cout), cuda_dev, 73).half()
+    gamma = _rand((cout,), cuda_dev, 74) * 0.1 + 1
+    beta = _rand((cout,), cuda_dev, 75) * 0.1
+    wp = pack_conv3x3(wt)
+    y = ops.conv3x3(x, wp, col_bias=bias, residual=res, gn_groups=groups)
+    assert hasattr(y, "_gn_stats")
+    st = y._gn_stats[0].clone()
+    out_fused = ops.groupnorm(y, gamma, beta, 1e-6, True, groups)
+    y2 = ops.conv3x3(x, wp, col_bias=bias, residual=res)                       # same values, no producer statistics
+    assert torch.equal(y, y2) and not hasattr(y2, "_gn_stats")
+    out_plain = ops.groupnorm(y2, gamma, beta, 1e-6, True, groups)
+    ref = F.silu(F.group_norm(y.float().permute(0, 3, 1, 2), groups, gamma, beta, 1e-6)).permute(0, 2, 3, 1)
+    assert float((out_fused.float() - ref).abs().max()) < 8e-3
+    assert float((out_fused.float() - out_plain.float()).abs().max()) < 4e-3       # fp32 (pre-rounding) vs fp16 inputs of the statistics
+    # statistics against a float64 reduction of the fp16 output
+    yg = y.double().view(n, h * w, groups, cout // groups)
+    s_ref, q_ref = yg.sum(dim=(1, 3)), (yg * yg).sum(dim=(1, 3))
+    s_got, q_got = st[..., 0].double() / 2 ** 20, st[..., 1].double() / 2 ** 20
+    assert float(((s_got - s_ref).abs() / (q_ref.sqrt() + 1)).max()) < 5e-2 and float(((q_got - q_ref).abs() / q_ref).max()) < 2e-3
+    # reproducible: integer accumulation does not depend on the order in which tiles finish
+    y3 = ops.conv3x3(x, wp, col_bias=bias, residual=res, gn_groups=groups)
+    assert torch.equal(y3._gn_stats[0], st)
+    assert torch.equal(ops.groupnorm(y2, gamma, beta, 1e-6, True, groups), out_plain)
+
+
 def test_conv3x3_small_cout_and_epilogue(cuda_dev):
     ops = _ops()
     from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
