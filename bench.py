@@ -238,8 +238,14 @@ def main():
     tc_calls = sum(fam[k]["calls"] * (4 if k == "conv_up2x" else 1) for k in TC if k in fam)
     total_ms = sum(d["ms"] for d in fam.values())
     achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:            # DRAM bytes per launch from the committed ncu --set full capture (profiles/); None if absent
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")))
+        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+    except Exception:
+        pass
     roofline = {"kernel": "k_gemm_conv (tcgen05 GEMM / implicit-GEMM conv3x3)", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src, "launches_per_step": tc_calls,
+                "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": tc_calls,
                 "share_of_step": tc_ms / total_ms if total_ms else None,
                 "flop_per_launch_avg": tc_flop / max(tc_calls, 1), "ms_per_launch_avg": tc_ms / max(tc_calls, 1)}
     breakdown = {k: {"calls": d["calls"], "ms": round(d["ms"], 3), "rate": (d["work"] / (d["ms"] * 1e-3) / (1e12 if d["unit"] == "FLOP" else 1e9)) if d["ms"] > 0 else 0.0,

@@ -257,6 +257,179 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cross-attention form (nkv <= 128: the 77 prompt tokens): one K/V tile, so the work per (batch, head, 256 query rows) is a
+// short latency chain (Q K^T -> softmax -> P V -> store) and one CTA per item, as above, spends most of its life in set-up.
+// Here 148 persistent CTAs each walk a contiguous range of items; the producer keeps the next item's Q / K / V in flight in a
+// second shared-memory buffer, and TMEM allocation, barrier set-up and descriptor fetches are paid once per CTA.
+// Same warp roles as k_attention_d64.  Barriers flip once per item (parity = item counter & 1).
+// ------------------------------------------------------------------------------------------------
+constexpr int ATT1_OFF_KV = 2 * ATT_QT * ATT_TILE_BYTES;                       // after Q[2 buffers][2 tiles]
+constexpr int ATT1_OFF_P = ATT1_OFF_KV + 2 * 2 * ATT_TILE_BYTES;               // after K/V[2 buffers]
+constexpr int ATT1_OFF_BAR = ATT1_OFF_P + ATT_QT * 32768;
+constexpr int ATT1_SMEM = ATT1_OFF_BAR + 256;
+
+__global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_constant__ AttnParams p, int heads, int batch) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;                                   // buffer u: Q tiles at u * 32K
+    uint8_t* sKV = smem + ATT1_OFF_KV;                    // buffer u: K at u * 32K, V at u * 32K + 16K
+    uint8_t* sP = smem + ATT1_OFF_P;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT1_OFF_BAR);
+    uint64_t* ld_full = bars;                // [2] Q + K + V of an item landed
+    uint64_t* ld_empty = bars + 2;           // [2] both P V of the item completed: its buffer may be refilled
+    uint64_t* s_full = bars + 4;             // [2]
+    uint64_t* p_full = bars + 6;             // [2]
+    uint64_t* o_full = bars + 8;             // [2]
+    uint64_t* o_free = bars + 10;            // [2] S_q and O_q have been read: the next item may overwrite them
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("fie: attention smem base misaligned\n"); __trap(); }
+
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+    const int nqp = (p.nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM);          // 256-row query blocks per (batch, head)
+    const int items = batch * heads * nqp;
+    const int per = (items + gridDim.x - 1) / gridDim.x;
+    const int it0 = blockIdx.x * per, it1 = min(it0 + per, items);
+
+    if (threadIdx.x == 0) {
+        for (int u = 0; u < 2; ++u) {
+            mbar_init(&ld_full[u], 1); mbar_init(&ld_empty[u], 1);
+            mbar_init(&s_full[u], 1); mbar_init(&p_full[u], 128); mbar_init(&o_full[u], 1); mbar_init(&o_free[u], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.v_map); }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            for (int it = it0, n = 0; it < it1; ++it, ++n) {
+                const int u = n & 1; const uint32_t ph = (uint32_t)((n >> 1) & 1);
+                const int qp = it % nqp, head = (it / nqp) % heads, b = it / (nqp * heads);
+                mbar_wait(&ld_empty[u], ph ^ 1);
+                mbar_arrive_expect_tx(&ld_full[u], (ATT_QT + 2) * ATT_TILE_BYTES);
+                for (int q = 0; q < ATT_QT; ++q)
+                    tma_load_3d(&p.q_map, &ld_full[u], sQ + (u * ATT_QT + q) * ATT_TILE_BYTES, head * ATT_D, (qp * ATT_QT + q) * ATT_BM, b);
+                tma_load_3d(&p.k_map, &ld_full[u], sKV + u * 2 * ATT_TILE_BYTES, head * ATT_D, 0, b);
+                tma_load_3d(&p.v_map, &ld_full[u], sKV + u * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, head * ATT_D, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_qk = umma_idesc_f16(ATT_BM, ATT_BN, 0, 0);
+        const uint32_t idesc_pv = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);   // B (= V) is MN-major
+        const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
+        for (int it = it0, n = 0; it < it1; ++it, ++n) {
+            const int u = n & 1; const uint32_t ph = (uint32_t)((n >> 1) & 1), par = (uint32_t)(n & 1);
+            mbar_wait(&ld_full[u], ph);
+            for (int q = 0; q < ATT_QT; ++q) {
+                if (n > 0) mbar_wait(&o_free[q], par ^ 1);             // previous item's S_q / O_q consumed
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint64_t ad = umma_desc_sw128(aQ + (u * ATT_QT + q) * ATT_TILE_BYTES), bd = umma_desc_sw128(aKV + u * 2 * ATT_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < ATT_D / 16; ++k) umma_f16(tmem + q * 128, ad + 2 * k, bd + 2 * k, idesc_qk, k ? 1u : 0u);
+                    umma_commit(&s_full[q]);
+                }
+                __syncwarp();
+            }
+            for (int q = 0; q < ATT_QT; ++q) {
+                mbar_wait(&p_full[q], par);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t aV = aKV + u * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < ATT_BN / 16; ++k) {
+                        if (k * 16 >= p.nkv) break;                       // P columns / V rows beyond nkv contribute nothing
+                        const uint64_t ad = umma_desc_sw128(aP + q * 32768 + (k >> 2) * 16384 + (k & 3) * 32);
+                        const uint64_t bd = umma_desc_sw128(aV + k * 2048, 1024, 1024);
+                        umma_f16(tmem + 256 + q * 64, ad, bd, idesc_pv, k ? 1u : 0u);
+                    }
+                    umma_commit(&o_full[q]);
+                    if (q == ATT_QT - 1) umma_commit(&ld_empty[u]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr;
+        const float sl2 = p.scale_log2;
+        uint8_t* prow = sP + q * 32768 + row * 128;
+        const int sw = row & 7;
+        const int kv = p.nkv;                                 // <= 128 valid columns
+        const int kv16 = (kv + 15) & ~15;
+        for (int it = it0, n = 0; it < it1; ++it, ++n) {
+            const uint32_t par = (uint32_t)(n & 1);
+            const int qp = it % nqp, head = (it / nqp) % heads, b = it / (nqp * heads);
+            mbar_wait(&s_full[q], par);
+            tc_fence_after();
+            uint32_t ra[64], rb[64];
+            tmem_ld_32x64(tS, ra);
+            tmem_ld_32x64(tS + 64, rb);
+            tmem_ld_wait();
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) { if (i < kv) mx = fmaxf(mx, __uint_as_float(ra[i])); if (64 + i < kv) mx = fmaxf(mx, __uint_as_float(rb[i])); }
+            const float mneg = -mx * sl2;
+            float l = 0.f;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint8_t* base = prow + hf * 16384;
+#pragma unroll
+                for (int uu = 0; uu < 8; ++uu) {
+                    if (hf * 64 + uu * 8 >= kv16) break;          // 16-column K blocks beyond nkv are never read by the P V MMAs
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = uu * 8 + 2 * i;
+                        const float s0 = __uint_as_float(hf ? rb[c] : ra[c]), s1 = __uint_as_float(hf ? rb[c + 1] : ra[c + 1]);
+                        float p0 = (hf * 64 + c < kv) ? ex2_approx(fmaf(s0, sl2, mneg)) : 0.f;
+                        float p1 = (hf * 64 + c + 1 < kv) ? ex2_approx(fmaf(s1, sl2, mneg)) : 0.f;
+                        l += p0 + p1;
+                        __half2 h = __floats2half2_rn(p0, p1);
+                        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(base + ((uu ^ sw) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(&p_full[q]);
+            mbar_wait(&o_full[q], par);
+            tc_fence_after();
+            uint32_t r[64];
+            tmem_ld_32x64(tO, r);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&o_free[q]);                              // S_q (read above) and O_q are in registers
+            const float inv_l = 1.0f / l;
+            const int qrow = (qp * ATT_QT + q) * ATT_BM + row;
+            if (qrow < p.nq) {
+                __half* orow = p.out + ((long long)b * p.nq + qrow) * p.ldo + head * ATT_D;
+#pragma unroll
+                for (int uu = 0; uu < 8; ++uu) {
+                    uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int e = uu * 8 + 2 * i;
+                        hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
+                    }
+                    *reinterpret_cast<uint4*>(orow + uu * 8) = v;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 }  // namespace fie
 using namespace fie;
 
@@ -289,6 +462,22 @@ extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k
         cudaError_t e = cudaFuncSetAttribute(k_attention_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
         attr = true;
+    }
+    static int kv1 = -1;
+    if (kv1 < 0) { const char* e = getenv("FIE_ATT_KV1"); kv1 = e ? atoi(e) : 1; }
+    if (kv1 && nkv <= ATT_BN) {
+        // cross-attention: persistent CTAs over (batch, head, 256-row query block) items
+        static bool attr1 = false;
+        if (!attr1) {
+            cudaError_t e = cudaFuncSetAttribute(k_attention_d64_kv1, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64_kv1): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+            attr1 = true;
+        }
+        const long long items = (long long)b * heads * ((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM));
+        int sms = 148; { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+        const int grid1 = (int)(items < sms ? items : sms);
+        k_attention_d64_kv1<<<grid1, 384, ATT1_SMEM, (cudaStream_t)stream>>>(p, heads, b);
+        return check_launch("fie_attention_d64_f16");
     }
     dim3 grid((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM), heads, b);
     k_attention_d64<<<grid, 384, ATT_SMEM, (cudaStream_t)stream>>>(p);

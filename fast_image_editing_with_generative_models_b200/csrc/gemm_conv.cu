@@ -752,8 +752,14 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     const int mt = p.mt;
     int kps = (g_force_kps > 0) ? g_force_kps : (p.num_kb >= 4 ? 2 : 1);
     if (kps == 2 && SMEM_BUDGET / (2 * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2)) < 2) kps = 1;
-    int halo_tps = 1;                              // halo: ring stage = B tiles of 3 taps (one kernel row) when two such stages fit, else 1 tap
-    if (p.mode == 2) { kps = 1; if (2 * 3 * (p.block_n / cg) * BLOCK_K * 2 <= SMEM_BUDGET - HALO_A_BYTES) halo_tps = 3; if (g_force_kps == 1) halo_tps = 1; }
+    int halo_tps = 1;                              // halo: ring stage = B tiles of 9 taps (narrow N), else 3 (one kernel row), else 1, as two stages fit
+    if (p.mode == 2) {
+        kps = 1;
+        const int bsub = (p.block_n / cg) * BLOCK_K * 2;
+        if (2 * 9 * bsub <= SMEM_BUDGET - HALO_A_BYTES) halo_tps = 9;          // one handshake per channel chunk: N <= 80 would be handshake-bound otherwise
+        else if (2 * 3 * bsub <= SMEM_BUDGET - HALO_A_BYTES) halo_tps = 3;
+        if (g_force_kps == 1) halo_tps = 1;
+    }
     p.kps = p.mode == 2 ? halo_tps : kps;
     const int stage_bytes = p.mode == 2 ? halo_tps * (p.block_n / cg) * BLOCK_K * 2 : kps * (mt * A_STAGE_BYTES + (p.block_n / cg) * BLOCK_K * 2);
     int stages = (p.mode == 2 ? SMEM_BUDGET - HALO_A_BYTES : SMEM_BUDGET) / stage_bytes; if (stages > MAX_STAGES) stages = MAX_STAGES;

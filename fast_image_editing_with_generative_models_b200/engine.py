@@ -15,6 +15,7 @@ NHWC fp16 activations through the hand-written kernels in ``csrc/``.  Weights ar
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -358,7 +359,12 @@ class _VAEAttention:
         self.norm = pk.norm(pre + ".group_norm")
         self.q, self.k, self.v, self.o = (pk.linear(f"{pre}.{n}") for n in ("to_q", "to_k", "to_v", "to_out.0"))
 
-    def __call__(self, x: Tensor, chunk: int = 4096) -> Tensor:
+    # rows of fp32 scores materialised at a time: 1024 x 16384 x 4 B = 64 MiB stays L2-resident between the score GEMM, the row
+    # softmax and the P V GEMM (4096-row chunks of 256 MiB went through HBM three times)
+    CHUNK = int(os.environ.get("FIE_VAE_CHUNK", "1024"))
+
+    def __call__(self, x: Tensor, chunk: Optional[int] = None) -> Tensor:
+        chunk = chunk or self.CHUNK
         n, hh, ww, c = x.shape
         ntok = hh * ww
         hn = ops.groupnorm(x, self.norm[0], self.norm[1], self.eps, False, self.groups).view(n, ntok, c)

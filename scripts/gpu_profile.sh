@@ -16,11 +16,11 @@ timeout -k 10 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 
 echo "ncu list rc=$?"
 # full captures of the dominant kernels (inside the 4th step = the timed one)
 timeout -k 10 600 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:k_gemm_conv -s $((NL * 3 * 1317 / 2482 + 300)) -c 4 \
+timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:k_gemm_conv -s $((NL * 3 * 1317 / 2482 + 300)) -c 6 \
     -o gpurun_out/prof_gemm_$TAG -f $CMD > gpurun_out/ncu_gemm_$TAG.log 2>&1
 echo "ncu gemm rc=$?"
 timeout -k 10 600 $CMD > gpurun_out/plain3_$TAG.log 2>&1 &&
-timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:"k_attention|k_gn_apply|k_gn_stats|k_layernorm" -s 2000 -c 8 \
+timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:"k_attention|k_gn_apply|k_gn_stats|k_layernorm|k_nms|k_union" -s 2000 -c 10 \
     -o gpurun_out/prof_attn_norm_$TAG -f $CMD > gpurun_out/ncu_attn_$TAG.log 2>&1
 echo "ncu attn/norm rc=$?"
 ls -la gpurun_out | tail -20

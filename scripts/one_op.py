@@ -28,6 +28,13 @@ elif kind == "conv":
     bias = torch.randn((cout,), device=dev)
     fn = lambda: ops.conv3x3(x, w, col_bias=bias)
     work = 2.0 * nb * h * wd * cout * 9 * cin
+elif kind == "up2x":
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv_up2x
+    nb, h, wd, cin, cout = map(int, args[:5])
+    x = torch.randn((nb, h, wd, cin), device=dev).half(); w = pack_conv_up2x(torch.randn((cout, cin, 3, 3), device=dev) / math.sqrt(9 * cin))
+    bias = torch.randn((cout,), device=dev)
+    fn = lambda: ops.conv_up2x(x, w, col_bias=bias)
+    work = 2.0 * nb * 4 * h * wd * cout * 4 * cin
 elif kind == "attn":
     b, heads, nq, nkv = map(int, args[:4])
     q = torch.randn((b * nq, heads * 64), device=dev).half(); k = torch.randn((b * nkv, heads * 64), device=dev).half(); v = torch.randn((b * nkv, heads * 64), device=dev).half()

@@ -355,7 +355,8 @@ def test_conv3x3_c8_image_input(cuda_dev, n, h, w, cout, silu):
 
 
 # ------------------------------------------------------------------ attention
-@pytest.mark.parametrize("b,heads,nq,nkv", [(1, 1, 128, 128), (2, 2, 256, 256), (2, 10, 1024, 1024), (2, 4, 256, 77), (1, 2, 64, 64), (2, 2, 4096, 4096), (1, 3, 200, 333)])
+@pytest.mark.parametrize("b,heads,nq,nkv", [(1, 1, 128, 128), (2, 2, 256, 256), (2, 10, 1024, 1024), (2, 4, 256, 77), (1, 2, 64, 64), (2, 2, 4096, 4096), (1, 3, 200, 333),
+                                            (16, 20, 1024, 77), (3, 5, 1000, 77), (2, 10, 4096, 77), (1, 1, 300, 1), (4, 7, 520, 128)])
 def test_attention_d64(cuda_dev, b, heads, nq, nkv):
     ops = _ops()
     c = heads * 64
