@@ -166,6 +166,7 @@ __device__ __noinline__ void epi_slow_chunk(const GemmParams& p, uint32_t taddr,
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) + mb;
+    if (nout >= p.n_store && p.act != FIE_ACT_GEGLU) return;                      // chunk entirely beyond the stored columns
     if (p.col_bias) for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(p.col_bias + nacc + i);
     if (rb) for (int i = 0; i < 32; ++i) if (nacc + i < p.N) v[i] += __ldg(rb + nacc + i);
     if (p.act == FIE_ACT_GEGLU) {
@@ -188,7 +189,12 @@ __device__ __noinline__ void epi_slow_chunk(const GemmParams& p, uint32_t taddr,
             const __half* rp = p.residual + m * p.ld_res + nout;
             for (int i = 0; i < 32; ++i) if (nout + i < p.n_store) v[i] += __half2float(rp[i]);
         }
-        store_chunk(p, m, nout, v);
+        if (!p.out_f32 && !p.up2 && nout == 0 && p.n_store <= 4 && p.ldd == 4 && (reinterpret_cast<uintptr_t>(p.D) & 7) == 0) {
+            // <= 4 output channels in a 4-wide row (decoder conv_out: 3 of 4): one 8-byte store per pixel; the spare lane gets 0
+            const __half2 h0 = __floats2half2_rn(v[0], p.n_store > 1 ? v[1] : 0.f), h1 = __floats2half2_rn(p.n_store > 2 ? v[2] : 0.f, p.n_store > 3 ? v[3] : 0.f);
+            uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.D) + m * 4) = u;
+        } else store_chunk(p, m, nout, v);
     }
 }
 
