@@ -14,6 +14,7 @@ CUDA kernels behind ``include/fie_b200.h``.  Differences, all forced by the envi
 """
 from __future__ import annotations
 
+import os
 import zlib
 from typing import Callable, Dict, Optional
 
@@ -73,6 +74,7 @@ class FastEditor:
             raise RuntimeError("FastEditor (B200-native) needs a CUDA device; there is no CPU path")
         if not torch.cuda.is_available():
             raise RuntimeError("FastEditor (B200-native): no CUDA device available")
+        tiny = tiny or os.environ.get("FIE_TINY") == "1"     # small same-topology models: CLI smoke tests
         if state is None:
             self._say("[FastEditor] Generating seeded synthetic weights (no checkpoints available offline)...")
             state = model_zoo.synthetic_state(model_name, use_full_controlnet, tiny)

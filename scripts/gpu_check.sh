@@ -21,5 +21,6 @@ run conv tests/test_gpu_kernels.py -k "test_conv3x3 and not cin4"
 run attention tests/test_gpu_kernels.py -k "attention"
 run engine tests/test_gpu_engine.py -s
 run fullsize tests/test_gpu_fullsize.py -s
+run dropin tests/test_gpu_dropin.py
 for extra in "$@"; do run extra tests -k "$extra"; done
 grep -E "^=== .* rc=" gpurun_out/gpu_check.log

@@ -1,0 +1,83 @@
+"""GPU: the reference's plugin surface end to end — ``FastEditor`` through the reference's import path, and the two CLIs.
+Small same-topology models (``tiny=True`` / ``FIE_TINY=1``) keep this fast; the arithmetic parity is covered by
+test_gpu_engine.py / test_gpu_fullsize.py, this file checks the contract of the boundary (reference ``src/pipeline.py:183-293``,
+``run_single_image.py``, ``run_batch.py``)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def editor(cuda_dev):
+    from src.pipeline import FastEditor
+    return FastEditor(model_name="ssd-1b", device="cuda", enable_cpu_offload=False, tiny=True, verbose=False)
+
+
+def _image(seed, size=(640, 480)):
+    from fast_image_editing_with_generative_models_b200.synthetic import synthetic_image
+    return Image.fromarray(synthetic_image(seed, 1024, 1024)).resize(size)
+
+
+def test_edit_contract_and_seed_reproducibility(editor):
+    editor.pipe.set_progress_bar_config(disable=True)                          # run_batch.py:157-158
+    img = _image(1)
+    a = editor.edit(image=img, prompt="a rusty bicycle", negative_prompt="", num_inference_steps=4, guidance_scale=1.5,
+                    controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200, seed=42)
+    assert isinstance(a, Image.Image) and a.mode == "RGB" and a.size == (1024, 1024)      # src/pipeline.py:251,274
+    b = editor.edit(image=img, prompt="a rusty bicycle", seed=42)              # second call: CUDA-graph replay of the same key
+    assert np.array_equal(np.array(a), np.array(b)), "same seed must give the same image (bit-reproducible statistics)"
+    c = editor.edit(image=img, prompt="a rusty bicycle", seed=43)
+    d = editor.edit(image=img, prompt="a wooden boat", seed=42)
+    assert not np.array_equal(np.array(a), np.array(c)) and not np.array_equal(np.array(a), np.array(d))
+    e = editor.edit(image=img, prompt="a rusty bicycle", strength=0.5, seed=42)           # another schedule: its own graph
+    assert e.size == (1024, 1024) and not np.array_equal(np.array(a), np.array(e))
+    mem = editor.get_memory_usage()
+    assert mem["allocated_gb"] > 0 and mem["reserved_gb"] >= mem["allocated_gb"]
+    editor.clear_memory()
+
+
+def test_preprocess_image_is_cv2_canny(editor):
+    from oracle import c_oracle
+    img = _image(2, (1024, 1024))
+    edges = np.array(editor.preprocess_image(img, 100, 200))
+    assert edges.shape == (1024, 1024, 3) and edges.dtype == np.uint8
+    ref = c_oracle.canny_u8(np.array(img)[None], 100, 200)[0]
+    assert np.array_equal(edges[..., 0], ref) and np.array_equal(edges[..., 1], ref) and np.array_equal(edges[..., 2], ref)
+    gray = np.array(img.convert("L"))
+    assert np.array(editor.preprocess_image(gray, 50, 150)).shape == (1024, 1024, 3)       # 2-D input: src/pipeline.py:196-203
+
+
+def test_editor_survives_a_failed_call(editor):
+    with pytest.raises(Exception):
+        editor.edit(image=None, prompt="x")
+    out = editor.edit(image=_image(3), prompt="x", seed=1)
+    assert out.size == (1024, 1024)
+
+
+def test_clis_run_unmodified(cuda_dev, tmp_path, monkeypatch):
+    monkeypatch.setenv("FIE_TINY", "1")
+    import run_batch
+    import run_single_image
+    src = tmp_path / "src_images"
+    (src / "0_random").mkdir(parents=True)
+    mapping = {}
+    for i in range(3):
+        rel = f"0_random/{i:012d}.jpg"
+        _image(10 + i, (512, 512)).save(src / rel)
+        mapping[f"{i:012d}"] = {"image_path": rel, "original_prompt": "a photo", "editing_prompt": f"a painting number {i}", "editing_type_id": "0"}
+    mapping["bad"] = {"image_path": "0_random/missing.jpg", "editing_prompt": "x", "editing_type_id": "0"}
+    mf = tmp_path / "mapping_file.json"
+    mf.write_text(json.dumps(mapping))
+    out = tmp_path / "outputs"
+    run_single_image.main(["--image", str(src / "0_random/000000000000.jpg"), "--prompt", "a rusty bicycle", "--model", "ssd-1b", "--seed", "7",
+                           "--output_dir", str(out), "--no_cpu_offload"])
+    singles = list((out / "single" / "edited" / "ssd-1b_fp16").glob("edited_*.jpg"))
+    assert len(singles) == 1 and Image.open(singles[0]).size == (1024, 1024)
+    run_batch.main(["--mapping_file", str(mf), "--source_dir", str(src), "--output_dir", str(out), "--model", "ssd-1b", "--seed", "7", "--no_cpu_offload"])
+    edited = sorted(p.name for p in out.rglob("0_random/*.jpg") if "single" not in str(p))
+    assert edited == [f"{i:012d}.jpg" for i in range(3)]                        # the missing source is counted as failed, not fatal
