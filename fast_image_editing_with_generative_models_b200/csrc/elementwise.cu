@@ -105,17 +105,79 @@ __global__ void k_sincos(SinCosArgs a, int count, int dim, __half* __restrict__ 
     }
 }
 
-// one CTA per row; cols up to 64K
-__global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ s, long long ld_in, __half* __restrict__ p, long long ld_out, int cols, float scale) {
+// one CTA per row; cols up to 64K.  T = float (raw scores, scaled here) or __half (scores already scaled by the GEMM epilogue).
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); } };
+template <> struct Vec4<__half> {
+    static __device__ __forceinline__ float4 ld(const __half* p) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+
+// Single-pass form for rows of at most 256 x 4 x NV columns: the row lives in registers (NV independent vector loads in flight
+// per thread), one block reduction for the max and one for the sum.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) k_softmax_rows_reg(const T* __restrict__ s, long long ld_in, __half* __restrict__ p, long long ld_out, int cols, float scale) {
     __shared__ float red[8];
     __shared__ float bc;
-    const float* row = s + (long long)blockIdx.x * ld_in;
+    const T* row = s + (long long)blockIdx.x * ld_in;
+    __half* orow = p + (long long)blockIdx.x * ld_out;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float4 v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = (k * 256 + tid) * 4;
+        v[k] = i + 4 <= cols ? Vec4<T>::ld(row + i) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) mx = fmaxf(mx, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+    mx = warp_max(mx);
+    if (lane == 0) red[wid] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bc = m; }
+    __syncthreads();
+    mx = bc;
+    const float sl2 = scale * 1.4426950408889634f, off = -mx * sl2;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        v[k].x = exp2f(fmaf(v[k].x, sl2, off)); v[k].y = exp2f(fmaf(v[k].y, sl2, off)); v[k].z = exp2f(fmaf(v[k].z, sl2, off)); v[k].w = exp2f(fmaf(v[k].w, sl2, off));
+        sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    if (tid == 0) { float t = 0; for (int i = 0; i < 8; ++i) t += red[i]; bc = 1.0f / t; }
+    __syncthreads();
+    const float inv = bc;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = (k * 256 + tid) * 4;
+        if (i + 4 <= cols) {
+            __half2 a = __floats2half2_rn(v[k].x * inv, v[k].y * inv), b = __floats2half2_rn(v[k].z * inv, v[k].w * inv);
+            uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+            *reinterpret_cast<uint2*>(orow + i) = u;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_softmax_rows(const T* __restrict__ s, long long ld_in, __half* __restrict__ p, long long ld_out, int cols, float scale) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const T* row = s + (long long)blockIdx.x * ld_in;
     __half* orow = p + (long long)blockIdx.x * ld_out;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     float mx = -INFINITY;
     for (int i = tid * 4; i < cols; i += 1024) {
-        if (i + 4 <= cols) { float4 v = *reinterpret_cast<const float4*>(row + i); mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); }
-        else for (int j = i; j < cols; ++j) mx = fmaxf(mx, row[j]);
+        if (i + 4 <= cols) { float4 v = Vec4<T>::ld(row + i); mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w))); }
+        else for (int j = i; j < cols; ++j) mx = fmaxf(mx, to_f(row[j]));
     }
     mx = warp_max(mx);
     if (lane == 0) red[wid] = mx;
@@ -126,8 +188,8 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ 
     const float sl2 = scale * 1.4426950408889634f;
     float sum = 0.f;
     for (int i = tid * 4; i < cols; i += 1024) {
-        if (i + 4 <= cols) { float4 v = *reinterpret_cast<const float4*>(row + i); sum += exp2f((v.x - mx) * sl2) + exp2f((v.y - mx) * sl2) + exp2f((v.z - mx) * sl2) + exp2f((v.w - mx) * sl2); }
-        else for (int j = i; j < cols; ++j) sum += exp2f((row[j] - mx) * sl2);
+        if (i + 4 <= cols) { float4 v = Vec4<T>::ld(row + i); sum += exp2f((v.x - mx) * sl2) + exp2f((v.y - mx) * sl2) + exp2f((v.z - mx) * sl2) + exp2f((v.w - mx) * sl2); }
+        else for (int j = i; j < cols; ++j) sum += exp2f((to_f(row[j]) - mx) * sl2);
     }
     sum = warp_sum(sum);
     __syncthreads();
@@ -138,42 +200,42 @@ __global__ void __launch_bounds__(256) k_softmax_rows(const float* __restrict__ 
     const float inv = bc;
     for (int i = tid * 4; i < cols; i += 1024) {
         if (i + 4 <= cols) {
-            float4 v = *reinterpret_cast<const float4*>(row + i);
+            float4 v = Vec4<T>::ld(row + i);
             __half2 a = __floats2half2_rn(exp2f((v.x - mx) * sl2) * inv, exp2f((v.y - mx) * sl2) * inv);
             __half2 b = __floats2half2_rn(exp2f((v.z - mx) * sl2) * inv, exp2f((v.w - mx) * sl2) * inv);
             uint2 u; u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
             *reinterpret_cast<uint2*>(orow + i) = u;
-        } else for (int j = i; j < cols; ++j) orow[j] = __float2half_rn(exp2f((row[j] - mx) * sl2) * inv);
+        } else for (int j = i; j < cols; ++j) orow[j] = __float2half_rn(exp2f((to_f(row[j]) - mx) * sl2) * inv);
     }
 }
 
-// z0 = (mean + exp(0.5*clamp(logvar,-30,20))*xi)*scaling ; x = sqrt_a*z0 + sqrt_1ma*noise   (fp16 rounding points as the reference)
+// z0 = (mean + exp(0.5*clamp(logvar,-30,20))*xi)*scaling ; x = sqrt_a*z0 + sqrt_1ma*noise.  The latent STATE is kept in fp32
+// across the scheduler steps (out32); out16 is the fp16 copy the UNet / ControlNet read.  (diffusers keeps the state in the model
+// dtype; the fp32 state removes one fp16 rounding of |x| <= 16, i.e. up to 4e-3, per step from the final latents.)
 __global__ void __launch_bounds__(256) k_vae_sample(const __half* __restrict__ mom, int ld_m, const __half* __restrict__ xi, const __half* __restrict__ noise,
-                                                    __half* __restrict__ out, long long npx, float scaling, float sa, float s1) {
+                                                    float* __restrict__ out32, __half* __restrict__ out16, long long npx, float scaling, float sa, float s1) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx * 4; i += (long long)gridDim.x * blockDim.x) {
         long long px = i >> 2; int c = (int)(i & 3);
-        float mean = __half2float(mom[px * ld_m + c]);
-        float logvar = fminf(fmaxf(__half2float(mom[px * ld_m + 4 + c]), -30.0f), 20.0f);
-        float stdv = __half2float(__float2half_rn(expf(0.5f * logvar)));
-        float z = __half2float(__float2half_rn(mean + __half2float(__float2half_rn(stdv * __half2float(xi[i])))));
-        z = __half2float(__float2half_rn(z * scaling));
-        float a = __half2float(__float2half_rn(sa * z)), b = __half2float(__float2half_rn(s1 * __half2float(noise[i])));
-        out[i] = __float2half_rn(a + b);
+        const float mean = __half2float(mom[px * ld_m + c]);
+        const float logvar = fminf(fmaxf(__half2float(mom[px * ld_m + 4 + c]), -30.0f), 20.0f);
+        const float z = (mean + expf(0.5f * logvar) * __half2float(xi[i])) * scaling;
+        const float r = sa * z + s1 * __half2float(noise[i]);
+        out32[i] = r; out16[i] = __float2half_rn(r);
     }
 }
 
-__global__ void __launch_bounds__(256) k_cfg_lcm(const __half* __restrict__ eu, const __half* __restrict__ ec, int ld_e, const __half* __restrict__ x,
-                                                 const __half* __restrict__ noise, __half* __restrict__ out, long long npx, float g, float sa, float s1,
-                                                 float c_skip, float c_out, float sap, float s1p, int last) {
+__global__ void __launch_bounds__(256) k_cfg_lcm(const __half* __restrict__ eu, const __half* __restrict__ ec, int ld_e, const float* __restrict__ x,
+                                                 const __half* __restrict__ noise, float* __restrict__ out32, __half* __restrict__ out16, long long npx, float g,
+                                                 float sa, float s1, float c_skip, float c_out, float sap, float s1p, int last) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npx * 4; i += (long long)gridDim.x * blockDim.x) {
         long long px = i >> 2; int c = (int)(i & 3);
         float u = __half2float(eu[px * ld_e + c]), cc = __half2float(ec[px * ld_e + c]);
         float eps = u + g * (cc - u);
-        float xv = __half2float(x[i]);
+        float xv = x[i];
         float x0 = (xv - s1 * eps) / sa;
         float den = c_out * x0 + c_skip * xv;
         float r = last ? den : sap * den + s1p * __half2float(noise[i]);
-        out[i] = __float2half_rn(r);
+        out32[i] = r; out16[i] = __float2half_rn(r);
     }
 }
 
@@ -222,22 +284,29 @@ extern "C" int fie_sincos_embedding(const float* host_vals, int count, int dim, 
 }
 extern "C" int fie_softmax_rows_f32_to_f16(const void* s, long long ld_in, void* p, long long ld_out, long long rows, int cols, float scale, void* stream) {
     FIE_REQUIRE(s && p && rows > 0 && rows < (1ll << 31) && cols > 0 && (ld_in % 4) == 0 && (ld_out % 4) == 0, "fie_softmax_rows: bad args");
-    k_softmax_rows<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const float*)s, ld_in, (__half*)p, ld_out, cols, scale);
+    if ((cols % 4) == 0 && cols <= 16384) k_softmax_rows_reg<float, 16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const float*)s, ld_in, (__half*)p, ld_out, cols, scale);
+    else k_softmax_rows<float><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const float*)s, ld_in, (__half*)p, ld_out, cols, scale);
     return check_launch("fie_softmax_rows_f32_to_f16");
 }
-extern "C" int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, void* x_out,
+extern "C" int fie_softmax_rows_f16(const void* s, long long ld_in, void* p, long long ld_out, long long rows, int cols, float scale, void* stream) {
+    FIE_REQUIRE(s && p && rows > 0 && rows < (1ll << 31) && cols > 0 && (ld_in % 4) == 0 && (ld_out % 4) == 0, "fie_softmax_rows_f16: bad args");
+    if ((cols % 4) == 0 && cols <= 16384) k_softmax_rows_reg<__half, 16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)s, ld_in, (__half*)p, ld_out, cols, scale);
+    else k_softmax_rows<__half><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)s, ld_in, (__half*)p, ld_out, cols, scale);
+    return check_launch("fie_softmax_rows_f16");
+}
+extern "C" int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, float* x_out_f32, void* x_out_f16,
                                         long long count_px, float scaling, float sqrt_a, float sqrt_1ma, void* stream) {
-    FIE_REQUIRE(moments && xi && noise && x_out && count_px > 0 && ld_m >= 8, "fie_vae_sample_add_noise: bad args");
+    FIE_REQUIRE(moments && xi && noise && x_out_f32 && x_out_f16 && count_px > 0 && ld_m >= 8, "fie_vae_sample_add_noise: bad args");
     k_vae_sample<<<grid_for(count_px * 4, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)moments, ld_m, (const __half*)xi, (const __half*)noise,
-                                                                                (__half*)x_out, count_px, scaling, sqrt_a, sqrt_1ma);
+                                                                                x_out_f32, (__half*)x_out_f16, count_px, scaling, sqrt_a, sqrt_1ma);
     return check_launch("fie_vae_sample_add_noise");
 }
-extern "C" int fie_cfg_lcm_step(const void* eps_u, const void* eps_c, int ld_e, const void* x, const void* noise, void* x_out,
+extern "C" int fie_cfg_lcm_step(const void* eps_u, const void* eps_c, int ld_e, const float* x_f32, const void* noise, float* x_out_f32, void* x_out_f16,
                                 long long count_px, float guidance, float sqrt_a, float sqrt_1ma, float c_skip, float c_out,
                                 float sqrt_a_prev, float sqrt_1ma_prev, int last, void* stream) {
-    FIE_REQUIRE(eps_u && eps_c && x && x_out && count_px > 0 && ld_e >= 4 && (last || noise), "fie_cfg_lcm_step: bad args");
-    k_cfg_lcm<<<grid_for(count_px * 4, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)eps_u, (const __half*)eps_c, ld_e, (const __half*)x,
-                                                                              (const __half*)noise, (__half*)x_out, count_px, guidance, sqrt_a, sqrt_1ma,
+    FIE_REQUIRE(eps_u && eps_c && x_f32 && x_out_f32 && x_out_f16 && count_px > 0 && ld_e >= 4 && (last || noise), "fie_cfg_lcm_step: bad args");
+    k_cfg_lcm<<<grid_for(count_px * 4, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)eps_u, (const __half*)eps_c, ld_e, x_f32,
+                                                                              (const __half*)noise, x_out_f32, (__half*)x_out_f16, count_px, guidance, sqrt_a, sqrt_1ma,
                                                                               c_skip, c_out, sqrt_a_prev, sqrt_1ma_prev, last);
     return check_launch("fie_cfg_lcm_step");
 }

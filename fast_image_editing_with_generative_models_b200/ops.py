@@ -159,11 +159,16 @@ def sincos_embedding(vals, dim: int, device) -> torch.Tensor:
 
 
 def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    _req(s, torch.float32, "softmax_rows")
+    """Row softmax of fp32 scores (scaled here) or fp16 scores (pre-scaled by the GEMM epilogue: pass scale = 1) -> fp16."""
+    if s.dtype not in (torch.float32, torch.float16):
+        raise _lib.FieError("softmax_rows: fp32 or fp16 scores expected")
+    _req(s, s.dtype, "softmax_rows")
     rows, cols = s.shape
     out = torch.empty((rows, cols), dtype=torch.float16, device=s.device) if out is None else out
-    with _prof("softmax_rows", 6.0 * rows * cols, "B"):
-        check(_lib.lib().fie_softmax_rows_f32_to_f16(_p(s), s.stride(0), _p(out), out.stride(0), rows, cols, float(scale), _stream()), "fie_softmax_rows")
+    f16 = s.dtype == torch.float16
+    with _prof("softmax_rows", (4.0 if f16 else 6.0) * rows * cols, "B"):
+        fn = _lib.lib().fie_softmax_rows_f16 if f16 else _lib.lib().fie_softmax_rows_f32_to_f16
+        check(fn(_p(s), s.stride(0), _p(out), out.stride(0), rows, cols, float(scale), _stream()), "fie_softmax_rows")
     _count()
     return out
 
@@ -354,23 +359,27 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, hea
     return out
 
 
-def vae_sample_add_noise(moments: torch.Tensor, xi: torch.Tensor, noise: torch.Tensor, scaling: float, sqrt_a: float, sqrt_1ma: float) -> torch.Tensor:
-    """moments [N,H,W,>=8] fp16, xi/noise [N,H,W,4] fp16 -> noisy latents [N,H,W,4] fp16."""
+def vae_sample_add_noise(moments: torch.Tensor, xi: torch.Tensor, noise: torch.Tensor, scaling: float, sqrt_a: float, sqrt_1ma: float):
+    """moments [N,H,W,>=8] fp16, xi/noise [N,H,W,4] fp16 -> noisy latents [N,H,W,4] as (fp32 state, fp16 copy for the UNet)."""
     _req(moments, torch.float16, "vae_sample_add_noise")
-    out = torch.empty_like(xi)
+    out32 = torch.empty(xi.shape, dtype=torch.float32, device=xi.device)
+    out16 = torch.empty_like(xi)
     npx = xi.numel() // 4
-    check(_lib.lib().fie_vae_sample_add_noise(_p(moments), moments.shape[-1], _p(xi), _p(noise), _p(out), npx, float(scaling), float(sqrt_a), float(sqrt_1ma),
-                                               _stream()), "fie_vae_sample_add_noise")
+    check(_lib.lib().fie_vae_sample_add_noise(_p(moments), moments.shape[-1], _p(xi), _p(noise), _p(out32), _p(out16), npx, float(scaling), float(sqrt_a),
+                                               float(sqrt_1ma), _stream()), "fie_vae_sample_add_noise")
     _count()
-    return out
+    return out32, out16
 
 
-def cfg_lcm_step(eps_u: torch.Tensor, eps_c: torch.Tensor, x: torch.Tensor, noise: Optional[torch.Tensor], guidance: float, c: dict) -> torch.Tensor:
-    """eps_u/eps_c: [N,H,W,ld] views (first 4 channels used); x [N,H,W,4]; c = LCM step coefficients."""
-    out = torch.empty_like(x)
-    npx = x.numel() // 4
-    check(_lib.lib().fie_cfg_lcm_step(_p(eps_u), _p(eps_c), eps_u.stride(-2), _p(x), _p(noise), _p(out), npx, float(guidance), float(c["sqrt_a"]),
+def cfg_lcm_step(eps_u: torch.Tensor, eps_c: torch.Tensor, x32: torch.Tensor, noise: Optional[torch.Tensor], guidance: float, c: dict):
+    """eps_u/eps_c: [N,H,W,ld] fp16 views (first 4 channels used); x32 [N,H,W,4] fp32 latent state; c = LCM step coefficients
+    -> (fp32 state, fp16 copy)."""
+    _req(x32, torch.float32, "cfg_lcm_step")
+    out32 = torch.empty_like(x32)
+    out16 = torch.empty(x32.shape, dtype=torch.float16, device=x32.device)
+    npx = x32.numel() // 4
+    check(_lib.lib().fie_cfg_lcm_step(_p(eps_u), _p(eps_c), eps_u.stride(-2), _p(x32), _p(noise), _p(out32), _p(out16), npx, float(guidance), float(c["sqrt_a"]),
                                        float(c["sqrt_1ma"]), float(c["c_skip"]), float(c["c_out"]), float(c["sqrt_a_prev"]), float(c["sqrt_1ma_prev"]),
                                        int(bool(c["last"])), _stream()), "fie_cfg_lcm_step")
     _count()
-    return out
+    return out32, out16

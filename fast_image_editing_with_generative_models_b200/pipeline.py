@@ -19,7 +19,7 @@ Tensor = torch.Tensor
 class EditOutput:
     images: Tensor                      # uint8 [B,H,W,3] on the device
     edges: Tensor                       # uint8 [B,H,W,3] Canny control image
-    latents: Optional[Tensor] = None    # fp16 [B,h,w,4] final latents (before decode)
+    latents: Optional[Tensor] = None    # fp32 [B,h,w,4] final latents (the scheduler state; the VAE decodes its fp16 copy)
     extras: Optional[Dict] = None
 
 
@@ -108,7 +108,7 @@ class EditEngine:
         # ---- VAE encode -> posterior sample -> scale -> add_noise ----
         moments = self.vae.encode_moments(ops.preprocess_pad8(images_u8, normalize=True))
         sa, s1 = sched.add_noise_coeffs(timesteps[0]) if timesteps else (1.0, 0.0)
-        x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)
+        x32, x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)    # fp32 state, fp16 copy
         # ---- prompt conditioning (step-invariant): rows [neg]*B + [pos]*B as diffusers ----
         if pe.dim() == 3:
             pe, pl = pe[None].expand(B, -1, -1, -1), pl[None].expand(B, -1, -1)
@@ -134,9 +134,9 @@ class EditEngine:
             eu, ec = (eps[:B], eps[B:]) if do_cfg else (eps, eps)
             if return_extras:
                 eps_list.append(eps)
-            x = ops.cfg_lcm_step(eu, ec, x, z, guidance_scale if do_cfg else 1.0, c)
+            x32, x = ops.cfg_lcm_step(eu, ec, x32, z, guidance_scale if do_cfg else 1.0, c)
         # ---- VAE decode (latents / scaling folded into post_quant_conv) + postprocess ----
         decoded = self.vae.decode(x)
         images = ops.postprocess(decoded)
         extras = dict(moments=moments, eps=eps_list, decoded=decoded) if return_extras else None
-        return EditOutput(images=images, edges=edges3, latents=x if (return_latents or return_extras) else None, extras=extras)
+        return EditOutput(images=images, edges=edges3, latents=x32 if (return_latents or return_extras) else None, extras=extras)

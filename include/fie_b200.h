@@ -63,6 +63,9 @@ int fie_sincos_embedding(const float* host_vals, int count, int dim, void* out_f
 /* softmax over rows: fp32 [rows, cols] (ld_in) * scale -> fp16 [rows, cols] (ld_out) */
 int fie_softmax_rows_f32_to_f16(const void* s_f32, long long ld_in, void* p_f16, long long ld_out,
                                 long long rows, int cols, float scale, void* stream);
+/* the same with fp16 scores (already scaled by the producing GEMM's epilogue when scale = 1); may run in place (p = s) */
+int fie_softmax_rows_f16(const void* s_f16, long long ld_in, void* p_f16, long long ld_out,
+                         long long rows, int cols, float scale, void* stream);
 
 /* ---- GroupNorm(+SiLU), NHWC fp16: replaces F.group_norm (+F.silu) in ResnetBlock2D / Transformer2DModel ----
  * x0: [n, hw, c0]; optional x1: [n, hw, c1] is the channel-concatenated second source (torch.cat of the skip
@@ -157,13 +160,14 @@ int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long
 
 /* ---- Scheduler / latent math: replaces DiagonalGaussianDistribution.sample, LCMScheduler.add_noise,
  *      the CFG combine and LCMScheduler.step inside the diffusers call ---- */
-/* moments fp16 [n,hw,ld_m] (mean = ch 0..3, logvar = ch 4..7), xi/noise fp16 [n,hw,4]:
- * z0 = (mean + exp(0.5*clamp(logvar,-30,20))*xi)*scaling; x = sqrt_a*z0 + sqrt_1ma*noise. Writes x (fp16 [n,hw,4]) */
-int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, void* x_out,
+/* The latent state is carried in fp32 between the scheduler steps; each call also writes the fp16 copy the UNet / ControlNet read.
+ * moments fp16 [n,hw,ld_m] (mean = ch 0..3, logvar = ch 4..7), xi/noise fp16 [n,hw,4]:
+ * z0 = (mean + exp(0.5*clamp(logvar,-30,20))*xi)*scaling; x = sqrt_a*z0 + sqrt_1ma*noise. Writes x as fp32 and fp16 [n,hw,4] */
+int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, float* x_out_f32, void* x_out_f16,
                              long long count_px, float scaling, float sqrt_a, float sqrt_1ma, void* stream);
-/* eps_u/eps_c fp16 [count_px, ld_e] (first 4 ch), x fp16 [count_px,4], noise or NULL:
- * eps = eps_u + g*(eps_c-eps_u); x0 = (x - s1*eps)/sa; den = c_out*x0 + c_skip*x; x' = sap*den + s1p*noise */
-int fie_cfg_lcm_step(const void* eps_u, const void* eps_c, int ld_e, const void* x, const void* noise, void* x_out,
+/* eps_u/eps_c fp16 [count_px, ld_e] (first 4 ch), x fp32 [count_px,4], noise fp16 or NULL:
+ * eps = eps_u + g*(eps_c-eps_u); x0 = (x - s1*eps)/sa; den = c_out*x0 + c_skip*x; x' = sap*den + s1p*noise (fp32 and fp16 out) */
+int fie_cfg_lcm_step(const void* eps_u, const void* eps_c, int ld_e, const float* x_f32, const void* noise, float* x_out_f32, void* x_out_f16,
                      long long count_px, float guidance, float sqrt_a, float sqrt_1ma, float c_skip, float c_out,
                      float sqrt_a_prev, float sqrt_1ma_prev, int last, void* stream);
 

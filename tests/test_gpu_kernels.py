@@ -83,12 +83,18 @@ def test_layernorm(cuda_dev, rows, c):
     assert float((out.float() - ref).abs().max()) < 6e-3
 
 
-def test_softmax_rows(cuda_dev):
+@pytest.mark.parametrize("rows,cols", [(100, 1000), (64, 16384), (7, 20000), (33, 1020)])
+def test_softmax_rows(cuda_dev, rows, cols):
     ops = _ops()
-    s = _rand((100, 1000), cuda_dev, 11) * 5
+    s = _rand((rows, cols), cuda_dev, 11) * 5
     out = ops.softmax_rows(s, 0.3)
     ref = torch.softmax(s * 0.3, dim=-1)
-    assert float((out.float() - ref).abs().max()) < 1e-3
+    assert float((out.float() - ref).abs().max()) < 1e-3 and float((out.float().sum(-1) - 1).abs().max()) < 2e-2
+    # fp16 scores (pre-scaled by the producing GEMM), softmax in place
+    h = (s * 0.3).half()
+    ref16 = torch.softmax(h.float(), dim=-1)
+    out16 = ops.softmax_rows(h, 1.0, out=h)
+    assert out16.data_ptr() == h.data_ptr() and float((out16.float() - ref16).abs().max()) < 1e-3
 
 
 def test_scheduler_kernels(cuda_dev):
@@ -100,18 +106,19 @@ def test_scheduler_kernels(cuda_dev):
     xi = _rand((2, 16, 16, 4), cuda_dev, 13).half()
     nz = _rand((2, 16, 16, 4), cuda_dev, 14).half()
     sa, s1 = sched.add_noise_coeffs(ts[0])
-    out = ops.vae_sample_add_noise(mom, xi, nz, 0.13025, sa, s1)
+    out, out16 = ops.vae_sample_add_noise(mom, xi, nz, 0.13025, sa, s1)
+    assert out.dtype == torch.float32 and torch.equal(out16, out.half())
     z0 = vae_sample(mom.permute(0, 3, 1, 2).float(), xi.permute(0, 3, 1, 2).float(), 0.13025)
     ref = (sa * z0 + s1 * nz.permute(0, 3, 1, 2).float()).permute(0, 2, 3, 1)
-    assert float((out.float() - ref).abs().max()) < 3e-3
+    assert float((out.float() - ref).abs().max()) < 1e-5
     eps = _rand((4, 16, 16, 32), cuda_dev, 15).half()
-    x = _rand((2, 16, 16, 4), cuda_dev, 16).half()
+    x = _rand((2, 16, 16, 4), cuda_dev, 16)
     for k in (0, 1):
         c = sched.step_coeffs(begin + k)
-        got = ops.cfg_lcm_step(eps[:2], eps[2:], x, None if c["last"] else nz, 1.5, c)
+        got, got16 = ops.cfg_lcm_step(eps[:2], eps[2:], x, None if c["last"] else nz, 1.5, c)
         e = eps[:2, ..., :4].float() + 1.5 * (eps[2:, ..., :4].float() - eps[:2, ..., :4].float())
-        ref = sched.step(e, begin + k, x.float(), nz.float())
-        assert float((got.float() - ref).abs().max()) < 6e-3
+        ref = sched.step(e, begin + k, x, nz.float())
+        assert float((got - ref).abs().max()) < 2e-5 and torch.equal(got16, got.half())
 
 
 # ------------------------------------------------------------------ tensor-core GEMM / conv
