@@ -16,7 +16,22 @@
 #include "tc_common.cuh"
 #include <type_traits>
 
+#ifndef FIE_ATT_EMU
+#define FIE_ATT_EMU 2          // exponentials per 8 evaluated without MUFU in the self-attention softmax
+#endif
+
 namespace fie {
+
+// 2^x for x <= 127 without the MUFU unit: x = n + f (add with round-down against 1.5 * 2^23 leaves n in the low mantissa bits),
+// 2^f by a cubic on [0, 1) (relative error ~1e-4), exponent patched in with an integer add.  Inputs below -126 give ~1e-38.
+__device__ __forceinline__ float ex2_emulated(float x) {
+    x = fmaxf(x, -126.0f);
+    float t;
+    asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(t) : "f"(x), "f"(12582912.0f));
+    const float f = x - (t - 12582912.0f);
+    const float p = fmaf(fmaf(fmaf(0.0771190897f, f, 0.2275643945f), f, 0.6951461434f), f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64, ATT_QT = 2, ATT_KV_STAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                                   // 16 KiB (Q, K or V tile)
@@ -151,8 +166,11 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = u * 8 + 2 * i;
-                    float p0 = ex2_approx(fmaf(__uint_as_float(r[c]), sl2, mneg));
-                    float p1 = ex2_approx(fmaf(__uint_as_float(r[c + 1]), sl2, mneg));
+                    // The MUFU unit (16 ex2 / clk / SM) is this kernel's limit: FIE_ATT_EMU of every 8 exponentials run on the
+                    // FMA / ALU pipes instead (Cody-Waite split + cubic, ~1e-4 relative: below the fp16 rounding of P).
+                    const float x0 = fmaf(__uint_as_float(r[c]), sl2, mneg), x1 = fmaf(__uint_as_float(r[c + 1]), sl2, mneg);
+                    float p0 = (2 * i >= 8 - FIE_ATT_EMU) ? ex2_emulated(x0) : ex2_approx(x0);
+                    float p1 = (2 * i + 1 >= 8 - FIE_ATT_EMU) ? ex2_emulated(x1) : ex2_approx(x1);
                     if (!FULL) { if (hf * 64 + c >= kv_left) p0 = 0.f; if (hf * 64 + c + 1 >= kv_left) p1 = 0.f; }
                     if (i & 1) { ps2 += p0; ps3 += p1; } else { ps0 += p0; ps1 += p1; }
                     __half2 h = __floats2half2_rn(p0, p1);
