@@ -222,8 +222,10 @@ def main():
 
     # ---- per-kernel-family attribution (one instrumented step, after the timed regions) ----
     ops.PROFILE = []
+    ops.STAGES.clear()
     eng.edit_batch(imgs, pe_d, pl_d, nz_d, strength=0.5)
     fam = ops.profile_summary()
+    stages = ops.stage_summary()
     ops.PROFILE = None
     peaks = {}
     try:
@@ -238,10 +240,11 @@ def main():
     tc_calls = sum(fam[k]["calls"] * (4 if k == "conv_up2x" else 1) for k in TC if k in fam)
     total_ms = sum(d["ms"] for d in fam.values())
     achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    traffic, traffic_src = None, None
+    traffic, traffic_src, tensor_pct = None, None, None
     try:            # DRAM bytes per launch from the committed ncu --set full capture (profiles/); None if absent
         tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")))
         traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
+        tensor_pct = tj.get("tensor_pipe_active_pct_time_weighted")
     except Exception:
         pass
     roofline = {"kernel": "k_gemm_conv (tcgen05 GEMM / implicit-GEMM conv3x3)", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
@@ -272,6 +275,11 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "image_roofline": {"tflop_per_image": TFLOP_PER_IMAGE[a.model], "achieved_tflops_per_gpu": value / world * TFLOP_PER_IMAGE[a.model],
                                    "frac_of_peak": value / world * TFLOP_PER_IMAGE[a.model] / peak_tf},
+                # the other two quantities BASELINE.json's metric names: UNet step time and tensor-pipe utilisation
+                "unet_step_ms": (stages.get("unet_step", 0.0) / 2.0) if stages else None,          # per executed step, CFG batch of 2 x images_per_gpu rows
+                "stages_ms": {k: round(v, 3) for k, v in stages.items()},
+                "tensor_pipe": {"achieved_over_measured_peak": achieved / peak_tf, "ncu_sm__pipe_tensor_cycles_active_pct": tensor_pct,
+                                "ncu_source": traffic_src},
                 "breakdown": breakdown}
         print(json.dumps(line), flush=True)
     if world > 1:

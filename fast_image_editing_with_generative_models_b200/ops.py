@@ -47,6 +47,26 @@ class _prof:
         return False
 
 
+STAGES = []   # (name, event) marks recorded by stage() while PROFILE is a list
+
+
+def stage(name: str):
+    """Mark the start of a pipeline stage (Canny, VAE encode, denoising step k, VAE decode) on the launch stream; only when profiling."""
+    if PROFILE is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        STAGES.append((name, e))
+
+
+def stage_summary():
+    """-> {stage: ms} between consecutive marks (the last mark must be 'end')."""
+    torch.cuda.synchronize()
+    out = {}
+    for (n0, e0), (_, e1) in zip(STAGES[:-1], STAGES[1:]):
+        out[n0] = out.get(n0, 0.0) + e0.elapsed_time(e1)
+    return out
+
+
 def profile_summary(by_tag: bool = False):
     """-> {family: dict(calls, ms, work, unit)} from the recorded events (synchronises)."""
     torch.cuda.synchronize()

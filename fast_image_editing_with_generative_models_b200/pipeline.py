@@ -101,15 +101,18 @@ class EditEngine:
         do_cfg = guidance_scale > 1
         nrow = 2 if do_cfg else 1
         # ---- Canny control image + conditioning embedding (step-invariant) ----
+        ops.stage("canny+cond_embedding")
         edges3 = ops.canny(images_u8, canny_low, canny_high, out_channels=3)
         cond_emb = self.cn.cond_embedding(ops.preprocess_pad8(edges3, normalize=False))
         if do_cfg:
             cond_emb = torch.cat([cond_emb, cond_emb], 0)
         # ---- VAE encode -> posterior sample -> scale -> add_noise ----
+        ops.stage("vae_encode")
         moments = self.vae.encode_moments(ops.preprocess_pad8(images_u8, normalize=True))
         sa, s1 = sched.add_noise_coeffs(timesteps[0]) if timesteps else (1.0, 0.0)
         x32, x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)    # fp32 state, fp16 copy
         # ---- prompt conditioning (step-invariant): rows [neg]*B + [pos]*B as diffusers ----
+        ops.stage("prompt_kv")
         if pe.dim() == 3:
             pe, pl = pe[None].expand(B, -1, -1, -1), pl[None].expand(B, -1, -1)
         rows = [0, 1] if do_cfg else [1]
@@ -123,8 +126,10 @@ class EditEngine:
         zi = 2
         eps_list = []
         for k, t in enumerate(timesteps):
+            ops.stage("controlnet_step")
             x2 = torch.cat([x] * nrow, 0) if do_cfg else x
             down, mid = self.cn.forward(x2, float(t), ps_cn, cond_emb, controlnet_conditioning_scale, nctx)
+            ops.stage("unet_step")
             eps = self.unet.forward(x2, float(t), ps_un, down, mid, nctx)
             c = sched.step_coeffs(begin + k)
             z = None
@@ -136,7 +141,9 @@ class EditEngine:
                 eps_list.append(eps)
             x32, x = ops.cfg_lcm_step(eu, ec, x32, z, guidance_scale if do_cfg else 1.0, c)
         # ---- VAE decode (latents / scaling folded into post_quant_conv) + postprocess ----
+        ops.stage("vae_decode")
         decoded = self.vae.decode(x)
         images = ops.postprocess(decoded)
+        ops.stage("end")
         extras = dict(moments=moments, eps=eps_list, decoded=decoded) if return_extras else None
         return EditOutput(images=images, edges=edges3, latents=x32 if (return_latents or return_extras) else None, extras=extras)
