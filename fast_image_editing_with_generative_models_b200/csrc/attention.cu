@@ -46,6 +46,7 @@ struct AttnParams {
     long long ldo;
     int nq, nkv;
     float scale_log2;
+    int causal;       // (kv1 kernel only) key j is visible to query row i iff j <= i
 };
 
 __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant__ AttnParams p) {
@@ -391,9 +392,10 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
             tmem_ld_32x64(tS, ra);
             tmem_ld_32x64(tS + 64, rb);
             tmem_ld_wait();
+            const int kvr = p.causal ? min(kv, (qp * ATT_QT + q) * ATT_BM + row + 1) : kv;       // columns visible to this row
             float mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) { if (i < kv) mx = fmaxf(mx, __uint_as_float(ra[i])); if (64 + i < kv) mx = fmaxf(mx, __uint_as_float(rb[i])); }
+            for (int i = 0; i < 64; ++i) { if (i < kvr) mx = fmaxf(mx, __uint_as_float(ra[i])); if (64 + i < kvr) mx = fmaxf(mx, __uint_as_float(rb[i])); }
             const float mneg = -mx * sl2;
             float l = 0.f;
 #pragma unroll
@@ -407,8 +409,8 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
                     for (int i = 0; i < 4; ++i) {
                         const int c = uu * 8 + 2 * i;
                         const float s0 = __uint_as_float(hf ? rb[c] : ra[c]), s1 = __uint_as_float(hf ? rb[c + 1] : ra[c + 1]);
-                        float p0 = (hf * 64 + c < kv) ? ex2_approx(fmaf(s0, sl2, mneg)) : 0.f;
-                        float p1 = (hf * 64 + c + 1 < kv) ? ex2_approx(fmaf(s1, sl2, mneg)) : 0.f;
+                        float p0 = (hf * 64 + c < kvr) ? ex2_approx(fmaf(s0, sl2, mneg)) : 0.f;
+                        float p1 = (hf * 64 + c + 1 < kvr) ? ex2_approx(fmaf(s1, sl2, mneg)) : 0.f;
                         l += p0 + p1;
                         __half2 h = __floats2half2_rn(p0, p1);
                         pk[i] = *reinterpret_cast<uint32_t*>(&h);
@@ -451,8 +453,8 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
 }  // namespace fie
 using namespace fie;
 
-extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                                     void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, void* stream) {
+static int attention_d64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                         void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, int causal, void* stream) {
     FIE_REQUIRE(q && k && v && out, "fie_attention_d64_f16: null pointer");
     FIE_REQUIRE(b > 0 && heads > 0 && nq > 0 && nkv > 0 && b <= 65535 && heads <= 65535, "fie_attention_d64_f16: bad shape");
     FIE_REQUIRE((ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0, "fie_attention_d64_f16: leading dims must be multiples of 8");
@@ -475,6 +477,8 @@ extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k
     }
     p.out = (__half*)out; p.ldo = ldo; p.nq = nq; p.nkv = nkv;
     p.scale_log2 = scale * 1.4426950408889634f;
+    p.causal = causal;
+    FIE_REQUIRE(!causal || nkv <= ATT_BN, "fie_attention_d64_causal_f16: nkv must be <= 128");
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_attention_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
@@ -483,7 +487,7 @@ extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k
     }
     static int kv1 = -1;
     if (kv1 < 0) { const char* e = getenv("FIE_ATT_KV1"); kv1 = e ? atoi(e) : 1; }
-    if (kv1 && nkv <= ATT_BN) {
+    if ((kv1 || causal) && nkv <= ATT_BN) {
         // cross-attention: persistent CTAs over (batch, head, 256-row query block) items
         static bool attr1 = false;
         if (!attr1) {
@@ -500,4 +504,13 @@ extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k
     dim3 grid((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM), heads, b);
     k_attention_d64<<<grid, 384, ATT_SMEM, (cudaStream_t)stream>>>(p);
     return check_launch("fie_attention_d64_f16");
+}
+
+extern "C" int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                     void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, void* stream) {
+    return attention_d64(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, nq, nkv, scale, 0, stream);
+}
+extern "C" int fie_attention_d64_causal_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                            void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, void* stream) {
+    return attention_d64(q, ldq, k, ldk, v, ldv, out, ldo, b, heads, nq, nkv, scale, 1, stream);
 }

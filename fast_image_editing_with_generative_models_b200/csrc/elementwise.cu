@@ -239,8 +239,29 @@ __global__ void __launch_bounds__(256) k_cfg_lcm(const __half* __restrict__ eu, 
     }
 }
 
+// token + position embedding: one 16-byte vector per thread
+__global__ void __launch_bounds__(256) k_embed_tokens(const int* __restrict__ ids, const uint4* __restrict__ tok, const uint4* __restrict__ pos, uint4* __restrict__ out,
+                                                      long long rows, int seq_len, int cv, int vocab) {
+    const long long total = rows * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cv; const int v = (int)(i - r * cv);
+        int id = ids[r]; id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        const uint4 a = __ldg(tok + (long long)id * cv + v), b = __ldg(pos + (long long)(r % seq_len) * cv + v);
+        uint4 o; const __half2* ah = reinterpret_cast<const __half2*>(&a); const __half2* bh = reinterpret_cast<const __half2*>(&b); __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 fa = __half22float2(ah[j]), fb = __half22float2(bh[j]); oh[j] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y); }
+        out[i] = o;
+    }
+}
+
 }  // namespace fie
 using namespace fie;
+
+extern "C" int fie_embed_tokens_f16(const int* ids, const void* tok, const void* pos, void* out, long long rows, int seq_len, int c, int vocab, void* stream) {
+    FIE_REQUIRE(ids && tok && pos && out && rows > 0 && seq_len > 0 && c > 0 && (c % 8) == 0 && vocab > 0, "fie_embed_tokens_f16: bad args");
+    k_embed_tokens<<<grid_for(rows * (c / 8), 256), 256, 0, (cudaStream_t)stream>>>(ids, (const uint4*)tok, (const uint4*)pos, (uint4*)out, rows, seq_len, c / 8, vocab);
+    return check_launch("fie_embed_tokens_f16");
+}
 
 extern "C" int fie_preprocess_u8_to_f16(const void* img, void* out, int n, int h, int w, int c_out, int normalize, void* stream) {
     FIE_REQUIRE(img && out && n > 0 && h > 0 && w > 0 && c_out >= 3, "fie_preprocess_u8_to_f16: bad args");

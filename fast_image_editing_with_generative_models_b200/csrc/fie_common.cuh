@@ -38,6 +38,8 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
     return 0.5f * x * (x < 0.0f ? q : 2.0f - q);
 }
 
+__device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -57,7 +57,7 @@ class FastEditor:
 
     def __init__(self, model_name="sdxl", device="cuda", dtype=torch.float16, enable_cpu_offload=True, use_full_precision=False,
                  use_full_controlnet=False, *, state: Optional[Dict] = None, prompt_encoder: Optional[Callable] = None, tiny: bool = False,
-                 verbose: bool = True):
+                 text_encoders: bool = False, verbose: bool = True):
         if model_name not in self.MODEL_CONFIGS:
             raise ValueError(f"Unknown model: {model_name}. Choose from {list(self.MODEL_CONFIGS.keys())}")
         self.model_name = model_name
@@ -83,6 +83,19 @@ class FastEditor:
         self.controlnet = self._engine.cn
         self.pipe = _PipeShim(self._engine)
         self._prompt_encoder = prompt_encoder
+        self._text = None
+        if text_encoders and prompt_encoder is None:
+            # the two CLIP text towers of encode_prompt on the same kernels (seeded random-init weights; the BPE
+            # tokenizer's vocabulary is not available offline, so prompts go through text_encoder.pseudo_token_ids)
+            from . import text_encoder as T
+            ucfg = self._engine.unet.cfg
+            c1, c2 = (T.tiny_clip_config(False, "quick_gelu"), T.tiny_clip_config(True, "gelu")) if tiny else (T.clip_l_config(), T.openclip_bigg_config())
+            pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+            if c1.hidden_size + c2.hidden_size != ucfg.cross_attention_dim or c2.projection_dim != pooled_dim:
+                raise ValueError("text encoder widths do not match the UNet's cross_attention_dim / pooled embedding size")
+            self._say("[FastEditor] Building the CLIP text encoders (synthetic weights)...")
+            self._text = T.SDXLTextEncoders(T.make_clip_params(c1), c1, T.make_clip_params(c2), c2, device)
+            self._text_vocab = c1.vocab_size
         self._say("[FastEditor] Initialization complete!")
 
     # ---- prompt -> embeddings (text encoders are not on the accelerated path) ----
@@ -90,6 +103,10 @@ class FastEditor:
         ucfg = self._engine.unet.cfg
         if self._prompt_encoder is not None:
             return self._prompt_encoder(prompt, negative_prompt)
+        if self._text is not None:
+            from .text_encoder import pseudo_token_ids
+            ids = torch.stack([pseudo_token_ids(negative_prompt, self._text_vocab), pseudo_token_ids(prompt, self._text_vocab)])   # the empty negative prompt is ENCODED, as in the reference
+            return self._text.encode(ids, ids)          # ([neg, pos] x 77 x 2048, [neg, pos] x 1280)
         pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
         pos = S.synthetic_prompt(zlib.crc32(prompt.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)
         neg = S.synthetic_prompt(zlib.crc32(negative_prompt.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import Epilogue, check
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_QUICKGELU = 0, 1, 2, 3, 4
 LAUNCHES = 0  # number of our kernels launched through this module (bench reports it)
 _KERNELS_PER_CALL = {"canny3": 4, "canny1": 3, "groupnorm": 2}
 
@@ -165,6 +165,17 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
     with _prof("upsample2x", 2.0 * out.numel() + 2.0 * x.numel(), "B"):
         check(_lib.lib().fie_upsample2x_f16(_p(x), _p(out), n, h, w, c, _stream()), "fie_upsample2x_f16")
+    _count()
+    return out
+
+
+def embed_tokens(ids: torch.Tensor, tok: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """ids int32 [B, T] -> fp16 [B*T, C] = tok[ids] + pos[t]  (CLIPTextEmbeddings)."""
+    _req(ids, torch.int32, "embed_tokens"); _req(tok, torch.float16, "embed_tokens"); _req(pos, torch.float16, "embed_tokens")
+    b, t = ids.shape
+    c = tok.shape[1]
+    out = torch.empty((b * t, c), dtype=torch.float16, device=ids.device)
+    check(_lib.lib().fie_embed_tokens_f16(_p(ids), _p(tok), _p(pos), _p(out), b * t, t, c, tok.shape[0], _stream()), "fie_embed_tokens_f16")
     _count()
     return out
 
@@ -365,7 +376,7 @@ def conv3x3_cin4(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor],
 
 
 def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, heads: int, nq: int, nkv: int, out: Optional[torch.Tensor] = None,
-                  scale: float = 0.125) -> torch.Tensor:
+                  scale: float = 0.125, causal: bool = False) -> torch.Tensor:
     """q [b*nq, >=heads*64] (row-strided views allowed), k/v [b*nkv, ...] -> [b*nq, heads*64]."""
     for t in (q, k, v):
         if t.dtype != torch.float16 or not t.is_cuda or t.stride(-1) != 1:
@@ -373,7 +384,8 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, hea
     if out is None:
         out = torch.empty((b * nq, heads * 64), dtype=torch.float16, device=q.device)
     with _prof("attention", 4.0 * b * heads * nq * nkv * 64, "FLOP", f"b{b} h{heads} nq{nq} nkv{nkv}"):
-        check(_lib.lib().fie_attention_d64_f16(_p(q), q.stride(-2), _p(k), k.stride(-2), _p(v), v.stride(-2), _p(out), out.stride(-2),
+        fn = _lib.lib().fie_attention_d64_causal_f16 if causal else _lib.lib().fie_attention_d64_f16
+        check(fn(_p(q), q.stride(-2), _p(k), k.stride(-2), _p(v), v.stride(-2), _p(out), out.stride(-2),
                                                 b, heads, nq, nkv, float(scale), _stream()), "fie_attention_d64_f16")
     _count()
     return out

@@ -82,7 +82,7 @@ int fie_layernorm_f16(const void* x, void* out, long long rows, int c, const flo
 /* ---- Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA) ----
  * D[M, N] = epilogue( A[M, K] * B[N, K]^T ), fp16 operands, fp32 accumulation in TMEM.
  * Replaces F.linear (cuBLASLt) and F.conv2d (cuDNN) in every diffusers module on the path. */
-enum { FIE_ACT_NONE = 0, FIE_ACT_SILU = 1, FIE_ACT_GEGLU = 2 };
+enum { FIE_ACT_NONE = 0, FIE_ACT_SILU = 1, FIE_ACT_GEGLU = 2, FIE_ACT_GELU = 3 /* exact erf GELU */, FIE_ACT_QUICKGELU = 4 /* x*sigmoid(1.702x), CLIP-L */ };
 
 typedef struct {
     /* epilogue: v = acc + col_bias[n] + row_bias[m / rows_per_group][n]  (+ chan_bias[m] if per-row bias)
@@ -157,6 +157,13 @@ int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, long long ldd
  * q: fp16 rows [b*nq, ldq] (head h at columns h*64..), k/v: [b*nkv, ldk/ldv], out: [b*nq, ldo]. No mask. */
 int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                           void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, void* stream);
+/* the same with a causal mask (key j visible to query i iff j <= i): the CLIP text encoders of the prompt-encoding stage that
+ * precedes the path (transformers CLIPTextModel inside the diffusers call).  nkv <= 128. */
+int fie_attention_d64_causal_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                 void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, void* stream);
+/* token + position embedding lookup (CLIPTextEmbeddings): ids int32 [rows] (row r is position r % seq_len),
+ * tok fp16 [vocab, c], pos fp16 [seq_len, c] -> out fp16 [rows, c]; c multiple of 8 */
+int fie_embed_tokens_f16(const int* ids, const void* tok, const void* pos, void* out, long long rows, int seq_len, int c, int vocab, void* stream);
 
 /* ---- Scheduler / latent math: replaces DiagonalGaussianDistribution.sample, LCMScheduler.add_noise,
  *      the CFG combine and LCMScheduler.step inside the diffusers call ---- */

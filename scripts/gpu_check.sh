@@ -22,5 +22,6 @@ run attention tests/test_gpu_kernels.py -k "attention"
 run engine tests/test_gpu_engine.py -s
 run fullsize tests/test_gpu_fullsize.py -s
 run dropin tests/test_gpu_dropin.py
+run text_encoder tests/test_gpu_text_encoder.py -s
 for extra in "$@"; do run extra tests -k "$extra"; done
 grep -E "^=== .* rc=" gpurun_out/gpu_check.log

@@ -7,6 +7,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 from PIL import Image
 
 pytestmark = pytest.mark.gpu
@@ -81,3 +82,23 @@ def test_clis_run_unmodified(cuda_dev, tmp_path, monkeypatch):
     run_batch.main(["--mapping_file", str(mf), "--source_dir", str(src), "--output_dir", str(out), "--model", "ssd-1b", "--seed", "7", "--no_cpu_offload"])
     edited = sorted(p.name for p in out.rglob("0_random/*.jpg") if "single" not in str(p))
     assert edited == [f"{i:012d}.jpg" for i in range(3)]                        # the missing source is counted as failed, not fatal
+
+
+def test_editor_with_text_encoders(cuda_dev):
+    """prompt -> (pseudo) token ids -> the two CLIP towers on the GPU -> embeddings -> edit: the whole GPU side of pipe(...)."""
+    from src.pipeline import FastEditor
+    # the tiny UNet's cross-attention width is 128, the tiny towers give 256: use matching encoders through the hook instead
+    from fast_image_editing_with_generative_models_b200 import text_encoder as T
+    c1 = T.CLIPTextConfig(name="t1", vocab_size=1000, hidden_size=64, num_layers=2, num_heads=1, intermediate_size=128, seed=41)
+    c2 = T.CLIPTextConfig(name="t2", vocab_size=1000, hidden_size=64, num_layers=2, num_heads=1, intermediate_size=128, hidden_act="gelu", projection_dim=64, seed=42)
+    te = T.SDXLTextEncoders(T.make_clip_params(c1), c1, T.make_clip_params(c2), c2, cuda_dev)
+
+    def encode(prompt, negative_prompt):
+        ids = torch.stack([T.pseudo_token_ids(negative_prompt, 1000), T.pseudo_token_ids(prompt, 1000)])
+        return te.encode(ids, ids)
+
+    import torch
+    ed = FastEditor(model_name="sdxl", device="cuda", tiny=True, verbose=False, prompt_encoder=encode)
+    a = ed.edit(image=_image(5), prompt="a rusty bicycle", seed=3)
+    b = ed.edit(image=_image(5), prompt="a wooden boat on a lake", seed=3)
+    assert a.size == (1024, 1024) and not np.array_equal(np.array(a), np.array(b))
