@@ -131,9 +131,11 @@ class FastEditor:
             gen.manual_seed(int(seed))
         else:
             gen.seed()
-        input_image = image.resize((1024, 1024), Image.LANCZOS)      # host-side, identity for 1024x1024 inputs
-        arr = np.ascontiguousarray(np.array(input_image.convert("RGB")))
+        # image.resize((1024, 1024), Image.LANCZOS) of the reference (src/pipeline.py:251) on the GPU, bit-identical to Pillow
+        arr = np.ascontiguousarray(np.array(image.convert("RGB")))
         img = torch.from_numpy(arr[None]).to(self.device)
+        if img.shape[1] != 1024 or img.shape[2] != 1024:
+            img = ops.resize_lanczos(img, 1024, 1024)
         pe, pl = self._encode_prompt(prompt, negative_prompt)
         n_exec = min(int(num_inference_steps * strength), num_inference_steps)
         # reference RNG order: posterior sample, init noise, then one draw per non-final executed step

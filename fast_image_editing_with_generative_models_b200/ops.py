@@ -113,6 +113,32 @@ def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: i
     return out
 
 
+_RS_TABLES = {}
+
+
+def resize_lanczos(img_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """uint8 [N,H,W,3] (CUDA) -> uint8 [N,out_h,out_w,3], bit-identical to PIL ``Image.resize((out_w, out_h), Image.LANCZOS)``."""
+    from .resize import lanczos_tables
+    _req(img_u8, torch.uint8, "resize_lanczos")
+    n, h, w, c = img_u8.shape
+    if c != 3:
+        raise _lib.FieError("resize_lanczos: RGB images expected")
+    dev = img_u8.device
+    key = (h, w, out_h, out_w, str(dev))
+    if key not in _RS_TABLES:
+        bx, kx, ksx = lanczos_tables(w, out_w)
+        by, ky, ksy = lanczos_tables(h, out_h)
+        _RS_TABLES[key] = (bx.to(dev), kx.to(dev), ksx, by.to(dev), ky.to(dev), ksy)
+    bx, kx, ksx, by, ky, ksy = _RS_TABLES[key]
+    out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=dev)
+    tmp = torch.empty((n, h, out_w, 3), dtype=torch.uint8, device=dev) if (out_w != w and out_h != h) else None
+    with _prof("resize", float(img_u8.numel() + out.numel()), "B"):
+        check(_lib.lib().fie_resample_lanczos_u8(_p(img_u8), _p(out), _p(tmp), n, h, w, out_h, out_w, _p(bx), _p(kx), ksx, _p(by), _p(ky), ksy, _stream()),
+              "fie_resample_lanczos_u8")
+    _count((out_w != w) + (out_h != h))
+    return out
+
+
 def preprocess(img_u8: torch.Tensor, c_out: int = 4, normalize: bool = True) -> torch.Tensor:
     _req(img_u8, torch.uint8, "preprocess")
     n, h, w, _ = img_u8.shape

@@ -40,6 +40,14 @@ size_t fie_canny_workspace_bytes(int n, int h, int w);
 int fie_canny_u8(const void* img, void* edges, int n, int h, int w, int in_channels, int out_channels,
                  int low, int high, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Lanczos resize: replaces image.resize((1024, 1024), Image.LANCZOS) at reference src/pipeline.py:251 ----
+ * uint8 [n,h,w,3] -> uint8 [n,oh,ow,3], bit-identical to Pillow: a horizontal then a vertical fixed-point pass (a pass is skipped when
+ * that size does not change).  bounds_* int32 [out,2] = (first input index, count), coeff_* int32 [out,ksize] = 2^22 fixed-point
+ * weights, computed on the host in double precision as Pillow does (resize.py); tmp: uint8 [n,h,ow,3] scratch (both passes). */
+int fie_resample_lanczos_u8(const void* in_u8, void* out_u8, void* tmp_u8, int n, int h, int w, int oh, int ow,
+                            const int* bounds_x, const int* coeff_x, int ksize_x, const int* bounds_y, const int* coeff_y, int ksize_y,
+                            void* stream);
+
 /* ---- Pre/post-processing: replaces VaeImageProcessor.preprocess/postprocess inside the diffusers call
  *      at reference src/pipeline.py:261-272 ---- */
 /* uint8 [n,h,w,3] -> fp16 [n,h,w,c_out] (c_out >= 3, extra channels zero): x/127.5-1 (normalize=1) or x/255 */

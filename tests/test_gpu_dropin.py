@@ -102,3 +102,22 @@ def test_editor_with_text_encoders(cuda_dev):
     a = ed.edit(image=_image(5), prompt="a rusty bicycle", seed=3)
     b = ed.edit(image=_image(5), prompt="a wooden boat on a lake", seed=3)
     assert a.size == (1024, 1024) and not np.array_equal(np.array(a), np.array(b))
+
+
+@pytest.mark.parametrize("h,w,oh,ow", [(512, 512, 1024, 1024), (480, 640, 1024, 1024), (1500, 1100, 1024, 1024), (1024, 512, 1024, 1024), (333, 777, 256, 300)])
+def test_gpu_lanczos_is_pillow_lanczos(cuda_dev, h, w, oh, ow):
+    """image.resize((1024, 1024), Image.LANCZOS) of the reference (src/pipeline.py:251) on the GPU: bit-identical to Pillow."""
+    from fast_image_editing_with_generative_models_b200 import ops
+    rng = np.random.default_rng(h + w)
+    a = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    out = ops.resize_lanczos(torch.from_numpy(a).to(cuda_dev), oh, ow).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(out[i], np.array(Image.fromarray(a[i]).resize((ow, oh), Image.LANCZOS)))
+
+
+def test_edit_resizes_like_the_reference(editor):
+    """A 512x512 source goes through the GPU Lanczos path; the result equals editing the PIL-resized image."""
+    small = _image(7, (512, 512))
+    a = editor.edit(image=small, prompt="a rusty bicycle", seed=5)
+    b = editor.edit(image=small.resize((1024, 1024), Image.LANCZOS), prompt="a rusty bicycle", seed=5)
+    assert np.array_equal(np.array(a), np.array(b))
