@@ -57,7 +57,7 @@ class FastEditor:
 
     def __init__(self, model_name="sdxl", device="cuda", dtype=torch.float16, enable_cpu_offload=True, use_full_precision=False,
                  use_full_controlnet=False, *, state: Optional[Dict] = None, prompt_encoder: Optional[Callable] = None, tiny: bool = False,
-                 text_encoders: bool = False, verbose: bool = True):
+                 text_encoders: bool = False, checkpoints: Optional[Dict[str, str]] = None, verbose: bool = True):
         if model_name not in self.MODEL_CONFIGS:
             raise ValueError(f"Unknown model: {model_name}. Choose from {list(self.MODEL_CONFIGS.keys())}")
         self.model_name = model_name
@@ -75,6 +75,11 @@ class FastEditor:
         if not torch.cuda.is_available():
             raise RuntimeError("FastEditor (B200-native): no CUDA device available")
         tiny = tiny or os.environ.get("FIE_TINY") == "1"     # small same-topology models: CLI smoke tests
+        if state is None and checkpoints:
+            # real weights: diffusers folders {unet, controlnet, vae} (+ optional LCM-LoRA file), see checkpoints.py
+            from . import checkpoints as K
+            self._say("[FastEditor] Loading checkpoints...")
+            state = K.load_state(checkpoints["unet"], checkpoints["controlnet"], checkpoints["vae"], checkpoints.get("lora"))
         if state is None:
             self._say("[FastEditor] Generating seeded synthetic weights (no checkpoints available offline)...")
             state = model_zoo.synthetic_state(model_name, use_full_controlnet, tiny)
