@@ -32,6 +32,7 @@ SIGNATURES = {
     "fie_resample_lanczos_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "fie_preprocess_u8_to_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fie_preprocess_u8_to_f16_pad8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "fie_pad8_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fie_postprocess_f16_to_u8": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fie_add_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "fie_silu_f16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),

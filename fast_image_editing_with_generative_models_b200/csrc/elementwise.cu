@@ -48,6 +48,18 @@ __global__ void __launch_bounds__(256) k_pre_pad8(const uint8_t* __restrict__ in
     }
 }
 
+// fp16 [n,h,w,4] (latents) -> the same zero-padded 8-channel layout [n][h+2][w+8][8] (channels 4..7 and borders zero)
+__global__ void __launch_bounds__(256) k_pad8_f16(const uint2* __restrict__ in, uint4* __restrict__ out, int n, int h, int w) {
+    const int wp = w + 8, hp = h + 2;
+    const long long total = (long long)n * hp * wp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % wp) - 1; const long long t = i / wp; const int yy = (int)(t % hp) - 1; const long long img = t / hp;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (xx >= 0 && xx < w && yy >= 0 && yy < h) { const uint2 v = __ldg(in + (img * h + yy) * w + xx); u.x = v.x; u.y = v.y; }
+        out[i] = u;
+    }
+}
+
 // ---- VaeImageProcessor.postprocess: clamp(x/2+0.5,0,1) -> round(x*255) -> u8 ----
 __global__ void __launch_bounds__(256) k_post(const __half* __restrict__ in, int ld, uint8_t* __restrict__ out, long long npix) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
@@ -274,6 +286,12 @@ extern "C" int fie_preprocess_u8_to_f16_pad8(const void* img, void* out, int n, 
     const long long total = (long long)n * (h + 2) * (w + 8);
     k_pre_pad8<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)img, (uint4*)out, n, h, w, normalize);
     return check_launch("fie_preprocess_u8_to_f16_pad8");
+}
+extern "C" int fie_pad8_f16(const void* x4, void* out, int n, int h, int w, void* stream) {
+    FIE_REQUIRE(x4 && out && n > 0 && h > 0 && w > 0, "fie_pad8_f16: bad args");
+    const long long total = (long long)n * (h + 2) * (w + 8);
+    k_pad8_f16<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint2*)x4, (uint4*)out, n, h, w);
+    return check_launch("fie_pad8_f16");
 }
 extern "C" int fie_postprocess_f16_to_u8(const void* x, int ld, void* out, int n, int h, int w, void* stream) {
     FIE_REQUIRE(x && out && n > 0 && h > 0 && w > 0 && ld >= 3, "fie_postprocess_f16_to_u8: bad args");

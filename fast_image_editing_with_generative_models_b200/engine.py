@@ -197,7 +197,7 @@ class _EncoderPart:
         ch = cfg.block_out_channels
         self.temb_slot: List = []
         self.kv_slot: List = []
-        self.conv_in = pk.cin4("conv_in")
+        self.conv_in = pk.c8("conv_in")           # 4 latent channels -> block_out_channels[0] on the tensor cores (zero-padded 8-channel input)
         self.t1, self.t2 = pk.linear("time_embedding.linear_1"), pk.linear("time_embedding.linear_2")
         self.a1, self.a2 = pk.linear("add_embedding.linear_1"), pk.linear("add_embedding.linear_2")
         self.down: List[dict] = []
@@ -291,7 +291,7 @@ class UNet:
         ctx_kv, aug = prompt_state
         cfg = self.cfg
         temb = self.enc.time_rows(t, aug)
-        h = ops.conv3x3_cin4(x, self.enc.conv_in[0], self.enc.conv_in[1], cfg.block_out_channels[0])
+        h = ops.conv3x3_c8(ops.pad8(x), self.enc.conv_in[0], col_bias=self.enc.conv_in[1])
         h, skips = self.enc.down_mid(h, temb, ctx_kv, nctx)
         if down_res is not None:
             skips = [ops.add(s, r) for s, r in zip(skips, down_res)]
@@ -341,8 +341,7 @@ class ControlNet:
         """-> (down residuals, mid residual), each already multiplied by the conditioning scale."""
         ctx_kv, aug = prompt_state
         temb = self.enc.time_rows(t, aug)
-        h = ops.conv3x3_cin4(x, self.enc.conv_in[0], self.enc.conv_in[1], self.cfg.unet.block_out_channels[0])
-        h = ops.add(h, cond_emb)
+        h = ops.conv3x3_c8(ops.pad8(x), self.enc.conv_in[0], col_bias=self.enc.conv_in[1], residual=cond_emb)     # conv_in(x) + conditioning embedding
         h, skips = self.enc.down_mid(h, temb, ctx_kv, nctx)
         down = [ops.gemm(s, w, col_bias=b, scale=scale) for s, (w, b) in zip(skips, self.zero)]
         mid = ops.gemm(h, self.zero_mid[0], col_bias=self.zero_mid[1], scale=scale)
@@ -415,7 +414,7 @@ class VAE:
         w = torch.zeros((L, 3, 3, 4), dtype=torch.float32, device=device)
         w[:, 1, 1, :L] = pq_w.reshape(L, L) / cfg.scaling_factor          # 1x1 conv as centre tap; latents/scaling folded in
         self.pq = (w.contiguous(), pq_b)
-        self.d_in = pk.cin4("decoder.conv_in")
+        self.d_in = pk.c8("decoder.conv_in")
         self.d_mid = (Resnet(pk, "decoder.mid_block.resnets.0", eps, g), _VAEAttention(pk, "decoder.mid_block.attentions.0", g, eps),
                       Resnet(pk, "decoder.mid_block.resnets.1", eps, g))
         self.d_up = []
@@ -455,7 +454,7 @@ class VAE:
         cfg = self.cfg
         L = cfg.latent_channels
         h = ops.conv3x3_cin4(z, self.pq[0], self.pq[1], L, ld_out=4)
-        h = ops.conv3x3_cin4(h, self.d_in[0], self.d_in[1], cfg.block_out_channels[-1])
+        h = ops.conv3x3_c8(ops.pad8(h), self.d_in[0], col_bias=self.d_in[1], gn_groups=self.gn_groups)
         h = self.d_mid[0](h)
         h = self.d_mid[1](h)
         h = self.d_mid[2](h)

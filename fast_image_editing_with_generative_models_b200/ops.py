@@ -158,6 +158,18 @@ def preprocess_pad8(img_u8: torch.Tensor, normalize: bool = True) -> torch.Tenso
     return out
 
 
+def pad8(x4: torch.Tensor) -> torch.Tensor:
+    """fp16 [N,H,W,4] -> zero-padded fp16 [N,H+2,W+8,8] (input layout of :func:`conv3x3_c8`)."""
+    _req(x4, torch.float16, "pad8")
+    n, h, w, c = x4.shape
+    if c != 4:
+        raise _lib.FieError("pad8: 4-channel input expected")
+    out = torch.empty((n, h + 2, w + 8, 8), dtype=torch.float16, device=x4.device)
+    check(_lib.lib().fie_pad8_f16(_p(x4), _p(out), n, h, w, _stream()), "fie_pad8_f16")
+    _count()
+    return out
+
+
 def postprocess(x: torch.Tensor) -> torch.Tensor:
     """fp16 [N,H,W,C>=3] -> uint8 [N,H,W,3]."""
     _req(x, torch.float16, "postprocess")
@@ -368,7 +380,8 @@ def conv_up2x(x: torch.Tensor, w4: torch.Tensor, *, col_bias=None, out: Optional
     return out
 
 
-def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] = None, col_bias=None, act=ACT_NONE, gn_groups: int = 0) -> torch.Tensor:
+def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] = None, col_bias=None, act=ACT_NONE, gn_groups: int = 0,
+               residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Tensor-core conv_in.  xp: zero-padded [N,H+2,W+8,8] fp16 (:func:`preprocess_pad8`), w: [Cout, 384] (weights.pack_conv3x3_c8)
     -> [N,H,W,cout_valid]."""
     _req(xp, torch.float16, "conv3x3_c8")
@@ -381,7 +394,7 @@ def conv3x3_c8(xp: torch.Tensor, w: torch.Tensor, *, cout_valid: Optional[int] =
     gn = None
     if gn_groups and cv == cout and _gn_stats_ok(cout, gn_groups, h * wd, out.stride(-2)):
         gn = (_gn_stats_alloc(out, n, gn_groups), gn_groups, h * wd)
-    ep = _epilogue(col_bias, act=act, gn=gn)
+    ep = _epilogue(col_bias, act=act, gn=gn, residual=residual)
     with _prof("conv_in_c8", 2.0 * out.numel() + 2.0 * xp.numel(), "B", f"[{n},{h},{wd},8]->{cv}"):
         check(_lib.lib().fie_conv3x3_c8_f16(_p(xp), _p(w), _p(out), out.stride(-2), n, h, wd, cout, cv, ctypes.byref(ep), _stream()), "fie_conv3x3_c8_f16")
     _count()

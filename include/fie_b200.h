@@ -55,6 +55,8 @@ int fie_preprocess_u8_to_f16(const void* img_u8, void* out_f16, int n, int h, in
 /* uint8 [n,h,w,3] -> fp16 [n,h+2,w+8,8]: the same conversion written into the zero-padded 8-channel layout read by
  * fie_conv3x3_c8_f16 (real pixel (y,x) at (y+1,x+1); borders and channels 3..7 are zero) */
 int fie_preprocess_u8_to_f16_pad8(const void* img_u8, void* out_f16, int n, int h, int w, int normalize, void* stream);
+/* fp16 [n,h,w,4] (latents) -> the same zero-padded layout fp16 [n,h+2,w+8,8] (channels 4..7 and borders zero) */
+int fie_pad8_f16(const void* x4_f16, void* out_f16, int n, int h, int w, void* stream);
 /* fp16 [n,h,w,ld] (first 3 channels) -> uint8 [n,h,w,3]: round(clamp(x/2+0.5,0,1)*255) */
 int fie_postprocess_f16_to_u8(const void* x_f16, int ld, void* out_u8, int n, int h, int w, void* stream);
 

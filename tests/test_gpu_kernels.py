@@ -361,6 +361,26 @@ def test_conv3x3_c8_image_input(cuda_dev, n, h, w, cout, silu):
     assert rel_err(out, ref) < 1e-3, rel_err(out, ref)
 
 
+@pytest.mark.parametrize("n,h,w,cout,res", [(2, 128, 128, 320, True), (1, 16, 16, 64, False), (3, 32, 32, 512, True), (2, 8, 8, 32, False)])
+def test_conv3x3_c8_latent_input(cuda_dev, n, h, w, cout, res):
+    """Latent-resolution conv_in (4 channels padded to 8) with the ControlNet's fused `+ cond_emb` residual, vs F.conv2d."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3_c8
+    x = (_rand((n, h, w, 4), cuda_dev, 56) * 3).half()
+    xp = ops.pad8(x)
+    assert xp.shape == (n, h + 2, w + 8, 8)
+    assert torch.equal(xp[:, 1:h + 1, 1:w + 1, :4], x) and float(xp[..., 4:].abs().max()) == 0.0
+    assert float(xp[:, 0].abs().max()) == 0.0 and float(xp[:, -1].abs().max()) == 0.0 and float(xp[:, :, 0].abs().max()) == 0.0 and float(xp[:, :, w + 1:].abs().max()) == 0.0
+    wt = _rand((cout, 4, 3, 3), cuda_dev, 57) / 6
+    bias = _rand((cout,), cuda_dev, 58)
+    r = _rand((n, h, w, cout), cuda_dev, 59).half() if res else None
+    out = ops.conv3x3_c8(xp, pack_conv3x3_c8(wt), col_bias=bias, residual=r)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    assert rel_err(out, ref) < 1e-3, rel_err(out, ref)
+
+
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("b,heads,nq,nkv", [(1, 1, 128, 128), (2, 2, 256, 256), (2, 10, 1024, 1024), (2, 4, 256, 77), (1, 2, 64, 64), (2, 2, 4096, 4096), (1, 3, 200, 333),
                                             (16, 20, 1024, 77), (3, 5, 1000, 77), (2, 10, 4096, 77), (1, 1, 300, 1), (4, 7, 520, 128)])
