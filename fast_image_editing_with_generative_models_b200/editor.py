@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import os
 import zlib
-from typing import Callable, Dict, Optional
+from typing import Sequence, Callable, Dict, Optional
 
 import numpy as np
 import torch
@@ -57,7 +57,8 @@ class FastEditor:
 
     def __init__(self, model_name="sdxl", device="cuda", dtype=torch.float16, enable_cpu_offload=True, use_full_precision=False,
                  use_full_controlnet=False, *, state: Optional[Dict] = None, prompt_encoder: Optional[Callable] = None, tiny: bool = False,
-                 text_encoders: bool = False, checkpoints: Optional[Dict[str, str]] = None, verbose: bool = True):
+                 text_encoders: bool = False, checkpoints: Optional[Dict[str, str]] = None, tokenizers: Optional[Sequence[str]] = None,
+                 verbose: bool = True):
         if model_name not in self.MODEL_CONFIGS:
             raise ValueError(f"Unknown model: {model_name}. Choose from {list(self.MODEL_CONFIGS.keys())}")
         self.model_name = model_name
@@ -101,6 +102,11 @@ class FastEditor:
             self._say("[FastEditor] Building the CLIP text encoders (synthetic weights)...")
             self._text = T.SDXLTextEncoders(T.make_clip_params(c1), c1, T.make_clip_params(c2), c2, device)
             self._text_vocab = c1.vocab_size
+            self._tokenizers = None
+            if tokenizers:
+                # (tokenizer, tokenizer_2) folders with vocab.json + merges.txt: the real CLIP BPE (tokenizer.py)
+                from .tokenizer import CLIPBPETokenizer
+                self._tokenizers = (CLIPBPETokenizer.from_files(tokenizers[0]), CLIPBPETokenizer.from_files(tokenizers[1], pad_token="!"))
         self._say("[FastEditor] Initialization complete!")
 
     # ---- prompt -> embeddings (text encoders are not on the accelerated path) ----
@@ -109,6 +115,9 @@ class FastEditor:
         if self._prompt_encoder is not None:
             return self._prompt_encoder(prompt, negative_prompt)
         if self._text is not None:
+            if self._tokenizers is not None:
+                ids1, ids2 = (torch.tensor(t([negative_prompt, prompt]), dtype=torch.int64) for t in self._tokenizers)
+                return self._text.encode(ids1, ids2)
             from .text_encoder import pseudo_token_ids
             ids = torch.stack([pseudo_token_ids(negative_prompt, self._text_vocab), pseudo_token_ids(prompt, self._text_vocab)])   # the empty negative prompt is ENCODED, as in the reference
             return self._text.encode(ids, ids)          # ([neg, pos] x 77 x 2048, [neg, pos] x 1280)
