@@ -19,7 +19,8 @@ class Epilogue(ctypes.Structure):
     """Mirror of ``fie_epilogue`` (include/fie_b200.h)."""
     _fields_ = [("col_bias", c_void_p), ("row_bias", c_void_p), ("rows_per_group", c_ll), ("ld_row_bias", c_ll), ("m_bias", c_void_p),
                 ("residual", c_void_p), ("ld_res", c_ll), ("scale", c_float), ("act", c_int), ("out_f32", c_int),
-                ("gn_stats", c_void_p), ("gn_groups", c_int), ("gn_rows_per_image", c_ll)]
+                ("gn_stats", c_void_p), ("gn_groups", c_int), ("gn_rows_per_image", c_ll),
+                ("ln_stats_out", c_void_p), ("ln_stats_in", c_void_p), ("ln_eps", c_float), ("ln_dim", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/fie_b200.h declares

@@ -85,6 +85,11 @@ struct GemmParams {
     unsigned long long* gn_stats;   // optional GroupNorm statistics of the output [images][groups][2], 2^-20 fixed point
     int gn_cpg, gn_groups;          // channels per group (divides 32), groups
     long long gn_rows;              // rows per image
+    // LayerNorm folding (see fie_epilogue): statistics of the output rows / normalisation of the input rows
+    unsigned long long* ln_out;     // [M][2] (sum, sum of squares of the fp16 outputs; 2^-20 fixed point) or NULL
+    const unsigned long long* ln_in;  // [M][2] statistics of the A rows, or NULL
+    float ln_eps;
+    double ln_inv;                  // 1 / (2^20 * length of the normalised A rows)
 };
 
 // Output row of accumulator row m (identity, or the strided scatter of one phase of the fused nearest-2x upsample).
@@ -201,6 +206,9 @@ __device__ __noinline__ void epi_slow_chunk(const GemmParams& p, uint32_t taddr,
         } else store_chunk(p, m, nout, v);
     }
 }
+
+// acc * rstd + bias: rstd is the epilogue thread's LayerNorm row scale, exactly 1 (-> acc + bias) when no LayerNorm is folded
+#define FIE_LN_LIN(acc, b) fmaf(__uint_as_float(acc), ln_rstd, __uint_as_float(b))
 
 // Debug accounting: clock cycles a role spends blocked on a barrier (only when a trace buffer is installed).
 #define FIE_TIMED(acc, stmt) do { if (p.trace) { const long long t0_ = clock64(); stmt; (acc) += clock64() - t0_; } else { stmt; } } while (0)
@@ -467,8 +475,15 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
         // it per chunk, lane i fetches element i of each of this warp's chunks for the NEXT (tile, mt) group into registers
         // while the current group is processed, then parks them in the warp's private staging area, where the hot loop reads
         // them back as broadcast 128-bit shared loads.  Slots 0-3: value columns (col_bias + row_bias), 4-7: GEGLU gate columns.
+        // Folded LayerNorm (p.ln_in): A holds the raw rows x and the rows of B = gamma (.) W are centred over K, so that
+        // sum_k x_k B_nk = sum_k (x_k - mean) (gamma W)_nk and LN(x) W^T + b = rstd * acc + (b + W beta): the epilogue only scales
+        // by this row's 1/sigma (a thread owns one row; its statistics are fetched with the next group's biases).
         const uint32_t bias_s = smem_u32(epi_smem) + (uint32_t)(warp - W_EPI0) * 1024u;
         float nb_col[4], nb_row[4], nb_gate[4];
+        const bool ln_on = p.ln_in != nullptr;
+        unsigned long long nl_s = 0, nl_q = 0;                 // next group's row statistics
+        float ln_rstd = 1.0f;                                  // this group's 1/sigma (1 when no LayerNorm is folded)
+        float lo_s = 0.0f, lo_q = 0.0f;                        // p.ln_out: this thread's partial row sums over its chunks
         auto bias_issue = [&](int tile_, int mt_) {
             if (!fast_cfg || tile_ >= num_tiles) return;
             const int n_blk_ = tile_ % p.num_n_blocks;
@@ -482,6 +497,11 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                 nb_row[j] = (rbp && in) ? __ldg(rbp + n_) : 0.0f;
                 if (GEGLU) nb_gate[j] = (p.col_bias && in && n_ + (block_n >> 1) < p.N) ? __ldg(p.col_bias + n_ + (block_n >> 1)) : 0.0f;
             }
+            if (ln_on) {
+                const long long m_ = mw_ + lane;
+                nl_s = nl_q = 0;
+                if (m_ < p.M) { nl_s = __ldg(p.ln_in + 2 * m_); nl_q = __ldg(p.ln_in + 2 * m_ + 1); }
+            }
         };
         auto bias_commit = [&]() {
             if (!fast_cfg) return;
@@ -490,6 +510,11 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
             for (int j = 0; j < 4; ++j) {
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + j * 128 + lane * 4), "f"(nb_col[j] + nb_row[j]) : "memory");
                 if (GEGLU) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + (4 + j) * 128 + lane * 4), "f"(nb_gate[j]) : "memory");
+            }
+            if (ln_on) {                                          // biased variance in double: E[x^2] - mean^2 cancels
+                const double mean = __ll2double_rn((long long)nl_s) * p.ln_inv;
+                const double var = fma(-mean, mean, __ll2double_rn((long long)nl_q) * p.ln_inv);
+                ln_rstd = rsqrtf(fmaxf((float)var, 0.0f) + p.ln_eps);
             }
             __syncwarp();
         };
@@ -563,10 +588,10 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const uint4 bv = lds128(bslot + i * 16), bg = lds128(bslot + 512 + i * 16);
-                            v[4 * i] = (__uint_as_float(r[4 * i]) + __uint_as_float(bv.x)) * gelu_erf_f(__uint_as_float(g[4 * i]) + __uint_as_float(bg.x));
-                            v[4 * i + 1] = (__uint_as_float(r[4 * i + 1]) + __uint_as_float(bv.y)) * gelu_erf_f(__uint_as_float(g[4 * i + 1]) + __uint_as_float(bg.y));
-                            v[4 * i + 2] = (__uint_as_float(r[4 * i + 2]) + __uint_as_float(bv.z)) * gelu_erf_f(__uint_as_float(g[4 * i + 2]) + __uint_as_float(bg.z));
-                            v[4 * i + 3] = (__uint_as_float(r[4 * i + 3]) + __uint_as_float(bv.w)) * gelu_erf_f(__uint_as_float(g[4 * i + 3]) + __uint_as_float(bg.w));
+                            v[4 * i] = FIE_LN_LIN(r[4 * i], bv.x) * gelu_erf_f(FIE_LN_LIN(g[4 * i], bg.x));
+                            v[4 * i + 1] = FIE_LN_LIN(r[4 * i + 1], bv.y) * gelu_erf_f(FIE_LN_LIN(g[4 * i + 1], bg.y));
+                            v[4 * i + 2] = FIE_LN_LIN(r[4 * i + 2], bv.z) * gelu_erf_f(FIE_LN_LIN(g[4 * i + 2], bg.z));
+                            v[4 * i + 3] = FIE_LN_LIN(r[4 * i + 3], bv.w) * gelu_erf_f(FIE_LN_LIN(g[4 * i + 3], bg.w));
                         }
                     } else {
                         uint32_t r[32];
@@ -575,8 +600,8 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const uint4 bv = lds128(bslot + i * 16);
-                            v[4 * i] = __uint_as_float(r[4 * i]) + __uint_as_float(bv.x); v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + __uint_as_float(bv.y);
-                            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + __uint_as_float(bv.z); v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + __uint_as_float(bv.w);
+                            v[4 * i] = FIE_LN_LIN(r[4 * i], bv.x); v[4 * i + 1] = FIE_LN_LIN(r[4 * i + 1], bv.y);
+                            v[4 * i + 2] = FIE_LN_LIN(r[4 * i + 2], bv.z); v[4 * i + 3] = FIE_LN_LIN(r[4 * i + 3], bv.w);
                         }
                         if (p.act == FIE_ACT_SILU) {
 #pragma unroll
@@ -602,6 +627,13 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                         for (int i = 0; i < 8; ++i) {
                             float2 f = __half22float2(*reinterpret_cast<const __half2*>(&res0[i])); v[2 * i] += f.x; v[2 * i + 1] += f.y;
                             f = __half22float2(*reinterpret_cast<const __half2*>(&res1[i])); v[16 + 2 * i] += f.x; v[16 + 2 * i + 1] += f.y;
+                        }
+                    }
+                    if (p.ln_out) {                                     // LayerNorm statistics of this row of the (fp16-rounded) output
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 f = __half22float2(__floats2half2_rn(v[2 * i], v[2 * i + 1]));
+                            lo_s += f.x + f.y; lo_q = fmaf(f.x, f.x, fmaf(f.y, f.y, lo_q));
                         }
                     }
                     if (p.gn_stats) {                                   // GroupNorm statistics of the (fp16-rounded) output for the consumer
@@ -639,6 +671,13 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                         }
                         stg256(orow + nout, o0); stg256(orow + nout + 16, o1);
                     }
+                }
+                if (p.ln_out) {
+                    if (row_ok) {
+                        atomicAdd(p.ln_out + 2 * m, (unsigned long long)__float2ll_rn(lo_s * 1048576.0f));
+                        atomicAdd(p.ln_out + 2 * m + 1, (unsigned long long)__float2ll_rn(lo_q * 1048576.0f));
+                    }
+                    lo_s = 0.0f; lo_q = 0.0f;
                 }
             }   // mt
             tc_fence_before();
@@ -735,7 +774,7 @@ static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out
 }
 
 static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
-    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0, nullptr, 0, 0};
+    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0, nullptr, 0, 0, nullptr, nullptr, 0.0f, 0};
     if (!ep) ep = &kDefault;
     p.D = D; p.ldd = ldd;
     p.col_bias = ep->col_bias; p.row_bias = ep->row_bias; p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
@@ -756,6 +795,17 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
                     (!p.residual || ((p.ld_res % 16) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0)) &&
                     (!p.row_bias || (p.rows_per_group % 32) == 0),
                     "epilogue: fused GroupNorm statistics need the fast epilogue path (fp16 output, N %% 32 == 0, 32-byte aligned rows)");
+    }
+    p.ln_out = (unsigned long long*)ep->ln_stats_out; p.ln_in = (const unsigned long long*)ep->ln_stats_in;
+    p.ln_eps = ep->ln_eps; p.ln_inv = ep->ln_dim > 0 ? 1.0 / (1048576.0 * (double)ep->ln_dim) : 0.0;
+    if (p.ln_out || p.ln_in) {
+        const int n_out = p.act == FIE_ACT_GEGLU ? N / 2 : N;
+        FIE_REQUIRE(!p.out_f32 && (n_out % 32) == 0 && (N % 32) == 0 && (ldd % 16) == 0 && (reinterpret_cast<uintptr_t>(D) & 31) == 0 &&
+                    (!p.residual || ((p.ld_res % 16) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0)) &&
+                    (!p.row_bias || (p.rows_per_group % 32) == 0),
+                    "epilogue: folded LayerNorm needs the fast epilogue path (fp16 output, N %% 32 == 0, 32-byte aligned rows)");
+        FIE_REQUIRE(!p.ln_in || (ep->ln_dim > 0 && p.ln_eps >= 0.0f && !p.row_bias && !p.m_bias), "epilogue: ln_stats_in needs ln_dim > 0, ln_eps >= 0 and no row / m bias");
+        FIE_REQUIRE(!(p.ln_out && p.act == FIE_ACT_GEGLU), "epilogue: ln_stats_out is not supported with the GEGLU epilogue");
     }
     (void)M;
     return FIE_OK;

@@ -22,10 +22,14 @@ import torch
 
 from . import ops
 from .configs import ControlNetConfig, UNetConfig, VAEConfig, skip_channels
-from .weights import fuse_lora, pack_conv3x3, pack_conv3x3_c8, pack_conv_up2x, pack_geglu
+from .weights import fold_layernorm, fuse_lora, pack_conv3x3, pack_conv3x3_c8, pack_conv_up2x, pack_geglu
 
 Tensor = torch.Tensor
 Params = Dict[str, Tensor]
+
+
+# Fold the transformer blocks' LayerNorms into the neighbouring GEMMs (FIE_FOLD_LN=0: separate fie_layernorm_f16 launches)
+FOLD_LN = os.environ.get("FIE_FOLD_LN", "1") != "0"
 
 
 def _pad32(n: int) -> int:
@@ -140,28 +144,52 @@ class Resnet:
 
 
 class TransformerBlock:
+    """BasicTransformerBlock.  With FOLD_LN the three LayerNorms never run as kernels: the GEMM that produces each residual
+    stream also accumulates its row statistics (ln_out), and the GEMM that consumes LN(x) runs on the raw rows with gamma, beta
+    and the mean subtraction folded into its weights (weights.fold_layernorm) and scales by 1/sigma in its epilogue (ln_in)."""
+    LN_EPS = 1e-5
+
     def __init__(self, pk: _Packer, pre: str, c: int, kv_slot: List):
         self.c = c
-        self.ln1, self.ln2, self.ln3 = pk.norm(pre + ".norm1"), pk.norm(pre + ".norm2"), pk.norm(pre + ".norm3")
-        self.wqkv = torch.cat([pk.w(f"{pre}.attn1.{n}") for n in ("to_q", "to_k", "to_v")], 0).to(torch.float16).contiguous()
+        self.fold = FOLD_LN
+        ln1, ln2, ln3 = pk.norm(pre + ".norm1"), pk.norm(pre + ".norm2"), pk.norm(pre + ".norm3")
+        wqkv = torch.cat([pk.w(f"{pre}.attn1.{n}") for n in ("to_q", "to_k", "to_v")], 0)
         self.wo1 = pk.linear(pre + ".attn1.to_out.0")
-        self.wq2 = pk.linear(pre + ".attn2.to_q")[0]
         self.kv_off = sum(t.shape[0] for t in kv_slot)
         kv_slot.append(torch.cat([pk.w(pre + ".attn2.to_k"), pk.w(pre + ".attn2.to_v")], 0).to(torch.float16))
         self.wo2 = pk.linear(pre + ".attn2.to_out.0")
-        self.wg, self.bg = pack_geglu(*pk.linear(pre + ".ff.net.0.proj"))
         self.wf = pk.linear(pre + ".ff.net.2")
+        if self.fold:
+            self.wqkv, self.bqkv = fold_layernorm(wqkv, None, *ln1)
+            self.wq2, self.bq2 = fold_layernorm(pk.w(pre + ".attn2.to_q"), pk.b(pre + ".attn2.to_q"), *ln2)
+            self.wg, self.bg = pack_geglu(*fold_layernorm(pk.w(pre + ".ff.net.0.proj"), pk.b(pre + ".ff.net.0.proj"), *ln3))
+        else:
+            self.ln1, self.ln2, self.ln3 = ln1, ln2, ln3
+            self.wqkv = wqkv.to(torch.float16).contiguous()
+            self.wq2 = pk.linear(pre + ".attn2.to_q")[0]
+            self.wg, self.bg = pack_geglu(*pk.linear(pre + ".ff.net.0.proj"))
 
-    def __call__(self, h: Tensor, b: int, ntok: int, ctx_kv: Tensor, nctx: int) -> Tensor:
+    def __call__(self, h: Tensor, b: int, ntok: int, ctx_kv: Tensor, nctx: int, st: Optional[Tensor] = None, st_next: Optional[Tensor] = None) -> Tensor:
+        """st: int64 [3, M, 2] row statistics (st[0] already holds those of h); st_next receives those of the result."""
         c, heads = self.c, self.c // 64
+        k = ctx_kv[:, self.kv_off:self.kv_off + c]
+        v = ctx_kv[:, self.kv_off + c:self.kv_off + 2 * c]
+        if self.fold:
+            eps = self.LN_EPS
+            qkv = ops.gemm(h, self.wqkv, col_bias=self.bqkv, ln_in=(st[0], eps))
+            a = ops.attention_d64(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], b, heads, ntok, ntok)
+            h = ops.gemm(a, self.wo1[0], col_bias=self.wo1[1], residual=h, ln_out=st[1])
+            q = ops.gemm(h, self.wq2, col_bias=self.bq2, ln_in=(st[1], eps))
+            a = ops.attention_d64(q, k, v, b, heads, ntok, nctx)
+            h = ops.gemm(a, self.wo2[0], col_bias=self.wo2[1], residual=h, ln_out=st[2])
+            g = ops.gemm(h, self.wg, col_bias=self.bg, act=ops.ACT_GEGLU, ln_in=(st[2], eps))
+            return ops.gemm(g, self.wf[0], col_bias=self.wf[1], residual=h, ln_out=st_next)
         n1 = ops.layernorm(h, *self.ln1)
         qkv = ops.gemm(n1, self.wqkv)
         a = ops.attention_d64(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], b, heads, ntok, ntok)
         h = ops.gemm(a, self.wo1[0], col_bias=self.wo1[1], residual=h)
         n2 = ops.layernorm(h, *self.ln2)
         q = ops.gemm(n2, self.wq2)
-        k = ctx_kv[:, self.kv_off:self.kv_off + c]
-        v = ctx_kv[:, self.kv_off + c:self.kv_off + 2 * c]
         a = ops.attention_d64(q, k, v, b, heads, ntok, nctx)
         h = ops.gemm(a, self.wo2[0], col_bias=self.wo2[1], residual=h)
         n3 = ops.layernorm(h, *self.ln3)
@@ -181,9 +209,15 @@ class Transformer2D:
         n, hh, ww, c = x.shape
         ntok = hh * ww
         h = ops.groupnorm(x, self.norm[0], self.norm[1], 1e-6, False, self.groups)
-        h = ops.gemm(h.view(n * ntok, c), self.pin[0], col_bias=self.pin[1])
-        for blk in self.blocks:
-            h = blk(h, n, ntok, ctx_kv, nctx)
+        fold = bool(self.blocks) and self.blocks[0].fold
+        # one zero-fill for the row statistics of all 3 x depth LayerNorm inputs of this transformer
+        st = ops.zeros_i64((3 * len(self.blocks), n * ntok, 2), x.device) if fold else None
+        h = ops.gemm(h.view(n * ntok, c), self.pin[0], col_bias=self.pin[1], ln_out=st[0] if fold else None)
+        for i, blk in enumerate(self.blocks):
+            if fold:
+                h = blk(h, n, ntok, ctx_kv, nctx, st[3 * i:3 * i + 3], st[3 * i + 3] if i + 1 < len(self.blocks) else None)
+            else:
+                h = blk(h, n, ntok, ctx_kv, nctx)
         out = ops.gemm(h, self.pout[0], col_bias=self.pout[1], residual=x.view(n * ntok, c))
         return out.view(n, hh, ww, c)
 

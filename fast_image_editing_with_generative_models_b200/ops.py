@@ -262,6 +262,11 @@ def _gn_stats_alloc(out: torch.Tensor, n_img: int, groups: int) -> torch.Tensor:
     return st
 
 
+def zeros_i64(shape, device) -> torch.Tensor:
+    """Zeroed int64 statistics workspace (one memset node; device memory is torch's job)."""
+    return torch.zeros(shape, dtype=torch.int64, device=device)
+
+
 def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool, groups: int = 32,
               x1: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x0 [N,H,W,C0] (+ optional concatenated x1 [N,H,W,C1]) -> [N,H,W,C0+C1] normalised (+SiLU).  If x0 was produced by a
@@ -296,7 +301,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False, gn=None):
+def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False, gn=None,
+              ln_out=None, ln_in=None):
     ep = Epilogue()
     ep.col_bias = _p(col_bias); ep.row_bias = _p(row_bias); ep.rows_per_group = int(rows_per_group)
     ep.ld_row_bias = row_bias.stride(-2) if (row_bias is not None and row_bias.dim() >= 2) else 0
@@ -305,13 +311,19 @@ def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, resid
     ep.scale = float(scale); ep.act = int(act); ep.out_f32 = int(out_f32)
     if gn is not None:                      # (stats tensor, groups, rows per image)
         ep.gn_stats = _p(gn[0]); ep.gn_groups = int(gn[1]); ep.gn_rows_per_image = int(gn[2])
+    if ln_out is not None:                  # int64 [M, 2] row statistics of the output, zeroed by the caller
+        ep.ln_stats_out = _p(ln_out)
+    if ln_in is not None:                   # (int64 [M, 2] statistics of the A rows, eps)
+        ep.ln_stats_in = _p(ln_in[0]); ep.ln_eps = float(ln_in[1])
     return ep
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, n_valid: Optional[int] = None,
          col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False,
-         gn_groups: int = 0, gn_rows: int = 0) -> torch.Tensor:
-    """D = epilogue(A @ W^T).  a: [..., K] fp16 rows (row stride may exceed K), w: [N, K] fp16; optional a1 continues K."""
+         gn_groups: int = 0, gn_rows: int = 0, ln_out: Optional[torch.Tensor] = None, ln_in=None) -> torch.Tensor:
+    """D = epilogue(A @ W^T).  a: [..., K] fp16 rows (row stride may exceed K), w: [N, K] fp16; optional a1 continues K.
+    ln_out: zeroed int64 [M, 2] that receives the LayerNorm statistics of the output rows.  ln_in = (stats, eps): the A rows are
+    layer-normalised on the fly (w / col_bias from weights.fold_layernorm)."""
     if a.dtype != torch.float16 or w.dtype != torch.float16 or not a.is_cuda:
         raise _lib.FieError("gemm: fp16 CUDA tensors required")
     k0 = a.shape[-1]
@@ -332,7 +344,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
     gn = None
     if gn_groups and gn_rows and not out_f32 and m % gn_rows == 0 and _gn_stats_ok(n_out, gn_groups, gn_rows, ldd):
         gn = (_gn_stats_alloc(out, m // gn_rows, gn_groups), gn_groups, gn_rows)
-    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32, gn)
+    if ln_out is not None and (ln_out.dtype != torch.int64 or ln_out.numel() != 2 * m or not ln_out.is_contiguous()):
+        raise _lib.FieError("gemm: ln_out must be a contiguous int64 [M, 2] tensor")
+    if ln_in is not None and (ln_in[0].dtype != torch.int64 or ln_in[0].numel() != 2 * m or not ln_in[0].is_contiguous()):
+        raise _lib.FieError("gemm: ln_in = (contiguous int64 [M, 2] statistics, eps)")
+    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32, gn, ln_out, ln_in)
+    ep.ln_dim = k
     with _prof("gemm", 2.0 * m * n * k, "FLOP", f"M{m} N{n} K{k} act{act} res{int(residual is not None)} f32{int(out_f32)}"):
         check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")
     _count()

@@ -66,6 +66,19 @@ def pack_geglu(w: torch.Tensor, b: Optional[torch.Tensor]) -> Tuple[torch.Tensor
     return wp, bp
 
 
+def fold_layernorm(w: torch.Tensor, b: Optional[torch.Tensor], gamma: torch.Tensor, beta: Optional[torch.Tensor]):
+    """LayerNorm (gamma, beta over K) followed by Linear(W [N, K], b) as ONE GEMM on the un-normalised rows (fie_epilogue
+    ln_stats_in).  With W' = W (.) gamma and its rows centred over K, W'' = W' - mean_k(W'):
+        sum_k x_k W''_nk = sum_k (x_k - mean(x)) W'_nk,   so   LN(x) W^T + b = rstd(x) * (x W''^T) + (b + W beta)
+    and the epilogue only has to scale each row by its 1/sigma.  Returns (W'' fp16 [N, K], bias fp32 [N])."""
+    w32 = w.float() * gamma.float()[None, :]
+    w16 = (w32 - w32.mean(dim=1, keepdim=True)).to(torch.float16).contiguous()
+    bias = torch.zeros(w.shape[0], dtype=torch.float32, device=w.device) if b is None else b.float().clone()
+    if beta is not None:
+        bias = bias + w.float() @ beta.float()
+    return w16, bias.contiguous()
+
+
 def fuse_lora(w: torch.Tensor, lora_a: torch.Tensor, lora_b: torch.Tensor, scale: float) -> torch.Tensor:
     """W' = W + scale * B A  (re-association of the reference's unfused peft path, src/pipeline.py:154).
     Linear: A [r, in], B [out, r].  Conv: A [r, in, k, k], B [out, r, 1, 1]."""

@@ -114,6 +114,16 @@ typedef struct {
     void* gn_stats;          /* or NULL */
     int gn_groups;
     long long gn_rows_per_image;
+    /* Folded LayerNorm (BasicTransformerBlock: x -> LN -> Linear).  Producer side: ln_stats_out = int64 [M][2] (sum, sum of
+     * squares of every fp16 output row over ALL N columns, 2^-20 fixed point; zeroed by the caller) is accumulated while the
+     * rows are written.  Consumer side: ln_stats_in (the statistics of the A rows, ln_dim = their length K) makes the GEMM
+     * compute LN(A) W^T without a normalisation pass: B must hold gamma (.) W with every row centred over K (then
+     * sum_k x_k B_nk = sum_k (x_k - mean) gamma_k W_nk), col_bias includes W beta, and v = rstd[m] * acc + bias (see
+     * weights.fold_layernorm).  Both need the fast epilogue path (fp16 output, N % 32 == 0, 32-byte aligned rows). */
+    void* ln_stats_out;
+    const void* ln_stats_in;
+    float ln_eps;
+    int ln_dim;
 } fie_epilogue;
 
 /* Accumulator tile width used for a GEGLU projection with N = 8C weight rows.  The host packs those rows per tile as

@@ -15,7 +15,7 @@ run() { # name, pytest args...
 run canny tests/test_gpu_canny.py
 run elementwise tests/test_gpu_kernels.py -k "pre_post or add_silu or sincos or groupnorm or layernorm or softmax or scheduler or cin4"
 run gemm_plain tests/test_gpu_kernels.py -k "gemm_plain"
-run gemm_epi tests/test_gpu_kernels.py -k "gemm_epilogue"
+run gemm_epi tests/test_gpu_kernels.py -k "gemm_epilogue or folded_layernorm"
 run gemm_geglu tests/test_gpu_kernels.py -k "gemm_geglu"
 run conv tests/test_gpu_kernels.py -k "test_conv3x3 and not cin4"
 run attention tests/test_gpu_kernels.py -k "attention"

@@ -188,6 +188,56 @@ def test_gemm_epilogue_persistent_ragged(cuda_dev, force_bn):
     assert rel_err(out3, (ref + rowb[g]) * 0.25 + res.float()) < 2e-3
 
 
+@pytest.mark.parametrize("m,c,n", [(16384, 1280, 3840), (4096, 640, 640), (100, 64, 192), (45000, 320, 352), (128, 128, 128)])
+def test_gemm_folded_layernorm(cuda_dev, m, c, n):
+    """x = A W0^T + b0 + res (producer writes LayerNorm row statistics) ; y = LN(x) W^T + b without a normalisation pass
+    (BasicTransformerBlock: norm -> Linear), vs F.layer_norm + F.linear in fp32 on the same fp16 x."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import fold_layernorm
+    a = _rand((m, 64), cuda_dev, 90).half()
+    w0 = (_rand((c, 64), cuda_dev, 91) / 8).half()
+    b0 = _rand((c,), cuda_dev, 92) * 0.5 + 0.7                    # rows with a non-zero mean
+    res = (_rand((m, c), cuda_dev, 93) * 2).half()
+    st = ops.zeros_i64((m, 2), cuda_dev)
+    x = ops.gemm(a, w0, col_bias=b0, residual=res, ln_out=st)
+    xf = x.float()
+    s_ref, q_ref = xf.double().sum(1), (xf.double() ** 2).sum(1)
+    got = st.double() / 2 ** 20
+    assert float((got[:, 0] - s_ref).abs().max()) < 2e-3 * max(1.0, float(s_ref.abs().max())), "row sums"
+    assert float(((got[:, 1] - q_ref).abs() / q_ref).max()) < 1e-4, "row sums of squares"
+    gamma = 1.0 + 0.3 * _rand((c,), cuda_dev, 94)
+    beta = 0.2 * _rand((c,), cuda_dev, 95)
+    w = _rand((n, c), cuda_dev, 96) / math.sqrt(c)
+    b = _rand((n,), cuda_dev, 97)
+    ref = F.linear(F.layer_norm(xf, (c,), gamma, beta, 1e-5), w, b)
+    wf, bf = fold_layernorm(w, b, gamma, beta)
+    y = ops.gemm(x, wf, col_bias=bf, ln_in=(st, 1e-5))
+    assert rel_err(y, ref) < 2e-3, rel_err(y, ref)
+    y2 = ops.gemm(ops.layernorm(x, gamma, beta), w.half(), col_bias=b)           # the unfused path it replaces
+    assert rel_err(y, ref) <= 1.5 * rel_err(y2, ref) + 1e-4, (rel_err(y, ref), rel_err(y2, ref))
+
+
+@pytest.mark.parametrize("m,c", [(1024, 640), (16384, 1280), (200, 64)])
+def test_gemm_folded_layernorm_geglu(cuda_dev, m, c):
+    """LN -> GEGLU projection (FeedForward of BasicTransformerBlock) folded into one GEMM."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import fold_layernorm, pack_geglu
+    x = (_rand((m, c), cuda_dev, 80) * 1.5 + 0.3).half()
+    eye = torch.eye(c, device=cuda_dev).half()
+    st = ops.zeros_i64((m, 2), cuda_dev)
+    x2 = ops.gemm(x, eye, ln_out=st)                                 # copy through the GEMM to obtain the statistics
+    assert torch.equal(x2, x)
+    gamma = 1.0 + 0.3 * _rand((c,), cuda_dev, 81)
+    beta = 0.2 * _rand((c,), cuda_dev, 82)
+    w = _rand((8 * c, c), cuda_dev, 83) / math.sqrt(c)
+    b = _rand((8 * c,), cuda_dev, 84)
+    h = F.linear(F.layer_norm(x.float(), (c,), gamma, beta, 1e-5), w, b)
+    ref = h[:, :4 * c] * F.gelu(h[:, 4 * c:])
+    wg, bg = pack_geglu(*fold_layernorm(w, b, gamma, beta))
+    y = ops.gemm(x, wg, col_bias=bg, act=ops.ACT_GEGLU, ln_in=(st, 1e-5))
+    assert rel_err(y, ref) < 3e-3, rel_err(y, ref)
+
+
 @pytest.mark.parametrize("m,c", [(256, 64), (1024, 640), (300, 128)])
 def test_gemm_geglu(cuda_dev, m, c):
     ops = _ops()
