@@ -6,9 +6,13 @@
 // Per Q tile q and K/V tile j:
 //   S_q = Q_q K_j^T   tcgen05.mma 128x128x64 -> TMEM columns [128q, 128q+128)
 //   softmax           one warpgroup per Q tile, one thread per row (TMEM lane == row: no cross-thread reductions),
-//                     online max / sum with 4-way ILP; P_q written as fp16 into shared memory in the K-major
-//                     128B-swizzled operand layout
-//   O_qj = P_q V_j    tcgen05.mma 128x64x128 (V consumed MN-major straight from its row-major TMA tile) -> TMEM
+//                     online max / sum with 4-way ILP; P_q written as packed fp16 back into TMEM (tcgen05.st, 64 columns):
+//                     with d = 64 the Q K^T product alone reads shared memory at the SM's 128 B/clk, so a P tile that went
+//                     through shared memory (32 KB written + 32 KB read per 128 x 128 tile) would make shared-memory
+//                     bandwidth, not the tensor pipe or the exponentials, the limit
+//   O_qj = P_q V_j    tcgen05.mma 128x64x128, A = P_q from TMEM, B = V consumed MN-major straight from its row-major TMA
+//                     tile -> TMEM
+//   TMEM columns: S_0 0-127, S_1 128-255, O_0 256-319, O_1 320-383, P_0 384-447, P_1 448-511
 //   O_q accumulates in TMEM across K/V tiles; it is rescaled by exp2(m_old - m_new) (tcgen05.ld/st) only when the
 //   running row max of a warp moved.
 // The two warpgroups ping-pong: while one does its softmax the tensor core serves the other (FlashAttention-4 style).
@@ -33,11 +37,36 @@ __device__ __forceinline__ float ex2_emulated(float x) {
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, new on sm_100): one issue slot for two elements.  The softmax is bound by
+// instruction issue and the MUFU unit, not by the FMA pipe, so every scale / subtract / polynomial / row-sum step is done on
+// column pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fadd2_rm(f32x2 a, f32x2 b) { f32x2 r; asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fsub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// 2^x of a column pair without the MUFU unit (see ex2_emulated): x2 must already be clamped to >= -126.
+__device__ __forceinline__ void ex2_emulated2(f32x2 x2, float& p0, float& p1) {
+    const f32x2 magic = pack2(12582912.0f, 12582912.0f);
+    const f32x2 t = fadd2_rm(x2, magic);
+    const f32x2 f = fsub2(x2, fsub2(t, magic));
+    f32x2 q = ffma2(pack2(0.0771190897f, 0.0771190897f), f, pack2(0.2275643945f, 0.2275643945f));
+    q = ffma2(q, f, pack2(0.6951461434f, 0.6951461434f));
+    q = ffma2(q, f, pack2(1.0f, 1.0f));
+    float q0, q1, t0, t1;
+    unpack2(q, q0, q1); unpack2(t, t0, t1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64, ATT_QT = 2, ATT_KV_STAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                                   // 16 KiB (Q, K or V tile)
 constexpr int ATT_OFF_KV = ATT_QT * ATT_TILE_BYTES;                            // after Q0, Q1
-constexpr int ATT_OFF_P = ATT_OFF_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;     // after the K/V ring
-constexpr int ATT_OFF_BAR = ATT_OFF_P + ATT_QT * 32768;
+constexpr int ATT_OFF_BAR = ATT_OFF_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;   // after the K/V ring (P lives in TMEM)
 constexpr int ATT_SMEM = ATT_OFF_BAR + 256;
 
 struct AttnParams {
@@ -47,13 +76,15 @@ struct AttnParams {
     int nq, nkv;
     float scale_log2;
     int causal;       // (kv1 kernel only) key j is visible to query row i iff j <= i
+    long long* trace; // debug: per-CTA wait-cycle accounting [grid][16] (fie_attention_trace), or NULL
 };
+
+#define ATT_TIMED(acc, stmt) do { if (p.trace) { const long long t0_ = clock64(); stmt; (acc) += clock64() - t0_; } else { stmt; } } while (0)
 
 __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant__ AttnParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];     // no static smem in this kernel: base is 1024-aligned
     uint8_t* sQ = smem;
     uint8_t* sKV = smem + ATT_OFF_KV;                     // stage s: K at s*32K, V at s*32K + 16K
-    uint8_t* sP = smem + ATT_OFF_P;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
     uint64_t* q_full = bars;                 // [1]
     uint64_t* kv_full = bars + 1;            // [3]
@@ -98,7 +129,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     } else if (warp == 1) {
         const uint32_t idesc_qk = umma_idesc_f16(ATT_BM, ATT_BN, 0, 0);
         const uint32_t idesc_pv = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);   // B (= V) is MN-major
-        const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
+        const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
         auto issue_qk = [&](int q, int s) {        // S_q = Q_q K_s^T
             if (elect_one_sync()) {
                 const uint64_t ad = umma_desc_sw128(aQ + q * ATT_TILE_BYTES), bd = umma_desc_sw128(aKV + s * 2 * ATT_TILE_BYTES);
@@ -108,6 +139,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
             }
             __syncwarp();
         };
+        long long tw_kv = 0, tw_sfree = 0, tw_pfull = 0; const long long t_begin = p.trace ? clock64() : 0;
         mbar_wait(q_full, 0);
         mbar_wait(&kv_full[0], 0);
         tc_fence_after();
@@ -119,23 +151,22 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
             // S_q(j+1) = Q_q K_{j+1}^T is issued as soon as the softmax warps hold S_q(j) in registers, i.e. while they are
             // still exponentiating it: the next scores are ready when P_q(j) is, and the softmax never waits on the tensor pipe.
             if (j + 1 < n_tiles) {
-                mbar_wait(&kv_full[sn], phn);
+                ATT_TIMED(tw_kv, mbar_wait(&kv_full[sn], phn));
                 for (int q = 0; q < ATT_QT; ++q) {
-                    mbar_wait(&s_free[q], (uint32_t)(j & 1));
+                    ATT_TIMED(tw_sfree, mbar_wait(&s_free[q], (uint32_t)(j & 1)));
                     tc_fence_after();
                     issue_qk(q, sn);
                 }
             }
             for (int q = 0; q < ATT_QT; ++q) {
-                mbar_wait(&p_full[q], (uint32_t)(j & 1));
+                ATT_TIMED(tw_pfull, mbar_wait(&p_full[q], (uint32_t)(j & 1)));
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t aV = aKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < ATT_BN / 16; ++k) {
-                        const uint64_t ad = umma_desc_sw128(aP + q * 32768 + (k >> 2) * 16384 + (k & 3) * 32);
                         const uint64_t bd = umma_desc_sw128(aV + k * 2048, 1024, 1024);
-                        umma_f16(tmem + 256 + q * 64, ad, bd, idesc_pv, (j | k) ? 1u : 0u);   // O accumulates in TMEM across K/V tiles
+                        umma_f16_ts(tmem + 256 + q * 64, tmem + 384 + q * 64 + k * 8, bd, idesc_pv, (j | k) ? 1u : 0u);   // O accumulates in TMEM across K/V tiles
                     }
                     umma_commit(&o_full[q]);
                     if (q == ATT_QT - 1) umma_commit(&kv_empty[s]);
@@ -144,109 +175,149 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
             }
             s = sn; ph = phn;
         }
+        if (p.trace && lane == 0) {
+            long long* t = p.trace + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16;
+            t[0] = clock64() - t_begin; t[1] = tw_kv; t[2] = tw_sfree; t[3] = tw_pfull;
+        }
     } else if (warp >= 4) {
         // ===================== softmax / epilogue: warpgroup = Q tile, thread = row =====================
         const int q = (warp - 4) >> 2;
         const int wq = warp & 3;                          // TMEM lane quadrant of this warp
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr;
+        const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr, tP = tmem + 384 + q * 64 + lane_addr;
         float m_run = -INFINITY, l_run = 0.f;
         const float sl2 = p.scale_log2;
-        uint8_t* prow = sP + q * 32768 + row * 128;
-        const int sw = row & 7;
-        // exp2 of one 64-column half -> fp16 -> swizzled smem; returns the row sum of the half
-        // exp2 of one 64-column half -> fp16 -> swizzled smem; returns the row sum of the half.  FULL: no column masking.
-        auto exp_store = [&](const uint32_t (&r)[64], int hf, float mneg, int kv_left, auto full_c) -> float {
+        // exp2 of one 64-column half against the reference max folded into mneg -> packed fp16 in pp (the A operand layout of
+        // P V: two columns per 32-bit TMEM column); returns the row sum of the half.  FULL: no column masking.  WITH_MAX: also
+        // folds the raw scores into the four running-max accumulators mx[] (one FMNMX3 per column pair), so that the maximum
+        // search rides in the issue slots the MUFU-bound exponentials leave free.
+        auto exp_cols = [&](const uint32_t* r, int col0, float mneg, int kv_left, auto full_c, auto max_c, auto nu_c, uint32_t* pp, float (&mx)[4]) -> float {
             constexpr bool FULL = decltype(full_c)::value;
-            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-            uint8_t* base = prow + hf * 16384;
+            constexpr bool WITH_MAX = decltype(max_c)::value;
+            constexpr int NU = decltype(nu_c)::value;           // units of 8 columns: 8 (a 64-column half) or 4
+            f32x2 psa = 0ull, psb = 0ull;                       // four partial row sums as two packed accumulators (0 bits == +0.f pair)
+            const f32x2 sl22 = pack2(sl2, sl2), mneg2 = pack2(mneg, mneg);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {                       // 8 units of 8 columns (16 bytes of fp16)
-                uint32_t pk[4];
+            for (int u = 0; u < NU; ++u) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int c = u * 8 + 2 * i;
-                    // The MUFU unit (16 ex2 / clk / SM) is this kernel's limit: FIE_ATT_EMU of every 8 exponentials run on the
-                    // FMA / ALU pipes instead (Cody-Waite split + cubic, ~1e-4 relative: below the fp16 rounding of P).
-                    const float x0 = fmaf(__uint_as_float(r[c]), sl2, mneg), x1 = fmaf(__uint_as_float(r[c + 1]), sl2, mneg);
-                    float p0 = (2 * i >= 8 - FIE_ATT_EMU) ? ex2_emulated(x0) : ex2_approx(x0);
-                    float p1 = (2 * i + 1 >= 8 - FIE_ATT_EMU) ? ex2_emulated(x1) : ex2_approx(x1);
-                    if (!FULL) { if (hf * 64 + c >= kv_left) p0 = 0.f; if (hf * 64 + c + 1 >= kv_left) p1 = 0.f; }
-                    if (i & 1) { ps2 += p0; ps3 += p1; } else { ps0 += p0; ps1 += p1; }
+                    // The MUFU unit (16 ex2 / clk / SM) and the issue slots are this kernel's limits: FIE_ATT_EMU of every 8
+                    // exponentials run on the FMA / ALU pipes instead (Cody-Waite split + cubic, ~1e-4 relative: below the fp16
+                    // rounding of P), as packed column pairs.
+                    if (WITH_MAX) {
+                        if (FULL) mx[i] = fmaxf(fmaxf(mx[i], __uint_as_float(r[c])), __uint_as_float(r[c + 1]));
+                        else { if (col0 + c < kv_left) mx[i] = fmaxf(mx[i], __uint_as_float(r[c])); if (col0 + c + 1 < kv_left) mx[i] = fmaxf(mx[i], __uint_as_float(r[c + 1])); }
+                    }
+                    const f32x2 x2 = ffma2(pack2u(r[c], r[c + 1]), sl22, mneg2);
+                    float x0, x1, p0, p1;
+                    unpack2(x2, x0, x1);
+                    if (2 * i >= 8 - FIE_ATT_EMU) ex2_emulated2(pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f)), p0, p1);
+                    else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
+                    if (!FULL) { if (col0 + c >= kv_left) p0 = 0.f; if (col0 + c + 1 >= kv_left) p1 = 0.f; }
+                    if (i & 1) psb = fadd2(psb, pack2(p0, p1)); else psa = fadd2(psa, pack2(p0, p1));
                     __half2 h = __floats2half2_rn(p0, p1);
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                    pp[4 * u + i] = *reinterpret_cast<uint32_t*>(&h);
                 }
-                *reinterpret_cast<uint4*>(base + ((u ^ sw) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
-            return (ps0 + ps1) + (ps2 + ps3);
+            float s0, s1;
+            unpack2(fadd2(psa, psb), s0, s1);
+            return s0 + s1;
         };
-        auto half_max = [&](const uint32_t (&r)[64], int hf, int kv_left, bool full_tile) -> float {
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        auto half_max = [&](const uint32_t (&r)[64], int hf, int kv_left, bool full_tile, float (&mx)[4]) {
             if (full_tile) {
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(r[i])); mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(r[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+                for (int i = 0; i < 64; i += 8) {                      // 3-input max (FMNMX3): two columns per instruction
+                    mx[0] = fmaxf(fmaxf(mx[0], __uint_as_float(r[i])), __uint_as_float(r[i + 1])); mx[1] = fmaxf(fmaxf(mx[1], __uint_as_float(r[i + 2])), __uint_as_float(r[i + 3]));
+                    mx[2] = fmaxf(fmaxf(mx[2], __uint_as_float(r[i + 4])), __uint_as_float(r[i + 5])); mx[3] = fmaxf(fmaxf(mx[3], __uint_as_float(r[i + 6])), __uint_as_float(r[i + 7]));
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) if (hf * 64 + i < kv_left) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+                for (int i = 0; i < 64; ++i) if (hf * 64 + i < kv_left) mx[0] = fmaxf(mx[0], __uint_as_float(r[i]));
             }
-            return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         };
+        const std::true_type yes{}; const std::false_type no{};
+        const std::integral_constant<int, 8> n8{}; const std::integral_constant<int, 4> n4{};
+        long long tw_sfull = 0, tw_ofull = 0, tw_st = 0; const long long t_begin = p.trace ? clock64() : 0;
         for (int j = 0; j < n_tiles; ++j) {
-            mbar_wait(&s_full[q], (uint32_t)(j & 1));
+            ATT_TIMED(tw_sfull, mbar_wait(&s_full[q], (uint32_t)(j & 1)));
             tc_fence_after();
             const int kv_left = p.nkv - j * ATT_BN;     // valid columns in this tile
             const bool full_tile = kv_left >= ATT_BN;
-            float mx;
+            // Optimistic single pass: the exponentials of the first half are taken against the CURRENT reference max while the
+            // tile's row maximum is still being searched.  The reference only has to move when a row maximum outgrows it by more
+            // than 2^8 in the exponent domain (P = exp2((s - m_run) * scale) <= 256 still fits fp16, and O / l stays exact because
+            // both are accumulated against the same reference) -- after the first tile that is rare, and then the first half is
+            // simply redone.
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            uint32_t pp0[32];
+            float psum = 0.f;
             {
                 uint32_t ra[64];
                 tmem_ld_32x64(tS, ra);
                 tmem_ld_wait();
-                mx = fmaxf(m_run, half_max(ra, 0, kv_left, full_tile));
+                if (j == 0) half_max(ra, 0, kv_left, full_tile, mx4);
+                else if (full_tile) psum = exp_cols(ra, 0, -m_run * sl2, kv_left, yes, yes, n8, pp0, mx4);
+                else psum = exp_cols(ra, 0, -m_run * sl2, kv_left, no, yes, n8, pp0, mx4);
             }
             uint32_t rb[64];
             tmem_ld_32x64(tS + 64, rb);
             tmem_ld_wait();
-            mx = fmaxf(mx, half_max(rb, 1, kv_left, full_tile));
-            // Lazy rescale: the running reference max only moves when a row max grew by more than 2^8 in the exponent
-            // domain (or on the first tile); until then P = exp2((s - m_run) * scale) <= 256 still fits fp16 and the final
-            // O / l is exact because both were accumulated against the same reference.
+            half_max(rb, 1, kv_left, full_tile, mx4);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             const bool move = (j == 0) || ((mx - m_run) * sl2 > 8.0f);
-            const float alpha = move ? ex2_approx((m_run - mx) * sl2) : 1.0f;      // first tile: exp2(-inf) = 0
-            if (move) m_run = mx;
+            float alpha = 1.0f;
             if (j > 0) {
-                // P_q and O_q are free once PV(q, j-1) has completed; O_q lives in TMEM and is rescaled only when the
-                // reference max of some row of this warp moved (rare after the first tile)
-                mbar_wait(&o_full[q], (uint32_t)((j - 1) & 1));
+                // P_q and O_q are free once PV(q, j-1) has completed
+                ATT_TIMED(tw_ofull, mbar_wait(&o_full[q], (uint32_t)((j - 1) & 1)));
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, move)) {
-                    uint32_t ro[64];
-                    tmem_ld_32x64(tO, ro);
-                    tmem_ld_wait();
+            }
+            if (__any_sync(0xffffffffu, move)) {
+                // the reference max of some row of this warp moves (always on the first tile): rescale O_q, which lives in TMEM,
+                // by exp2(m_old - m_new), and (re)do the first half against the new reference
+                if (move) { alpha = ex2_approx((m_run - fmaxf(mx, m_run)) * sl2); m_run = fmaxf(mx, m_run); }      // first tile: exp2(-inf) = 0
+                // (32 columns at a time: this rare path must not raise the register pressure of the common one)
+                if (j > 0) {
+#pragma unroll 1
+                    for (int hq = 0; hq < 2; ++hq) {
+                        uint32_t ro[32];
+                        tmem_ld_32x32(tO + (uint32_t)(hq * 32), ro);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-                    tmem_st_32x64(tO, ro);
-                    tmem_st_wait();
+                        for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                        tmem_st_32x32(tO + (uint32_t)(hq * 32), ro);
+                    }
+                }
+                float dummy[4];
+                psum = 0.f;
+#pragma unroll
+                for (int hq = 0; hq < 2; ++hq) {
+                    uint32_t rq[32];
+                    tmem_ld_32x32(tS + (uint32_t)(hq * 32), rq);
+                    tmem_ld_wait();
+                    if (full_tile) psum += exp_cols(rq, hq * 32, -m_run * sl2, kv_left, yes, no, n4, pp0 + hq * 16, dummy);
+                    else psum += exp_cols(rq, hq * 32, -m_run * sl2, kv_left, no, no, n4, pp0 + hq * 16, dummy);
                 }
             }
-            const float mneg = -m_run * sl2;
-            float psum;
-            if (full_tile) psum = exp_store(rb, 1, mneg, kv_left, std::true_type{}); else psum = exp_store(rb, 1, mneg, kv_left, std::false_type{});
+            tmem_st_32x32(tP, pp0);
+            tc_fence_before();
+            mbar_arrive(&s_free[q]);                      // S_q has been consumed: Q_q K_{j+1}^T may be issued now
             {
-                uint32_t ra[64];
-                tmem_ld_32x64(tS, ra);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&s_free[q]);                  // S_q is in registers: Q_q K_{j+1}^T may be issued now
-                if (full_tile) psum += exp_store(ra, 0, mneg, kv_left, std::true_type{}); else psum += exp_store(ra, 0, mneg, kv_left, std::false_type{});
+                uint32_t pp1[32];
+                float dummy[4];
+                if (full_tile) psum += exp_cols(rb, 64, -m_run * sl2, kv_left, yes, no, n8, pp1, dummy);
+                else psum += exp_cols(rb, 64, -m_run * sl2, kv_left, no, no, n8, pp1, dummy);
+                tmem_st_32x32(tP + 32u, pp1);
             }
             l_run = l_run * alpha + psum;
-            fence_proxy_async_smem();
+            ATT_TIMED(tw_st, tmem_st_wait());
             tc_fence_before();
             mbar_arrive(&p_full[q]);
+        }
+        if (p.trace && wq == 0 && lane == 0) {
+            long long* t = p.trace + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + 4 + q * 4;
+            t[0] = clock64() - t_begin; t[1] = tw_sfull; t[2] = tw_ofull; t[3] = tw_st;
         }
         mbar_wait(&o_full[q], (uint32_t)((n_tiles - 1) & 1));
         tc_fence_after();
@@ -453,6 +524,11 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
 }  // namespace fie
 using namespace fie;
 
+static long long* g_att_trace = nullptr;
+// Debug: per-CTA [16] int64: [0] MMA warp total cycles, [1] blocked on K/V tiles, [2] on "S in registers", [3] on "P ready";
+// [4 + 4q ..]: softmax warpgroup q total, blocked on "S ready", on "P V done", on the TMEM store of P.  NULL switches it off.
+extern "C" void fie_attention_trace(long long* device_buf) { g_att_trace = device_buf; }
+
 static int attention_d64(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                          void* out, long long ldo, int b, int heads, int nq, int nkv, float scale, int causal, void* stream) {
     FIE_REQUIRE(q && k && v && out, "fie_attention_d64_f16: null pointer");
@@ -478,6 +554,7 @@ static int attention_d64(const void* q, long long ldq, const void* k, long long 
     p.out = (__half*)out; p.ldo = ldo; p.nq = nq; p.nkv = nkv;
     p.scale_log2 = scale * 1.4426950408889634f;
     p.causal = causal;
+    p.trace = g_att_trace;
     FIE_REQUIRE(!causal || nkv <= ATT_BN, "fie_attention_d64_causal_f16: nkv must be <= 128");
     static bool attr = false;
     if (!attr) {

@@ -142,6 +142,10 @@ void fie_tune_conv_halo(int enable, int max_cout);
  * accounting (see gemm_conv.cu); NULL switches it off.  Not needed in production. */
 void fie_gemm_trace(long long* device_buf);
 
+/* Debug hook: device buffer of 16 x int64 per CTA that subsequent self-attention launches (nkv > 128) fill with per-role
+ * wait-cycle accounting (see attention.cu); NULL switches it off.  Not needed in production. */
+void fie_attention_trace(long long* device_buf);
+
 /* A: fp16 [M, K] with row stride lda (elements, multiple of 8); optional second source A1 supplies
  * K columns [k_split, K) (k_split multiple of 64) — a virtual torch.cat along K.
  * B: fp16 [N, K] row-major (ldb = K).  D: [M, N_out] row stride ldd. */
