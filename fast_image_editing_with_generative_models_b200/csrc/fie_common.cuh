@@ -38,6 +38,37 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
     return 0.5f * x * (x < 0.0f ? q : 2.0f - q);
 }
 
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, new on sm_100): one issue slot for two elements.  Measured on B200
+// (scripts/micro/mufu_overlap.cu): a MUFU instruction keeps its SM sub-partition's issue port busy for ~8 cycles and other
+// warps' FMAs do not fill them, so element-wise code is bound by 8 x (MUFU count) + (other instructions) per element -- worth
+// halving the "other" part wherever values come in pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fadd2_rm(f32x2 a, f32x2 b) { f32x2 r; asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fsub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// SiLU of a pair: y / (1 + 2^(-y log2 e)) with ONE MUFU per element (ex2); the reciprocal is a bit-trick seed (12 % error)
+// refined by three packed Newton steps r <- r (2 - d r) (error^2 each: 1.4e-2, 2e-4, 4e-8) instead of a second MUFU.
+__device__ __forceinline__ void silu2(float& y0, float& y1) {
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(-1.4426950408889634f * y0, 126.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(-1.4426950408889634f * y1, 126.0f)));
+    const f32x2 d = fadd2(pack2(e0, e1), pack2(1.0f, 1.0f));
+    float d0, d1;
+    unpack2(d, d0, d1);
+    f32x2 r = pack2(__int_as_float(0x7EF311C7 - __float_as_int(d0)), __int_as_float(0x7EF311C7 - __float_as_int(d1)));
+    const f32x2 two = pack2(2.0f, 2.0f), nd = pack2(-d0, -d1);
+    r = fmul2(r, ffma2(nd, r, two));
+    r = fmul2(r, ffma2(nd, r, two));
+    r = fmul2(r, ffma2(nd, r, two));
+    unpack2(fmul2(pack2(y0, y1), r), y0, y1);
+}
+
 __device__ __forceinline__ float quick_gelu_f(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

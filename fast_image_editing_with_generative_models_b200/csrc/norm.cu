@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(512) k_gn_apply(GNArgs a) {
         for (int j = 0; j < 4; ++j) {
             float2 f = __half22float2(h[j]);
             float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]), y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
-            if (a.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+            if (a.silu) silu2(y0, y1);
             oh[j] = __floats2half2_rn(y0, y1);
         }
         return o;
