@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(512) k_gn_stats(GNArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(512) k_gn_apply(GNArgs a) {
+__global__ void __launch_bounds__(512, 2) k_gn_apply(GNArgs a) {
     const int img = blockIdx.y;
     const int v = threadIdx.x % a.cv, rsub = threadIdx.x / a.cv;
     if (rsub >= a.rows_in_flight) return;

@@ -14,13 +14,17 @@ echo "launches per step: $NL" &&
 timeout -k 10 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s $((3 * NL)) -c $NL --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"
-# full captures of the dominant kernels (inside the 4th step = the timed one)
+# full captures of the dominant kernels (inside the 4th step = the timed one); -s counts launches that match -k
+NG=$(python -c "import json,sys; print(json.loads(open('gpurun_out/plain_$TAG.log').read().strip().splitlines()[-1])['roofline']['launches_per_step'])")
 timeout -k 10 600 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:k_gemm_conv -s $((NL * 3 * 1317 / 2482 + 300)) -c 6 \
+timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:k_gemm_conv -s $((NG * 3 + 300)) -c 6 \
     -o gpurun_out/prof_gemm_$TAG -f $CMD > gpurun_out/ncu_gemm_$TAG.log 2>&1
 echo "ncu gemm rc=$?"
 timeout -k 10 600 $CMD > gpurun_out/plain3_$TAG.log 2>&1 &&
-timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:"k_attention|k_gn_apply|k_gn_stats|k_layernorm|k_nms|k_union" -s 2000 -c 10 \
-    -o gpurun_out/prof_attn_norm_$TAG -f $CMD > gpurun_out/ncu_attn_$TAG.log 2>&1
-echo "ncu attn/norm rc=$?"
+timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:'^k_attention_d64$' -s $((3 * 160 + 40)) -c 3 \
+    -o gpurun_out/prof_attn_$TAG -f $CMD > gpurun_out/ncu_attn_$TAG.log 2>&1
+echo "ncu attention rc=$?"
+timeout -k 10 1200 ncu --set full --clock-control none --import-source on -k regex:'k_gn_apply|k_gn_stats' -s $((3 * 300 + 20)) -c 6 \
+    -o gpurun_out/prof_norm_$TAG -f $CMD > gpurun_out/ncu_norm_$TAG.log 2>&1
+echo "ncu norm rc=$?"
 ls -la gpurun_out | tail -20
