@@ -242,7 +242,8 @@ def main():
     achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
     traffic, traffic_src, tensor_pct = None, None, None
     try:            # DRAM bytes per launch from the committed ncu --set full capture (profiles/); None if absent
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1c_gemm_traffic.json")))
+        import glob
+        tj = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))[-1]))   # latest committed capture
         traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
         tensor_pct = tj.get("tensor_pipe_active_pct_time_weighted")
     except Exception:
