@@ -39,6 +39,10 @@ def conv_case(nb, h, wd, cin, cout):
     return lambda: ops.conv3x3(x, w, col_bias=bias)
 
 kps1, kps2 = 2 | (1 << 2), 2 | (2 << 2)
+if len(sys.argv) > 1 and sys.argv[1] == "conv":          # python scripts/gemm_trace.py conv  -> the VAE / UNet convolution shapes only
+    for c in [(8, 1024, 1024, 128, 128), (8, 512, 512, 256, 256), (8, 256, 256, 512, 512), (16, 128, 128, 320, 320), (16, 64, 64, 640, 640), (16, 32, 32, 1280, 1280)]:
+        run(f"conv {c}", conv_case(*c), ((0, 0),))
+    sys.exit(0)
 for (m, n, k, mode) in [(16384, 1280, 1280, "plain"), (16384, 1280, 1280, "res"), (16384, 10240, 1280, "geglu"), (65536, 5120, 640, "geglu"),
                         (65536, 640, 640, "res"), (16384, 1280, 5120, "res"), (16384, 3840, 1280, "plain")]:
     run(f"gemm M{m} N{n} K{k} {mode}", gemm_case(m, n, k, mode), ((0, 0),))
