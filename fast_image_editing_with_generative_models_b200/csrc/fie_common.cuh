@@ -39,9 +39,8 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
 }
 
 // Packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2, new on sm_100): one issue slot for two elements.  Measured on B200
-// (scripts/micro/mufu_overlap.cu): a MUFU instruction keeps its SM sub-partition's issue port busy for ~8 cycles and other
-// warps' FMAs do not fill them, so element-wise code is bound by 8 x (MUFU count) + (other instructions) per element -- worth
-// halving the "other" part wherever values come in pairs.
+// (scripts/micro/mufu_mix.cu): a packed instruction occupies the FMA pipe for 2 cycles -- the FLOP rate of scalar fp32 -- so the
+// gain is in issue slots, which MUFU-heavy element-wise code (8 clk per MUFU warp instruction) is short of.
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
