@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
@@ -349,6 +350,7 @@ constexpr int ATT1_SMEM = ATT1_OFF_BAR + 256;
 
 __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_constant__ AttnParams p, int heads, int batch) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // persistent grid (<= 1 CTA per SM): the next kernel may start launching (see gemm_conv.cu)
     uint8_t* sQ = smem;                                   // buffer u: Q tiles at u * 32K
     uint8_t* sKV = smem + ATT1_OFF_KV;                    // buffer u: K at u * 32K, V at u * 32K + 16K
     uint8_t* sP = smem + ATT1_OFF_P;
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
@@ -550,6 +553,11 @@ static int attention_d64(const void* q, long long ldq, const void* k, long long 
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
         attr = true;
     }
+    static int pdl = -1;                                 // FIE_PDL=0: plain stream-ordered launches (see gemm_conv.cu)
+    if (pdl < 0) { const char* e = getenv("FIE_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
     static int kv1 = -1;
     if (kv1 < 0) { const char* e = getenv("FIE_ATT_KV1"); kv1 = e ? atoi(e) : 1; }
     if ((kv1 || causal) && nkv <= ATT_BN) {
@@ -563,11 +571,19 @@ static int attention_d64(const void* q, long long ldq, const void* k, long long 
         const long long items = (long long)b * heads * ((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM));
         int sms = 148; { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
         const int grid1 = (int)(items < sms ? items : sms);
-        k_attention_d64_kv1<<<grid1, 384, ATT1_SMEM, (cudaStream_t)stream>>>(p, heads, b);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid1); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = ATT1_SMEM; cfg.stream = (cudaStream_t)stream;
+        cfg.attrs = pdl_attr; cfg.numAttrs = pdl ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, k_attention_d64_kv1, p, heads, b);
+        if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_attention_d64_kv1): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
         return check_launch("fie_attention_d64_f16");
     }
     dim3 grid((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM), heads, b);
-    k_attention_d64<<<grid, 384, ATT_SMEM, (cudaStream_t)stream>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = ATT_SMEM; cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = pdl_attr; cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_attention_d64, p);
+    if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_attention_d64): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
     return check_launch("fie_attention_d64_f16");
 }
 

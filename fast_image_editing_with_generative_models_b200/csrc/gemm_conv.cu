@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     const bool leader = cta_rank == 0;
     const int first_tile = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
+    // Programmatic dependent launch: the whole (persistent, <= 1 CTA per SM) grid is resident from the start, so the next kernel
+    // in the stream may begin launching right away; its CTAs land on SMs as this grid's CTAs retire and run their own prologue
+    // (barrier init, TMEM allocation, descriptor prefetch) under this kernel's tail.  No-ops without the launch attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == W_PROD && lane == 0) {
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
         tma_prefetch_desc(&p.b_map);
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything below may read what the previous kernel wrote (and overwrite what it read)
     const uint32_t tmem_base = tmem_base_slot;
     long long tr_wait = 0, tr_wait2 = 0;
     const long long tr_start = p.trace ? clock64() : 0;
@@ -854,10 +859,14 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     const int grid = cg * (tiles < slots ? tiles : slots);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    static int pdl = -1;                               // FIE_PDL=0: plain stream-ordered launches
+    if (pdl < 0) { const char* e = getenv("FIE_PDL"); pdl = e ? atoi(e) : 1; }
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cg; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_gemm_conv): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
     return check_launch("k_gemm_conv");
