@@ -19,6 +19,7 @@ run gemm_epi tests/test_gpu_kernels.py -k "gemm_epilogue or folded_layernorm"
 run gemm_geglu tests/test_gpu_kernels.py -k "gemm_geglu"
 run conv tests/test_gpu_kernels.py -k "test_conv3x3 and not cin4"
 run attention tests/test_gpu_kernels.py -k "attention"
+run guards tests/test_gpu_kernels.py -k "writes_only or write_only"
 run engine tests/test_gpu_engine.py -s
 run fullsize tests/test_gpu_fullsize.py -s
 run dropin tests/test_gpu_dropin.py

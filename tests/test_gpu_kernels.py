@@ -458,3 +458,66 @@ def test_attention_fused_qkv_views(cuda_dev):
     q, k, v = [t.float().reshape(b, n, heads, 64).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
     ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b * n, c)
     assert float((out.float() - ref).abs().max()) < 4e-3
+
+
+# ------------------------------------------------------------------ guard bands (compute-sanitizer is not available on the GPU pool)
+def _guarded(rows, cols, ld, dev, lead=64, tail=64):
+    """A [rows, cols] view with row stride ld inside a sentinel-filled buffer; returns (view, checker)."""
+    buf = torch.full((lead + rows * ld + tail,), 1234.0, dtype=torch.float16, device=dev)
+    view = buf[lead:lead + rows * ld].view(rows, ld)[:, :cols]
+
+    def untouched():
+        pad = buf[lead:lead + rows * ld].view(rows, ld)[:, cols:]
+        return bool((buf[:lead] == 1234.0).all()) and bool((buf[lead + rows * ld:] == 1234.0).all()) and bool((pad == 1234.0).all())
+    return view, untouched
+
+
+@pytest.mark.parametrize("m,n,k", [(300, 96, 128), (1000, 352, 64), (257, 640, 320), (128, 1280, 1280)])
+def test_gemm_writes_only_its_output(cuda_dev, m, n, k):
+    """Ragged M / N with a strided output inside a sentinel-filled buffer: rows >= M, columns >= N and the row padding stay intact
+    (fast and slow epilogue paths, residual prefetch queue, LayerNorm statistics)."""
+    ops = _ops()
+    a = _rand((m, k), cuda_dev, 70).half()
+    w = (_rand((n, k), cuda_dev, 71) / math.sqrt(k)).half()
+    bias = _rand((n,), cuda_dev, 72)
+    res = _rand((m, n), cuda_dev, 73).half()
+    for ld in (n + 16, n + 8):
+        out, ok = _guarded(m, n, ld, cuda_dev)
+        st = torch.zeros((m + 8, 2), dtype=torch.int64, device=cuda_dev)
+        use_ln = n % 32 == 0 and ld % 16 == 0
+        ops.gemm(a, w, col_bias=bias, residual=res, out=out, ln_out=st[:m] if use_ln else None)
+        torch.cuda.synchronize()
+        assert ok(), (m, n, k, ld)
+        assert rel_err(out, a.float() @ w.float().t() + bias + res.float()) < 2e-3
+        assert int(st[m:].abs().sum()) == 0                              # statistics rows beyond M untouched
+        if use_ln:
+            assert float((st[:m, 0].double() / 2 ** 20 - out.float().double().sum(1)).abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("b,heads,nq,nkv", [(2, 3, 200, 333), (1, 2, 130, 77), (2, 2, 256, 256)])
+def test_attention_writes_only_its_output(cuda_dev, b, heads, nq, nkv):
+    ops = _ops()
+    c = heads * 64
+    q = _rand((b * nq, c), cuda_dev, 74).half(); k = _rand((b * nkv, c), cuda_dev, 75).half(); v = _rand((b * nkv, c), cuda_dev, 76).half()
+    out, ok = _guarded(b * nq, c, c + 64, cuda_dev)
+    ops.attention_d64(q, k, v, b, heads, nq, nkv, out=out)
+    torch.cuda.synchronize()
+    assert ok()
+    ref = ops.attention_d64(q, k, v, b, heads, nq, nkv)
+    assert torch.equal(out, ref)
+
+
+def test_conv_and_groupnorm_write_only_their_output(cuda_dev):
+    """Outputs carved out of one sentinel-filled arena, back to back: a kernel that overruns its tensor corrupts the neighbour's guard."""
+    ops = _ops()
+    from fast_image_editing_with_generative_models_b200.weights import pack_conv3x3
+    n, h, w_, cin, cout = 2, 24, 32, 64, 96
+    x = _rand((n, h, w_, cin), cuda_dev, 77).half()
+    wt = pack_conv3x3((_rand((cout, cin, 3, 3), cuda_dev, 78) / math.sqrt(9 * cin)).half())
+    arena = torch.full((64 + n * h * w_ * cout + 64,), 1234.0, dtype=torch.float16, device=cuda_dev)
+    out = arena[64:64 + n * h * w_ * cout].view(n, h, w_, cout)
+    ops.conv3x3(x, wt, out=out)
+    torch.cuda.synchronize()
+    assert bool((arena[:64] == 1234.0).all()) and bool((arena[-64:] == 1234.0).all())
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.view(cout, 3, 3, cin).permute(0, 3, 1, 2).float(), padding=1).permute(0, 2, 3, 1)
+    assert rel_err(out, ref) < 2e-3
