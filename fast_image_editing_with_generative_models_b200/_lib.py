@@ -20,7 +20,7 @@ class Epilogue(ctypes.Structure):
     _fields_ = [("col_bias", c_void_p), ("row_bias", c_void_p), ("rows_per_group", c_ll), ("ld_row_bias", c_ll), ("m_bias", c_void_p),
                 ("residual", c_void_p), ("ld_res", c_ll), ("scale", c_float), ("act", c_int), ("out_f32", c_int),
                 ("gn_stats", c_void_p), ("gn_groups", c_int), ("gn_rows_per_image", c_ll),
-                ("ln_stats_out", c_void_p), ("ln_stats_in", c_void_p), ("ln_eps", c_float), ("ln_dim", c_int)]
+                ("ln_stats_out", c_void_p), ("ln_stats_in", c_void_p), ("ln_eps", c_float), ("ln_dim", c_int), ("row_scale", c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/fie_b200.h declares
@@ -41,6 +41,7 @@ SIGNATURES = {
     "fie_sincos_embedding": (c_int, [ctypes.POINTER(c_float), c_int, c_int, c_void_p, c_void_p]),
     "fie_softmax_rows_f32_to_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_float, c_void_p]),
     "fie_softmax_rows_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_float, c_void_p]),
+    "fie_softmax_rows_exp_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_float, c_void_p]),
     "fie_groupnorm_f16": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_float, c_int, c_void_p, c_int, c_void_p]),
     "fie_layernorm_f16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "fie_geglu_block_n": (c_int, [c_int]),

@@ -127,6 +127,7 @@ template <> struct Vec4<__half> {
         return make_float4(a.x, a.y, b.x, b.y);
     }
 };
+__device__ __forceinline__ float ex2_f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float to_f(float v) { return v; }
 __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
 
@@ -177,6 +178,57 @@ __global__ void __launch_bounds__(256) k_softmax_rows_reg(const T* __restrict__ 
             *reinterpret_cast<uint2*>(orow + i) = u;
         }
     }
+}
+
+// exp-only form for fp16 scores (rows of at most 256 x 4 x NV columns): writes P' = exp2((s - rowmax) * scale * log2 e) <= 1 as fp16 and
+// 1 / sum(P') per row; the normalisation is applied exactly, in fp32, by the epilogue of the P V GEMM (fie_epilogue.row_scale).
+// The row stays in registers as packed fp16 (the maximum of fp16 values is exact in fp16), so the kernel needs half the registers
+// of the normalising form, one block reduction before the stores instead of two, and keeps four to five CTAs per SM in flight.
+template <int NV>
+__global__ void __launch_bounds__(256, 4) k_softmax_rows_exp(const __half* __restrict__ s, long long ld_in, __half* __restrict__ p, long long ld_out,
+                                                             float* __restrict__ inv_sum, int cols, float scale) {
+    __shared__ float red[8];
+    __shared__ float bc;
+    const __half* row = s + (long long)blockIdx.x * ld_in;
+    __half* orow = p + (long long)blockIdx.x * ld_out;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint2 v[NV];
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m2 = ninf;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = (k * 256 + tid) * 4;
+        if (i + 4 <= cols) v[k] = *reinterpret_cast<const uint2*>(row + i);
+        else { v[k].x = *reinterpret_cast<const uint32_t*>(&ninf); v[k].y = v[k].x; }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) m2 = __hmax2(m2, __hmax2(*reinterpret_cast<const __half2*>(&v[k].x), *reinterpret_cast<const __half2*>(&v[k].y)));
+    float mx = warp_max(fmaxf(__low2float(m2), __high2float(m2)));
+    if (lane == 0) red[wid] = mx;
+    __syncthreads();
+    if (tid == 0) { float m = red[0]; for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]); bc = m; }
+    __syncthreads();
+    mx = bc;
+    const float sl2 = scale * 1.4426950408889634f, off = -mx * sl2;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int i = (k * 256 + tid) * 4;
+        if (i + 4 <= cols) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v[k].x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v[k].y));
+            const __half2 pa = __floats2half2_rn(ex2_f(fmaf(a.x, sl2, off)), ex2_f(fmaf(a.y, sl2, off)));
+            const __half2 pb = __floats2half2_rn(ex2_f(fmaf(b.x, sl2, off)), ex2_f(fmaf(b.y, sl2, off)));
+            const float2 ra = __half22float2(pa), rb = __half22float2(pb);        // the row sum is the sum of what the GEMM will read
+            sum += (ra.x + ra.y) + (rb.x + rb.y);
+            uint2 u; u.x = *reinterpret_cast<const uint32_t*>(&pa); u.y = *reinterpret_cast<const uint32_t*>(&pb);
+            *reinterpret_cast<uint2*>(orow + i) = u;
+        }
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[wid] = sum;
+    __syncthreads();
+    if (tid == 0) { float t = 0; for (int i = 0; i < 8; ++i) t += red[i]; inv_sum[blockIdx.x] = 1.0f / t; }
 }
 
 template <typename T>
@@ -332,6 +384,12 @@ extern "C" int fie_softmax_rows_f16(const void* s, long long ld_in, void* p, lon
     if ((cols % 4) == 0 && cols <= 16384) k_softmax_rows_reg<__half, 16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)s, ld_in, (__half*)p, ld_out, cols, scale);
     else k_softmax_rows<__half><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)s, ld_in, (__half*)p, ld_out, cols, scale);
     return check_launch("fie_softmax_rows_f16");
+}
+extern "C" int fie_softmax_rows_exp_f16(const void* s, long long ld_in, void* p, long long ld_out, float* inv_sum, long long rows, int cols, float scale, void* stream) {
+    FIE_REQUIRE(s && p && inv_sum && rows > 0 && rows < (1ll << 31) && cols > 0 && (cols % 4) == 0 && cols <= 16384 && (ld_in % 4) == 0 && (ld_out % 4) == 0,
+                "fie_softmax_rows_exp_f16: bad args (cols must be a multiple of 4, <= 16384)");
+    k_softmax_rows_exp<16><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const __half*)s, ld_in, (__half*)p, ld_out, inv_sum, cols, scale);
+    return check_launch("fie_softmax_rows_exp_f16");
 }
 extern "C" int fie_vae_sample_add_noise(const void* moments, int ld_m, const void* xi, const void* noise, float* x_out_f32, void* x_out_f16,
                                         long long count_px, float scaling, float sqrt_a, float sqrt_1ma, void* stream) {

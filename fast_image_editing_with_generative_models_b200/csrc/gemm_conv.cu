@@ -90,6 +90,7 @@ struct GemmParams {
     const unsigned long long* ln_in;  // [M][2] statistics of the A rows, or NULL
     float ln_eps;
     double ln_inv;                  // 1 / (2^20 * length of the normalised A rows)
+    const float* row_scale;         // [M] optional per-row scale of the accumulator (exclusive with ln_in)
 };
 
 // Output row of accumulator row m (identity, or the strided scatter of one phase of the fused nearest-2x upsample).
@@ -485,7 +486,8 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
         // by this row's 1/sigma (a thread owns one row; its statistics are fetched with the next group's biases).
         const uint32_t bias_s = smem_u32(epi_smem) + (uint32_t)(warp - W_EPI0) * 1024u;
         float nb_col[4], nb_row[4], nb_gate[4];
-        const bool ln_on = p.ln_in != nullptr;
+        const bool ln_on = p.ln_in != nullptr, rs_on = p.row_scale != nullptr;
+        float nl_rs = 1.0f;                                    // next group's row scale
         unsigned long long nl_s = 0, nl_q = 0;                 // next group's row statistics
         float ln_rstd = 1.0f;                                  // this group's 1/sigma (1 when no LayerNorm is folded)
         float lo_s = 0.0f, lo_q = 0.0f;                        // p.ln_out: this thread's partial row sums over its chunks
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                 nl_s = nl_q = 0;
                 if (m_ < p.M) { nl_s = __ldg(p.ln_in + 2 * m_); nl_q = __ldg(p.ln_in + 2 * m_ + 1); }
             }
+            if (rs_on) { const long long m_ = mw_ + lane; nl_rs = m_ < p.M ? __ldg(p.row_scale + m_) : 1.0f; }
         };
         auto bias_commit = [&]() {
             if (!fast_cfg) return;
@@ -521,6 +524,7 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                 const double var = fma(-mean, mean, __ll2double_rn((long long)nl_q) * p.ln_inv);
                 ln_rstd = rsqrtf(fmaxf((float)var, 0.0f) + p.ln_eps);
             }
+            if (rs_on) ln_rstd = nl_rs;
             __syncwarp();
         };
         // GroupNorm statistics of the output (optional): per chunk slot, accumulated over this warp's tiles
@@ -779,7 +783,7 @@ static void pick_config(long long M, int N, bool geglu, int* cg_out, int* bn_out
 }
 
 static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int N, void* D, long long ldd) {
-    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0, nullptr, 0, 0, nullptr, nullptr, 0.0f, 0};
+    static const fie_epilogue kDefault = {nullptr, nullptr, 1, 0, nullptr, nullptr, 0, 1.0f, FIE_ACT_NONE, 0, nullptr, 0, 0, nullptr, nullptr, 0.0f, 0, nullptr};
     if (!ep) ep = &kDefault;
     p.D = D; p.ldd = ldd;
     p.col_bias = ep->col_bias; p.row_bias = ep->row_bias; p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
@@ -803,12 +807,14 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
     }
     p.ln_out = (unsigned long long*)ep->ln_stats_out; p.ln_in = (const unsigned long long*)ep->ln_stats_in;
     p.ln_eps = ep->ln_eps; p.ln_inv = ep->ln_dim > 0 ? 1.0 / (1048576.0 * (double)ep->ln_dim) : 0.0;
-    if (p.ln_out || p.ln_in) {
+    p.row_scale = ep->row_scale;
+    FIE_REQUIRE(!(p.row_scale && p.ln_in), "epilogue: row_scale and ln_stats_in are exclusive");
+    if (p.ln_out || p.ln_in || p.row_scale) {
         const int n_out = p.act == FIE_ACT_GEGLU ? N / 2 : N;
         FIE_REQUIRE(!p.out_f32 && (n_out % 32) == 0 && (N % 32) == 0 && (ldd % 16) == 0 && (reinterpret_cast<uintptr_t>(D) & 31) == 0 &&
                     (!p.residual || ((p.ld_res % 16) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 31) == 0)) &&
                     (!p.row_bias || (p.rows_per_group % 32) == 0),
-                    "epilogue: folded LayerNorm needs the fast epilogue path (fp16 output, N %% 32 == 0, 32-byte aligned rows)");
+                    "epilogue: folded LayerNorm / row_scale need the fast epilogue path (fp16 output, N %% 32 == 0, 32-byte aligned rows)");
         FIE_REQUIRE(!p.ln_in || (ep->ln_dim > 0 && p.ln_eps >= 0.0f && !p.row_bias && !p.m_bias), "epilogue: ln_stats_in needs ln_dim > 0, ln_eps >= 0 and no row / m bias");
         FIE_REQUIRE(!(p.ln_out && p.act == FIE_ACT_GEGLU), "epilogue: ln_stats_out is not supported with the GEGLU epilogue");
     }

@@ -397,6 +397,8 @@ class _VAEAttention:
     CHUNK = int(os.environ.get("FIE_VAE_CHUNK", "4096"))
     # fp16 scores (scaled in the GEMM epilogue, softmax in place): half the score traffic; measured parity unchanged (1.5e-2)
     F16_SCORES = os.environ.get("FIE_VAE_F16_SCORES", "1") == "1"
+    # softmax without its division: the P V GEMM scales its rows by 1 / rowsum in fp32 (FIE_VAE_DEFER_NORM=0: normalise in the softmax)
+    DEFER_NORM = os.environ.get("FIE_VAE_DEFER_NORM", "1") == "1"
 
     def __call__(self, x: Tensor, chunk: Optional[int] = None) -> Tensor:
         chunk = chunk or self.CHUNK
@@ -413,6 +415,11 @@ class _VAEAttention:
             o = torch.empty((ntok, c), dtype=torch.float16, device=x.device)
             for r0 in range(0, ntok, chunk):
                 r1 = min(r0 + chunk, ntok)
+                if self.F16_SCORES and self.DEFER_NORM and ntok % 4 == 0 and ntok <= 16384:
+                    s = ops.gemm(q[r0:r1], k, scale=scale)                     # [rows, ntok] fp16, already scaled
+                    p, inv = ops.softmax_rows_exp(s, 1.0, out=s)               # exp only, in place; 1 / rowsum on the side
+                    ops.gemm(p, vt, out=o[r0:r1], row_scale=inv)               # ... applied in fp32 by the P V epilogue
+                    continue
                 if self.F16_SCORES:
                     s = ops.gemm(q[r0:r1], k, scale=scale)                     # [rows, ntok] fp16, already scaled
                     p = ops.softmax_rows(s, 1.0, out=s)                        # in place

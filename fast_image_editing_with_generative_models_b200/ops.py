@@ -242,6 +242,19 @@ def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
     return out
 
 
+def softmax_rows_exp(s: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None):
+    """fp16 scores [rows, cols] -> (P' = exp(scale (s - rowmax)) fp16, 1 / rowsum fp32 [rows]); pass the latter as ``row_scale`` of the
+    P V GEMM.  In place when ``out is s``."""
+    _req(s, torch.float16, "softmax_rows_exp")
+    rows, cols = s.shape
+    out = torch.empty((rows, cols), dtype=torch.float16, device=s.device) if out is None else out
+    inv = torch.empty((rows,), dtype=torch.float32, device=s.device)
+    with _prof("softmax_rows", 4.0 * rows * cols, "B"):
+        check(_lib.lib().fie_softmax_rows_exp_f16(_p(s), s.stride(0), _p(out), out.stride(0), _p(inv), rows, cols, float(scale), _stream()), "fie_softmax_rows_exp_f16")
+    _count()
+    return out, inv
+
+
 def _gn_stats_ok(n_out: int, groups: int, rows_per_image: int, ldd: int) -> bool:
     """Can the GEMM epilogue accumulate the GroupNorm statistics of its output? (see fie_epilogue.gn_stats)"""
     if groups <= 0 or n_out % groups or n_out % 32 or ldd % 16 or rows_per_image % 32:
@@ -303,7 +316,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 
 def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False, gn=None,
-              ln_out=None, ln_in=None):
+              ln_out=None, ln_in=None, row_scale=None):
     ep = Epilogue()
     ep.col_bias = _p(col_bias); ep.row_bias = _p(row_bias); ep.rows_per_group = int(rows_per_group)
     ep.ld_row_bias = row_bias.stride(-2) if (row_bias is not None and row_bias.dim() >= 2) else 0
@@ -316,12 +329,15 @@ def _epilogue(col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, resid
         ep.ln_stats_out = _p(ln_out)
     if ln_in is not None:                   # (int64 [M, 2] statistics of the A rows, eps)
         ep.ln_stats_in = _p(ln_in[0]); ep.ln_eps = float(ln_in[1])
+    if row_scale is not None:
+        ep.row_scale = _p(row_scale)
     return ep
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, n_valid: Optional[int] = None,
          col_bias=None, row_bias=None, rows_per_group=1, m_bias=None, residual=None, scale=1.0, act=ACT_NONE, out_f32=False,
-         gn_groups: int = 0, gn_rows: int = 0, ln_out: Optional[torch.Tensor] = None, ln_in=None) -> torch.Tensor:
+         gn_groups: int = 0, gn_rows: int = 0, ln_out: Optional[torch.Tensor] = None, ln_in=None,
+         row_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = epilogue(A @ W^T).  a: [..., K] fp16 rows (row stride may exceed K), w: [N, K] fp16; optional a1 continues K.
     ln_out: zeroed int64 [M, 2] that receives the LayerNorm statistics of the output rows.  ln_in = (stats, eps): the A rows are
     layer-normalised on the fly (w / col_bias from weights.fold_layernorm)."""
@@ -349,7 +365,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a1: Optional[torch.Tensor] = None,
         raise _lib.FieError("gemm: ln_out must be a contiguous int64 [M, 2] tensor")
     if ln_in is not None and (ln_in[0].dtype != torch.int64 or ln_in[0].numel() != 2 * m or not ln_in[0].is_contiguous()):
         raise _lib.FieError("gemm: ln_in = (contiguous int64 [M, 2] statistics, eps)")
-    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32, gn, ln_out, ln_in)
+    if row_scale is not None and (row_scale.dtype != torch.float32 or row_scale.numel() != m or not row_scale.is_contiguous()):
+        raise _lib.FieError("gemm: row_scale must be a contiguous fp32 [M] tensor")
+    ep = _epilogue(col_bias, row_bias, rows_per_group, m_bias, residual, scale, act, out_f32, gn, ln_out, ln_in, row_scale)
     ep.ln_dim = k
     with _prof("gemm", 2.0 * m * n * k, "FLOP", f"M{m} N{n} K{k} act{act} res{int(residual is not None)} f32{int(out_f32)}"):
         check(_lib.lib().fie_gemm_f16(_p(a), lda, _p(a1), lda1, k_split, _p(w), _p(out), ldd, m, n, k, ctypes.byref(ep), _stream()), "fie_gemm_f16")

@@ -76,6 +76,10 @@ int fie_softmax_rows_f32_to_f16(const void* s_f32, long long ld_in, void* p_f16,
 /* the same with fp16 scores (already scaled by the producing GEMM's epilogue when scale = 1); may run in place (p = s) */
 int fie_softmax_rows_f16(const void* s_f16, long long ld_in, void* p_f16, long long ld_out,
                          long long rows, int cols, float scale, void* stream);
+/* The same softmax without its division: p = exp(scale * (s - rowmax)) <= 1 as fp16 and inv_sum[row] = 1 / sum(p) (of the
+ * fp16-rounded values); the P V GEMM applies inv_sum through fie_epilogue.row_scale.  cols % 4 == 0, cols <= 16384; in place allowed. */
+int fie_softmax_rows_exp_f16(const void* s_f16, long long ld_in, void* p_f16, long long ld_out, float* inv_sum,
+                             long long rows, int cols, float scale, void* stream);
 
 /* ---- GroupNorm(+SiLU), NHWC fp16: replaces F.group_norm (+F.silu) in ResnetBlock2D / Transformer2DModel ----
  * x0: [n, hw, c0]; optional x1: [n, hw, c1] is the channel-concatenated second source (torch.cat of the skip
@@ -124,6 +128,9 @@ typedef struct {
     const void* ln_stats_in;
     float ln_eps;
     int ln_dim;
+    /* Optional per-row scale applied to the accumulator before the biases: v = row_scale[m] * acc + bias ... (softmax
+     * normalisation of the VAE mid-block attention).  Exclusive with ln_stats_in; needs the fast epilogue path. */
+    const float* row_scale;
 } fie_epilogue;
 
 /* Accumulator tile width used for a GEGLU projection with N = 8C weight rows.  The host packs those rows per tile as

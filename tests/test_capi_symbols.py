@@ -38,8 +38,8 @@ def test_no_gpu_calls_needed_for_queries():
 
 def test_epilogue_struct_layout():
     # fie_epilogue: 7 x 8-byte fields + float + 2 ints = 68 -> 72; + gn_stats pointer, gn_groups int (+4 pad), gn_rows_per_image = 96;
-    # + ln_stats_out, ln_stats_in pointers, ln_eps float, ln_dim int = 120
-    assert ctypes.sizeof(_lib.Epilogue) == 120
+    # + ln_stats_out, ln_stats_in pointers, ln_eps float, ln_dim int = 120; + row_scale pointer = 128
+    assert ctypes.sizeof(_lib.Epilogue) == 128
 
 
 def test_product_does_not_import_oracle():

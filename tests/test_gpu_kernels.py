@@ -460,6 +460,27 @@ def test_attention_fused_qkv_views(cuda_dev):
     assert float((out.float() - ref).abs().max()) < 4e-3
 
 
+@pytest.mark.parametrize("rows,cols,d", [(300, 1016, 64), (512, 16384, 512), (100, 4096, 128)])
+def test_softmax_exp_with_row_scale_in_the_pv_gemm(cuda_dev, rows, cols, d):
+    """VAE mid-block attention path: exp-only softmax (unnormalised fp16 P', 1 / rowsum on the side) + P V GEMM with the row scale in
+    its epilogue == softmax(S) @ V."""
+    ops = _ops()
+    s = (_rand((rows, cols), cuda_dev, 85) * 3).half()
+    v = _rand((cols, d), cuda_dev, 86).half()
+    vt = v.t().contiguous()
+    p, inv = ops.softmax_rows_exp(s.clone(), 1.0)
+    assert float(p.float().max()) <= 1.0 and float(p.float().max(1).values.min()) == 1.0      # the row maximum maps to exactly 1
+    assert torch.allclose(inv, 1.0 / p.float().sum(1), rtol=1e-5)
+    out = ops.gemm(p, vt, row_scale=inv)
+    ref = torch.softmax(s.float(), dim=1) @ v.float()
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+    s2 = s.clone()
+    p2, inv2 = ops.softmax_rows_exp(s2, 1.0, out=s2)                                           # in place
+    assert torch.equal(p2, p) and torch.equal(inv2, inv)
+    old = ops.gemm(ops.softmax_rows(s.clone(), 1.0), vt)                                       # the normalising form it replaces
+    assert rel_err(out, ref) <= rel_err(old, ref) + 1e-4
+
+
 # ------------------------------------------------------------------ guard bands (compute-sanitizer is not available on the GPU pool)
 def _guarded(rows, cols, ld, dev, lead=64, tail=64):
     """A [rows, cols] view with row stride ld inside a sentinel-filled buffer; returns (view, checker)."""
