@@ -320,13 +320,17 @@ class UNet:
         return self.enc.prepare_prompt(ctx, text_embeds, time_ids)
 
     def forward(self, x: Tensor, t: float, prompt_state, down_res: Optional[List[Tensor]] = None, mid_res: Optional[Tensor] = None,
-                nctx: int = 77) -> Tensor:
-        """x [B,H,W,4] fp16 -> eps [B,H,W,4] fp16 (UNet2DConditionModel.forward with ControlNet residuals)."""
+                nctx: int = 77, merge=None) -> Tensor:
+        """x [B,H,W,4] fp16 -> eps [B,H,W,4] fp16 (UNet2DConditionModel.forward with ControlNet residuals).
+        The residuals come either as tensors (down_res, mid_res: added here) or through ``merge(skips, h) -> (skips, h)``
+        (ControlNet.merge_into: the zero-convolution GEMMs add this UNet's skip tensors in their epilogue -- no add kernels)."""
         ctx_kv, aug = prompt_state
         cfg = self.cfg
         temb = self.enc.time_rows(t, aug)
         h = ops.conv3x3_c8(ops.pad8(x), self.enc.conv_in[0], col_bias=self.enc.conv_in[1])
         h, skips = self.enc.down_mid(h, temb, ctx_kv, nctx)
+        if merge is not None:
+            skips, h = merge(skips, h)
         if down_res is not None:
             skips = [ops.add(s, r) for s, r in zip(skips, down_res)]
         if mid_res is not None:
@@ -380,6 +384,29 @@ class ControlNet:
         down = [ops.gemm(s, w, col_bias=b, scale=scale) for s, (w, b) in zip(skips, self.zero)]
         mid = ops.gemm(h, self.zero_mid[0], col_bias=self.zero_mid[1], scale=scale)
         return down, mid
+
+    def encode(self, x: Tensor, t: float, prompt_state, cond_emb: Tensor, nctx: int = 77):
+        """The ControlNet up to (not including) its zero convolutions -> (skip features, mid feature); see merge_into."""
+        ctx_kv, aug = prompt_state
+        temb = self.enc.time_rows(t, aug)
+        h = ops.conv3x3_c8(ops.pad8(x), self.enc.conv_in[0], col_bias=self.enc.conv_in[1], residual=cond_emb)
+        return self.enc.down_mid(h, temb, ctx_kv, nctx)
+
+    def merge_into(self, feats, scale: float):
+        """-> merge(unet_skips, unet_h): every zero convolution writes scale * (W f + b) + <the UNet tensor it is added to> in one
+        GEMM epilogue, i.e. `down_block_res_samples[i] + down_block_additional_residuals[i]` and the mid-block add of
+        UNet2DConditionModel.forward without separate element-wise kernels (and with one rounding instead of two)."""
+        cn_h, cn_skips = feats
+
+        def merge(skips, h):
+            n_, hh, ww, c_ = h.shape
+            merged = []
+            for f, (w, b), s in zip(cn_skips, self.zero, skips):
+                sh = s.shape
+                merged.append(ops.gemm(f.view(-1, f.shape[-1]), w, col_bias=b, scale=scale, residual=s.view(-1, sh[-1])).view(sh))
+            hm = ops.gemm(cn_h.view(-1, c_), self.zero_mid[0], col_bias=self.zero_mid[1], scale=scale, residual=h.view(-1, c_)).view(n_, hh, ww, c_)
+            return merged, hm
+        return merge
 
 
 class _VAEAttention:

@@ -128,9 +128,9 @@ class EditEngine:
         for k, t in enumerate(timesteps):
             ops.stage("controlnet_step")
             x2 = torch.cat([x] * nrow, 0) if do_cfg else x
-            down, mid = self.cn.forward(x2, float(t), ps_cn, cond_emb, controlnet_conditioning_scale, nctx)
+            feats = self.cn.encode(x2, float(t), ps_cn, cond_emb, nctx)
             ops.stage("unet_step")
-            eps = self.unet.forward(x2, float(t), ps_un, down, mid, nctx)
+            eps = self.unet.forward(x2, float(t), ps_un, nctx=nctx, merge=self.cn.merge_into(feats, controlnet_conditioning_scale))
             c = sched.step_coeffs(begin + k)
             z = None
             if not c["last"]:
