@@ -46,7 +46,9 @@ def unet_config_from_json(d: Dict, name: str = "unet") -> C.UNetConfig:
     down_types = d.get("down_block_types", ["CrossAttnDownBlock2D"] * len(ch))
     down = [tuple(tl[i]) if "CrossAttn" in t else () for i, t in enumerate(down_types)]
     mid_type = d.get("mid_block_type", "UNetMidBlock2DCrossAttn")
-    mid = None if mid_type in (None, "UNetMidBlock2D") else int(tl[-1][-1])
+    if mid_type is None:
+        raise ValueError("mid_block_type: null (a UNet without a mid block) is not supported")
+    mid = None if mid_type == "UNetMidBlock2D" else int(tl[-1][-1])
     up_types = d.get("up_block_types", ["CrossAttnUpBlock2D"] * len(ch))
     rev = d.get("reverse_transformer_layers_per_block")
     rtl = _per_block(rev, len(ch), lpb + 1) if rev is not None else [[b[-1]] * (lpb + 1) for b in reversed(tl)]
@@ -90,11 +92,13 @@ def lora_to_peft(sd: Dict[str, Tensor], param_names: Sequence[str]) -> Dict[str,
     """LCM-LoRA state dict (kohya or peft/diffusers keys) -> {param}.lora_A.weight / {param}.lora_B.weight, ``alpha / rank`` folded into B."""
     by_flat = {n[: -len(".weight")].replace(".", "_"): n[: -len(".weight")] for n in param_names if n.endswith(".weight")}
     out: Dict[str, Tensor] = {}
+    unmapped = []
     for k, v in sd.items():
         if k.endswith(".lora_down.weight") and k.startswith("lora_unet_"):              # kohya
             flat = k[len("lora_unet_"): -len(".lora_down.weight")]
             name = by_flat.get(flat)
             if name is None:
+                unmapped.append(k)
                 continue
             up = sd[k.replace("lora_down", "lora_up")].float()
             alpha = sd.get(k.replace("lora_down.weight", "alpha"))
@@ -106,7 +110,53 @@ def lora_to_peft(sd: Dict[str, Tensor], param_names: Sequence[str]) -> Dict[str,
             kb = k.replace(".lora_A", ".lora_B").replace(".lora.down", ".lora.up")
             if name + ".weight" in param_names or name in by_flat.values():
                 out[name + ".lora_A.weight"], out[name + ".lora_B.weight"] = v.float(), sd[kb].float()
+            else:
+                unmapped.append(k)
+    if unmapped:            # a silently skipped adapter layer would give a quietly different model
+        raise ValueError(f"LoRA: {len(unmapped)} adapter tensors do not match any UNet parameter (first: {unmapped[:3]})")
     return out
+
+
+def clip_config_from_json(d: Dict, name: str):
+    """transformers ``CLIPTextConfig`` JSON (``text_encoder/config.json``) -> :class:`text_encoder.CLIPTextConfig`."""
+    from .text_encoder import CLIPTextConfig
+    act = d.get("hidden_act", "quick_gelu")
+    if act not in ("quick_gelu", "gelu"):
+        raise ValueError(f"CLIP text encoder: unsupported hidden_act {act!r}")
+    with_proj = "WithProjection" in "".join(d.get("architectures") or [])
+    return CLIPTextConfig(name=name, vocab_size=d.get("vocab_size", 49408), hidden_size=d["hidden_size"], num_layers=d["num_hidden_layers"],
+                          num_heads=d["num_attention_heads"], intermediate_size=d["intermediate_size"],
+                          max_positions=d.get("max_position_embeddings", 77), hidden_act=act, layer_norm_eps=d.get("layer_norm_eps", 1e-5),
+                          projection_dim=d.get("projection_dim") if with_proj else None)
+
+
+def load_clip_dir(folder: str):
+    """``text_encoder`` / ``text_encoder_2`` folder of an SDXL pipeline (``config.json`` + ``model[.fp16].safetensors``, transformers
+    ``CLIPTextModel`` / ``CLIPTextModelWithProjection`` parameter names) -> (CLIPTextConfig, {name: fp32 CPU tensor})."""
+    from safetensors.torch import load_file
+    with open(os.path.join(folder, "config.json")) as f:
+        cfg = clip_config_from_json(json.load(f), os.path.basename(os.path.normpath(folder)))
+    for fn in ("model.fp16.safetensors", "model.safetensors"):
+        if os.path.exists(os.path.join(folder, fn)):
+            sd = {k: v.float() for k, v in load_file(os.path.join(folder, fn)).items() if "position_ids" not in k}
+            if cfg.projection_dim and "text_projection.weight" not in sd:
+                raise ValueError(f"{folder}: CLIPTextModelWithProjection checkpoint without text_projection.weight")
+            return cfg, sd
+    raise FileNotFoundError(f"no model[.fp16].safetensors in {folder}")
+
+
+def save_clip_dir(folder: str, cfg, params: Dict[str, Tensor], fp16: bool = True):
+    """Writes the layout :func:`load_clip_dir` reads (tests, exporting synthetic towers)."""
+    from safetensors.torch import save_file
+    os.makedirs(folder, exist_ok=True)
+    d = {"architectures": ["CLIPTextModelWithProjection" if cfg.projection_dim else "CLIPTextModel"], "vocab_size": cfg.vocab_size,
+         "hidden_size": cfg.hidden_size, "num_hidden_layers": cfg.num_layers, "num_attention_heads": cfg.num_heads,
+         "intermediate_size": cfg.intermediate_size, "max_position_embeddings": cfg.max_positions, "hidden_act": cfg.hidden_act,
+         "layer_norm_eps": cfg.layer_norm_eps, "projection_dim": cfg.projection_dim or cfg.hidden_size}
+    with open(os.path.join(folder, "config.json"), "w") as f:
+        json.dump(d, f, indent=1)
+    save_file({k: (v.half() if fp16 else v.float()).contiguous() for k, v in params.items()},
+              os.path.join(folder, "model.fp16.safetensors" if fp16 else "model.safetensors"))
 
 
 def load_state(unet_dir: str, controlnet_dir: str, vae_dir: str, lora_file: Optional[str] = None, lora_scale: float = 1.0) -> Dict:

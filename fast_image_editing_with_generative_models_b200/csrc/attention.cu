@@ -547,7 +547,8 @@ static int attention_d64(const void* q, long long ldq, const void* k, long long 
     p.causal = causal;
     p.trace = g_att_trace;
     FIE_REQUIRE(!causal || nkv <= ATT_BN, "fie_attention_d64_causal_f16: nkv must be <= 128");
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {false};               // cudaFuncSetAttribute is per device
+    bool& attr = attr_dev[current_device()];
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_attention_d64, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
@@ -562,14 +563,15 @@ static int attention_d64(const void* q, long long ldq, const void* k, long long 
     if (kv1 < 0) { const char* e = getenv("FIE_ATT_KV1"); kv1 = e ? atoi(e) : 1; }
     if ((kv1 || causal) && nkv <= ATT_BN) {
         // cross-attention: persistent CTAs over (batch, head, 256-row query block) items
-        static bool attr1 = false;
+        static bool attr1_dev[kMaxDevices] = {false};
+        bool& attr1 = attr1_dev[current_device()];
         if (!attr1) {
             cudaError_t e = cudaFuncSetAttribute(k_attention_d64_kv1, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM);
             if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64_kv1): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
             attr1 = true;
         }
         const long long items = (long long)b * heads * ((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM));
-        int sms = 148; { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+        const int sms = device_sm_count();
         const int grid1 = (int)(items < sms ? items : sms);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid1); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = ATT1_SMEM; cfg.stream = (cudaStream_t)stream;

@@ -17,6 +17,21 @@ int check_launch(const char* what) {
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return FIE_ERR_CUDA; }
     return FIE_OK;
 }
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+int device_sm_count() {
+    static int sms[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (!sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        sms[dev] = n;
+    }
+    return sms[dev];
+}
 }  // namespace fie
 
 extern "C" const char* fie_last_error(void) { return fie::g_err; }

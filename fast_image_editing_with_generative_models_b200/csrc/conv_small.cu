@@ -97,7 +97,8 @@ extern "C" int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float
     FIE_REQUIRE(groups <= 256, "fie_conv3x3_cin4_f16: ld_out too large");
     const size_t smem = (size_t)37 * groups * vec * sizeof(float);
     FIE_REQUIRE(smem <= 160 * 1024, "fie_conv3x3_cin4_f16: cout too large");
-    static bool attr = false;
+    static bool attr_dev[kMaxDevices] = {false};
+    bool& attr = attr_dev[current_device()];
     if (!attr) { cudaFuncSetAttribute(k_conv_cin4, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
     const long long nquads = (long long)n * h * ((w + CIN4_PX - 1) / CIN4_PX);
     const int qpb = 256 / groups;

@@ -19,6 +19,12 @@ int  check_launch(const char* what);   // returns FIE_OK or FIE_ERR_CUDA after c
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-device one-time state: cudaFuncSetAttribute and the SM count belong to a DEVICE, and one process may drive several GPUs
+// (FastEditor(device="cuda:1")), so every "done once" flag in this library is an array indexed by the current device.
+constexpr int kMaxDevices = 64;
+int current_device();        // cudaGetDevice, clamped to [0, kMaxDevices)
+int device_sm_count();       // multiprocessor count of the current device (cached per device)
+
 // x * sigmoid(x) with two MUFU ops (ex2, rcp); the IEEE division it replaces cost ~10 extra issue slots per element.
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // Exact (erf) GELU, 0.5 x (1 + erf(x / sqrt 2)), with erfc from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below

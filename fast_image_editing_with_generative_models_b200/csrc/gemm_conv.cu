@@ -738,11 +738,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     return FIE_OK;
 }
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (!g_num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev); if (g_num_sms <= 0) g_num_sms = 148; }
-    return g_num_sms;
-}
+static int num_sms() { return device_sm_count(); }
 
 // Tile configuration.  Measured on B200 (scripts/gemm_bench.py, scripts/gemm_dbg.py): the producer/consumer mbarrier
 // handshake costs ~300 ns per pipeline stage regardless of tile width, so the kernel runs 2 K-blocks per stage (KPS = 2)
@@ -851,7 +847,8 @@ static int launch(GemmParams& p, cudaStream_t stream) {
     static const KernelFn kernels[2][2][2][2] = {{{FIE_K(1, 1, 1), FIE_K(1, 1, 2)}, {FIE_K(1, 2, 1), FIE_K(1, 2, 2)}},
                                                  {{FIE_K(2, 1, 1), FIE_K(2, 1, 2)}, {FIE_K(2, 2, 1), FIE_K(2, 2, 2)}}};
 #undef FIE_K
-    static bool attr_set = false;
+    static bool attr_set_dev[kMaxDevices] = {false};          // cudaFuncSetAttribute is per device
+    bool& attr_set = attr_set_dev[current_device()];
     if (!attr_set) {
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int c = 0; c < 2; ++c) for (int d = 0; d < 2; ++d) {
             cudaError_t e = cudaFuncSetAttribute(kernels[a][b][c][d], cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + EPI_STAGE_BYTES + 1024);

@@ -12,7 +12,6 @@ namespace fie {
 
 // 2^-20 fixed point in a 64-bit two's-complement integer: exact, order-independent accumulation (|sum| < 2^43).
 __device__ __forceinline__ unsigned long long gn_fix(float v) { return (unsigned long long)__float2ll_rn(v * 1048576.0f); }
-__device__ __forceinline__ float gn_unfix(unsigned long long v) { return (float)((double)(long long)v * (1.0 / 1048576.0)); }
 
 struct GNArgs {
     const uint4* x0; const uint4* x1; uint4* out;
@@ -80,13 +79,17 @@ __global__ void __launch_bounds__(512, 2) k_gn_apply(GNArgs a) {
     const int v = threadIdx.x % a.cv, rsub = threadIdx.x / a.cv;
     if (rsub >= a.rows_in_flight) return;
     float ga[8], be[8], mu[8], rs[8];
-    const float inv_cnt = 1.0f / ((float)a.hw * (float)a.cpg);
+    // mean / variance in double from the exact integer sums: E[x^2] - mean^2 cancels badly in fp32 when |mean| >> sigma.
+    // A sum of squares that wrapped the 64-bit fixed-point range (group RMS beyond ~1450 over a 1024^2 x 4-channel group) shows up
+    // as a negative integer and is turned into NaN -- loud instead of silently wrong.
+    const double inv_cnt = 1.0 / ((double)a.hw * (double)a.cpg * 1048576.0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         int c = v * 8 + j, g = c / a.cpg;
-        const float sum = gn_unfix(a.stats[((long long)img * a.groups + g) * 2]), sq = gn_unfix(a.stats[((long long)img * a.groups + g) * 2 + 1]);
-        float mean = sum * inv_cnt, var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-        mu[j] = mean; rs[j] = rsqrtf(var + a.eps);
+        const long long isum = (long long)a.stats[((long long)img * a.groups + g) * 2], isq = (long long)a.stats[((long long)img * a.groups + g) * 2 + 1];
+        const double mean = (double)isum * inv_cnt;
+        const double var = fmax(fma(-mean, mean, (double)isq * inv_cnt), 0.0);
+        mu[j] = (float)mean; rs[j] = isq < 0 ? __int_as_float(0x7fc00000) : rsqrtf((float)var + a.eps);
         ga[j] = __ldg(a.gamma + c); be[j] = __ldg(a.beta + c);
     }
     const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(512, 2) k_gn_apply(GNArgs a) {
     // fold the affine transform: y = x * sc + sh
     float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = rs[j] * ga[j]; sh[j] = be[j] - mu[j] * sc[j]; }
+    for (int j = 0; j < 8; ++j) { sc[j] = rs[j] * ga[j]; sh[j] = fmaf(-mu[j], sc[j], be[j]); }
     auto apply = [&](const uint4& u) -> uint4 {
         uint4 o;
         const __half2* h = reinterpret_cast<const __half2*>(&u);

@@ -1,22 +1,28 @@
 """``FastEditor`` — drop-in mirror of the reference class (``src/pipeline.py:17-293``) on the B200 engine.
 
 Same constructor, ``edit`` / ``preprocess_image`` / ``clear_memory`` / ``get_memory_usage`` signatures, attributes
-(``model_name, device, dtype, config, controlnet, pipe``) and error behaviour (``ValueError`` for an unknown model,
-Python exceptions per image, usable after a failed call) as the reference; the arithmetic runs in the hand-written
-CUDA kernels behind ``include/fie_b200.h``.  Differences, all forced by the environment and stated in DESIGN.md:
+(``model_name, device, dtype, config, controlnet, pipe``) and error behaviour (``ValueError`` for an unknown model and for
+an invalid ``strength``, Python exceptions per image, usable after a failed call) as the reference; the arithmetic runs in
+the hand-written CUDA kernels behind ``include/fie_b200.h``.  One addition: :meth:`FastEditor.edit_many`, the batched form
+of ``edit`` (micro-batches of 8 images per GPU) that ``run_batch.py`` uses.
 
-* weights are seeded synthetic tensors of the named architectures (no checkpoints / network); a state dict can be
-  injected with ``state=``;
-* the two CLIP text encoders are outside the accelerated path: prompts are mapped to deterministic
-  synthetic embeddings (seeded by the prompt text) unless ``prompt_encoder`` is supplied;
-* compute is fp16 on the GPU (``use_full_precision`` is accepted and recorded but the kernels are fp16/fp32-accumulate);
-  ``enable_cpu_offload`` is a no-op on a 180 GB part.
+Differences, all forced by the environment and stated in DESIGN.md:
+
+* weights: ``checkpoints={...}`` (or the ``FIE_CHECKPOINTS`` / ``FIE_CONTROLNET`` / ``FIE_VAE`` / ``FIE_LCM_LORA`` environment
+  variables, or the CLIs' ``--checkpoints`` flags) loads diffusers folders incl. the two CLIP text encoders and tokenizers;
+  without them seeded synthetic tensors of the named architectures are generated and a loud warning is printed (there are
+  no checkpoints and no network in the build environment);
+* compute is fp16 with fp32 accumulation on the GPU.  ``use_full_precision=True`` is accepted and ``.dtype`` reports
+  ``torch.float32`` like the reference (callers only use it for naming), but the kernels stay fp16 and a warning says so;
+  ``.compute_dtype`` is always ``torch.float16``.  ``enable_cpu_offload`` is a no-op on a 180 GB part.
 """
 from __future__ import annotations
 
 import os
+import warnings
 import zlib
-from typing import Sequence, Callable, Dict, Optional
+from collections import OrderedDict
+from typing import Callable, Dict, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
@@ -24,6 +30,31 @@ from PIL import Image
 
 from . import model_zoo, ops
 from . import synthetic as S
+
+_ENV_KEYS = {"root": "FIE_CHECKPOINTS", "controlnet": "FIE_CONTROLNET", "vae": "FIE_VAE", "lora": "FIE_LCM_LORA"}
+
+
+def checkpoints_from_env() -> Optional[Dict[str, str]]:
+    """``FIE_CHECKPOINTS`` = a diffusers SDXL pipeline folder (``unet/ vae/ text_encoder/ text_encoder_2/ tokenizer/ tokenizer_2/``),
+    ``FIE_CONTROLNET`` = the ControlNet folder, optional ``FIE_VAE`` (fp16-fix VAE folder) and ``FIE_LCM_LORA`` (safetensors file)."""
+    root = os.environ.get(_ENV_KEYS["root"])
+    if not root:
+        return None
+    return expand_checkpoints(root, os.environ.get(_ENV_KEYS["controlnet"]), os.environ.get(_ENV_KEYS["vae"]), os.environ.get(_ENV_KEYS["lora"]))
+
+
+def expand_checkpoints(root: str, controlnet: Optional[str], vae: Optional[str] = None, lora: Optional[str] = None, unet: Optional[str] = None) -> Dict[str, str]:
+    """Pipeline folder + ControlNet folder -> the ``checkpoints`` dict of :class:`FastEditor`.  ``unet`` overrides ``root/unet``
+    (SSD-1B: the ``latent-consistency/lcm-ssd-1b`` UNet replaces the base one, reference ``src/pipeline.py:115-124``)."""
+    if not controlnet:
+        raise ValueError("a ControlNet checkpoint folder is required (FIE_CONTROLNET / --controlnet_dir)")
+    ck = {"unet": unet or os.path.join(root, "unet"), "controlnet": controlnet, "vae": vae or os.path.join(root, "vae")}
+    if lora:
+        ck["lora"] = lora
+    for k in ("text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2"):
+        if os.path.isdir(os.path.join(root, k)):
+            ck[k] = os.path.join(root, k)
+    return ck
 
 
 class _PipeShim:
@@ -54,6 +85,8 @@ class FastEditor:
             "description": "SSD-1B distilled (50% smaller, 60% faster, ~4GB VRAM)",
         },
     }
+    MICRO_BATCH = 8            # images per GPU per engine call in edit_many
+    OUT_SIZE = 1024            # the reference resizes every input to 1024 x 1024 (src/pipeline.py:251)
 
     def __init__(self, model_name="sdxl", device="cuda", dtype=torch.float16, enable_cpu_offload=True, use_full_precision=False,
                  use_full_controlnet=False, *, state: Optional[Dict] = None, prompt_encoder: Optional[Callable] = None, tiny: bool = False,
@@ -64,6 +97,7 @@ class FastEditor:
         self.model_name = model_name
         self.device = device
         self.dtype = torch.float32 if use_full_precision else dtype
+        self.compute_dtype = torch.float16
         self.enable_cpu_offload = enable_cpu_offload
         self.use_full_controlnet = use_full_controlnet
         self.config = self.MODEL_CONFIGS[model_name]
@@ -75,42 +109,83 @@ class FastEditor:
             raise RuntimeError("FastEditor (B200-native) needs a CUDA device; there is no CPU path")
         if not torch.cuda.is_available():
             raise RuntimeError("FastEditor (B200-native): no CUDA device available")
+        self._dev = torch.device(device)
+        if self._dev.index is None:
+            self._dev = torch.device("cuda", torch.cuda.current_device())
+        if use_full_precision:
+            warnings.warn("FastEditor(use_full_precision=True): the B200 kernels compute fp16 operands with fp32 accumulation; the "
+                          "reference's fp32 'quality mode' (src/pipeline.py:67-71) is NOT executed in fp32 here", RuntimeWarning, stacklevel=2)
         tiny = tiny or os.environ.get("FIE_TINY") == "1"     # small same-topology models: CLI smoke tests
+        if state is None and checkpoints is None:
+            checkpoints = checkpoints_from_env()
+        self.synthetic_weights = state is None and not checkpoints
         if state is None and checkpoints:
             # real weights: diffusers folders {unet, controlnet, vae} (+ optional LCM-LoRA file), see checkpoints.py
             from . import checkpoints as K
             self._say("[FastEditor] Loading checkpoints...")
             state = K.load_state(checkpoints["unet"], checkpoints["controlnet"], checkpoints["vae"], checkpoints.get("lora"))
         if state is None:
-            self._say("[FastEditor] Generating seeded synthetic weights (no checkpoints available offline)...")
+            warnings.warn("FastEditor: NO CHECKPOINTS given (checkpoints= / FIE_CHECKPOINTS): running on seeded SYNTHETIC random-init weights of "
+                          f"the {model_name} architecture — outputs are not meaningful edits", RuntimeWarning, stacklevel=2)
+            self._say("[FastEditor] WARNING: generating seeded synthetic weights (no checkpoints given) — outputs are NOT meaningful edits")
             state = model_zoo.synthetic_state(model_name, use_full_controlnet, tiny)
-        self._engine = model_zoo.build_engine(state, device)
+        with torch.cuda.device(self._dev):
+            self._engine = model_zoo.build_engine(state, self._dev)
         self._engine.use_graphs = True      # every edit has the same shapes: replay it as one CUDA graph after the first call
         self.controlnet = self._engine.cn
         self.pipe = _PipeShim(self._engine)
         self._prompt_encoder = prompt_encoder
+        self._prompt_cache: "OrderedDict" = OrderedDict()
         self._text = None
-        if text_encoders and prompt_encoder is None:
-            # the two CLIP text towers of encode_prompt on the same kernels (seeded random-init weights; the BPE
-            # tokenizer's vocabulary is not available offline, so prompts go through text_encoder.pseudo_token_ids)
+        self._tokenizers = None
+        ck_text = bool(checkpoints and "text_encoder" in checkpoints and "text_encoder_2" in checkpoints)
+        if (text_encoders or ck_text) and prompt_encoder is None:
+            # the two CLIP text towers of encode_prompt on the same kernels
             from . import text_encoder as T
             ucfg = self._engine.unet.cfg
-            c1, c2 = (T.tiny_clip_config(False, "quick_gelu"), T.tiny_clip_config(True, "gelu")) if tiny else (T.clip_l_config(), T.openclip_bigg_config())
+            if ck_text:
+                from . import checkpoints as K
+                self._say("[FastEditor] Loading the CLIP text encoders...")
+                c1, p1 = K.load_clip_dir(checkpoints["text_encoder"])
+                c2, p2 = K.load_clip_dir(checkpoints["text_encoder_2"])
+                tokenizers = tokenizers or ((checkpoints["tokenizer"], checkpoints["tokenizer_2"]) if "tokenizer" in checkpoints and "tokenizer_2" in checkpoints else None)
+            else:
+                c1, c2 = (T.tiny_clip_config(False, "quick_gelu"), T.tiny_clip_config(True, "gelu")) if tiny else (T.clip_l_config(), T.openclip_bigg_config())
+                self._say("[FastEditor] Building the CLIP text encoders (synthetic weights)...")
+                p1, p2 = T.make_clip_params(c1), T.make_clip_params(c2)
             pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
             if c1.hidden_size + c2.hidden_size != ucfg.cross_attention_dim or c2.projection_dim != pooled_dim:
                 raise ValueError("text encoder widths do not match the UNet's cross_attention_dim / pooled embedding size")
-            self._say("[FastEditor] Building the CLIP text encoders (synthetic weights)...")
-            self._text = T.SDXLTextEncoders(T.make_clip_params(c1), c1, T.make_clip_params(c2), c2, device)
+            with torch.cuda.device(self._dev):
+                self._text = T.SDXLTextEncoders(p1, c1, p2, c2, self._dev)
             self._text_vocab = c1.vocab_size
-            self._tokenizers = None
             if tokenizers:
                 # (tokenizer, tokenizer_2) folders with vocab.json + merges.txt: the real CLIP BPE (tokenizer.py)
                 from .tokenizer import CLIPBPETokenizer
                 self._tokenizers = (CLIPBPETokenizer.from_files(tokenizers[0]), CLIPBPETokenizer.from_files(tokenizers[1], pad_token="!"))
+            elif ck_text:
+                warnings.warn("FastEditor: text encoder checkpoints given without tokenizer folders; prompts are mapped to pseudo token ids", RuntimeWarning)
+        elif checkpoints and prompt_encoder is None:
+            warnings.warn("FastEditor: checkpoints without text_encoder / text_encoder_2 folders — prompts are mapped to seeded RANDOM "
+                          "embeddings (pass prompt_encoder= or add the CLIP folders)", RuntimeWarning, stacklevel=2)
         self._say("[FastEditor] Initialization complete!")
 
-    # ---- prompt -> embeddings (text encoders are not on the accelerated path) ----
+    # ---- prompt -> embeddings ----
     def _encode_prompt(self, prompt: str, negative_prompt: str):
+        """-> (prompt_embeds [2,77,D], pooled [2,P]) with row 0 = negative, row 1 = positive (the empty negative prompt is ENCODED,
+        as in the reference: it is passed explicitly, src/pipeline.py:263)."""
+        key = (prompt, negative_prompt)
+        hit = self._prompt_cache.get(key)
+        if hit is not None:
+            self._prompt_cache.move_to_end(key)
+            return hit
+        val = self._encode_prompt_uncached(prompt, negative_prompt)
+        self._prompt_cache[key] = val
+        while len(self._prompt_cache) > 64:
+            self._prompt_cache.popitem(last=False)
+        return val
+
+    def _encode_prompt_uncached(self, prompt: str, negative_prompt: str):
         ucfg = self._engine.unet.cfg
         if self._prompt_encoder is not None:
             return self._prompt_encoder(prompt, negative_prompt)
@@ -119,7 +194,7 @@ class FastEditor:
                 ids1, ids2 = (torch.tensor(t([negative_prompt, prompt]), dtype=torch.int64) for t in self._tokenizers)
                 return self._text.encode(ids1, ids2)
             from .text_encoder import pseudo_token_ids
-            ids = torch.stack([pseudo_token_ids(negative_prompt, self._text_vocab), pseudo_token_ids(prompt, self._text_vocab)])   # the empty negative prompt is ENCODED, as in the reference
+            ids = torch.stack([pseudo_token_ids(negative_prompt, self._text_vocab), pseudo_token_ids(prompt, self._text_vocab)])
             return self._text.encode(ids, ids)          # ([neg, pos] x 77 x 2048, [neg, pos] x 1280)
         pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
         pos = S.synthetic_prompt(zlib.crc32(prompt.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)
@@ -133,38 +208,144 @@ class FastEditor:
             raise ValueError("preprocess_image expects an 8-bit RGB or gray image")
         if image_np.ndim == 3 and image_np.shape[2] != 3:
             image_np = np.ascontiguousarray(image_np[..., :3])
-        d = torch.from_numpy(image_np[None]).to(self.device)
-        edges = ops.canny(d, int(np.floor(low_threshold)), int(np.floor(high_threshold)), out_channels=3)
-        return Image.fromarray(edges[0].cpu().numpy())
+        with torch.cuda.device(self._dev):
+            d = torch.from_numpy(image_np[None]).to(self._dev)
+            edges = ops.canny(d, int(np.floor(low_threshold)), int(np.floor(high_threshold)), out_channels=3)
+            return Image.fromarray(edges[0].cpu().numpy())
 
-    def edit(self, image, prompt, negative_prompt="", strength=0.80, num_inference_steps=4, guidance_scale=1.5,
-             controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200, seed=None):
-        """Edit an image with a text prompt, preserving structure via Canny conditioning -> PIL RGB 1024x1024."""
-        gen = torch.Generator(device=self.device)
+    # ---- argument checks shared by edit / edit_many (diffusers img2img check_inputs + get_timesteps) ----
+    @staticmethod
+    def _executed_steps(strength: float, num_inference_steps: int) -> int:
+        if strength < 0 or strength > 1:
+            raise ValueError(f"The value of strength should in [0.0, 1.0] but is {strength}")
+        if not isinstance(num_inference_steps, int) or num_inference_steps <= 0:
+            raise ValueError(f"`num_inference_steps` has to be a positive integer but is {num_inference_steps}")
+        n_exec = min(int(num_inference_steps * strength), num_inference_steps)
+        if n_exec < 1:
+            raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number of pipeline steps is "
+                             f"{n_exec} which is < 1 and not appropriate for this pipeline.")
+        return n_exec
+
+    def _draw_noises(self, seed, n_exec: int) -> List[torch.Tensor]:
+        """Reference RNG order for one image: posterior sample, init noise, then one draw per non-final executed step."""
+        gen = torch.Generator(device=self._dev)
         if seed is not None:
             gen.manual_seed(int(seed))
         else:
             gen.seed()
-        # image.resize((1024, 1024), Image.LANCZOS) of the reference (src/pipeline.py:251) on the GPU, bit-identical to Pillow
+        h = self.OUT_SIZE // 8
+        return [torch.randn((1, 4, h, h), generator=gen, device=self._dev, dtype=torch.float16) for _ in range(2 + max(n_exec - 1, 0))]
+
+    def _to_device_1024(self, image) -> torch.Tensor:
+        """PIL image of any size -> uint8 [1,1024,1024,3] on the GPU; ``image.resize((1024, 1024), Image.LANCZOS)`` of the reference
+        (src/pipeline.py:251) runs on the GPU, bit-identical to Pillow."""
         arr = np.ascontiguousarray(np.array(image.convert("RGB")))
-        img = torch.from_numpy(arr[None]).to(self.device)
-        if img.shape[1] != 1024 or img.shape[2] != 1024:
-            img = ops.resize_lanczos(img, 1024, 1024)
-        pe, pl = self._encode_prompt(prompt, negative_prompt)
-        n_exec = min(int(num_inference_steps * strength), num_inference_steps)
-        # reference RNG order: posterior sample, init noise, then one draw per non-final executed step
-        noises = [torch.randn((1, 4, 128, 128), generator=gen, device=self.device, dtype=torch.float16) for _ in range(2 + max(n_exec - 1, 0))]
-        out = self._engine.edit_batch(img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
-                                      guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
-                                      canny_low=int(np.floor(canny_low_threshold)), canny_high=int(np.floor(canny_high_threshold)))
-        return Image.fromarray(out.images[0].cpu().numpy())
+        img = torch.from_numpy(arr[None]).to(self._dev, non_blocking=True)
+        if img.shape[1] != self.OUT_SIZE or img.shape[2] != self.OUT_SIZE:
+            img = ops.resize_lanczos(img, self.OUT_SIZE, self.OUT_SIZE)
+        return img
+
+    def edit(self, image, prompt, negative_prompt="", strength=0.80, num_inference_steps=4, guidance_scale=1.5,
+             controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200, seed=None):
+        """Edit an image with a text prompt, preserving structure via Canny conditioning -> PIL RGB 1024x1024."""
+        n_exec = self._executed_steps(strength, num_inference_steps)
+        with torch.cuda.device(self._dev):
+            img = self._to_device_1024(image)
+            pe, pl = self._encode_prompt(prompt, negative_prompt)
+            noises = self._draw_noises(seed, n_exec)
+            out = self._engine.edit_batch(img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
+                                          guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
+                                          canny_low=int(np.floor(canny_low_threshold)), canny_high=int(np.floor(canny_high_threshold)))
+            return Image.fromarray(out.images[0].cpu().numpy())
+
+    def edit_many(self, images: Sequence, prompts: Union[str, Sequence[str]], negative_prompt: Union[str, Sequence[str]] = "", strength=0.80,
+                  num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200,
+                  seed=None, seeds: Optional[Sequence[Optional[int]]] = None, micro_batch: Optional[int] = None) -> List[Image.Image]:
+        """Batched ``edit``: ``[edit(images[i], prompts[i], ..., seed=seeds[i]) for i]`` — same per-image semantics (each image gets its
+        own generator seeded with ``seeds[i]``, or ``seed`` for all, drawing in the reference's order; the results are the ones the
+        per-image calls give) but run in micro-batches of ``micro_batch`` (default 8) images per engine call.
+
+        The host side is pipelined: while the GPU runs micro-batch *i* (one CUDA-graph replay), the host converts the outputs of
+        micro-batch *i-1* to PIL images and stages the inputs of *i+1* (pinned buffers, asynchronous copies)."""
+        n = len(images)
+        if isinstance(prompts, str):
+            prompts = [prompts] * n
+        negs = [negative_prompt] * n if isinstance(negative_prompt, str) else list(negative_prompt)
+        if len(prompts) != n or len(negs) != n:
+            raise ValueError("edit_many: images, prompts (and negative prompts) must have the same length")
+        if seeds is None:
+            seeds = [seed] * n
+        if len(seeds) != n:
+            raise ValueError("edit_many: seeds must have one entry per image")
+        n_exec = self._executed_steps(strength, num_inference_steps)
+        mb = int(micro_batch or self.MICRO_BATCH)
+        lo, hi = int(np.floor(canny_low_threshold)), int(np.floor(canny_high_threshold))
+        S_ = self.OUT_SIZE
+        results: List[Optional[Image.Image]] = [None] * n
+        pending = None                                   # (index list, pinned output buffer, event) of the micro-batch in flight
+        with torch.cuda.device(self._dev):
+            stream = torch.cuda.current_stream(self._dev)
+            bufs = self._host_buffers(mb)
+
+            def finalize(p):
+                idx, host_out, ev = p
+                ev.synchronize()
+                for j, i in enumerate(idx):
+                    results[i] = Image.fromarray(host_out[j].numpy().copy())
+
+            for k, b0 in enumerate(range(0, n, mb)):
+                idx = list(range(b0, min(b0 + mb, n)))
+                nb = len(idx)
+                pad_to = mb if nb * 2 >= mb else 1 << (nb - 1).bit_length()       # ragged tail: reuse the full-size graph, or the next power of two
+                host_in, host_out = bufs[k & 1]
+                same = all(images[i].size == (S_, S_) for i in idx)
+                if same:
+                    for j, i in enumerate(idx):
+                        host_in[j].copy_(torch.from_numpy(np.array(images[i].convert("RGB"))))
+                    for j in range(nb, pad_to):
+                        host_in[j].copy_(host_in[nb - 1])
+                    d_img = host_in[:pad_to].to(self._dev, non_blocking=True)
+                else:
+                    parts = [self._to_device_1024(images[i]) for i in idx]
+                    d_img = torch.cat(parts + [parts[-1]] * (pad_to - nb), 0)
+                enc = [self._encode_prompt(prompts[i], negs[i]) for i in idx]
+                enc += [enc[-1]] * (pad_to - nb)
+                pe = torch.stack([e[0].to(self._dev, torch.float16) for e in enc])      # [B,2,77,D]
+                pl = torch.stack([e[1].to(self._dev, torch.float16) for e in enc])      # [B,2,P]
+                per_img = [self._draw_noises(seeds[i], n_exec) for i in idx]
+                per_img += [per_img[-1]] * (pad_to - nb)
+                noises = [torch.cat([p[d] for p in per_img], 0) for d in range(len(per_img[0]))]
+                out = self._engine.edit_batch(d_img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
+                                              guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
+                                              canny_low=lo, canny_high=hi)
+                host_out[:nb].copy_(out.images[:nb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                if pending is not None:
+                    finalize(pending)                    # host work of the previous micro-batch overlaps this one's GPU time
+                pending = (idx, host_out, ev)
+            if pending is not None:
+                finalize(pending)
+        return results  # type: ignore[return-value]
+
+    def _host_buffers(self, mb: int):
+        """Two (input, output) pairs of pinned uint8 staging buffers [mb,1024,1024,3] (allocated once per micro-batch size)."""
+        cache = self.__dict__.setdefault("_pinned", {})
+        if mb not in cache:
+            S_ = self.OUT_SIZE
+            cache[mb] = [(torch.empty((mb, S_, S_, 3), dtype=torch.uint8).pin_memory(), torch.empty((mb, S_, S_, 3), dtype=torch.uint8).pin_memory())
+                         for _ in range(2)]
+        return cache[mb]
 
     def clear_memory(self):
-        """Clear GPU memory cache."""
+        """Clear GPU memory cache (reference ``src/pipeline.py:276-279``).  Also drops every captured CUDA graph except the most
+        recently used one (each holds a private memory pool), so a parameter sweep cannot grow memory without bound."""
         if str(self.device).startswith("cuda"):
-            torch.cuda.empty_cache()
+            self._engine.release_graphs(keep=1)
+            with torch.cuda.device(self._dev):
+                torch.cuda.empty_cache()
 
     def get_memory_usage(self):
         if str(self.device).startswith("cuda"):
-            return {"allocated_gb": torch.cuda.memory_allocated() / 1024 ** 3, "reserved_gb": torch.cuda.memory_reserved() / 1024 ** 3}
+            return {"allocated_gb": torch.cuda.memory_allocated(self._dev) / 1024 ** 3, "reserved_gb": torch.cuda.memory_reserved(self._dev) / 1024 ** 3}
         return {"allocated_gb": 0, "reserved_gb": 0}

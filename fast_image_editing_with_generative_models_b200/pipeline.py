@@ -2,6 +2,8 @@
 does for the reference at ``src/pipeline.py:261-272`` (order per SURVEY Appendix A.1), batched over images."""
 from __future__ import annotations
 
+import os
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -17,6 +19,9 @@ Tensor = torch.Tensor
 
 @dataclass
 class EditOutput:
+    """Results of one engine call.  With ``use_graph`` the tensors ALIAS the CUDA graph's static output buffers: they are valid
+    until the next ``edit_batch`` call with the same (shapes, arguments) key, which overwrites them in stream order — copy them
+    (``.cpu()``, ``.clone()``, an asynchronous D2H copy enqueued before the next call) if they must outlive it."""
     images: Tensor                      # uint8 [B,H,W,3] on the device
     edges: Tensor                       # uint8 [B,H,W,3] Canny control image
     latents: Optional[Tensor] = None    # fp32 [B,h,w,4] final latents (the scheduler state; the VAE decodes its fp16 copy)
@@ -37,7 +42,16 @@ class EditEngine:
             self.vae = VAE(vae_params, vae_cfg, self.dev)
         self.sched = LCMSchedule()
         self.use_graphs = False           # opt-in: replay each edit as one CUDA graph (see edit_batch)
-        self._graphs: Dict = {}
+        # captured graphs, least recently used first.  Every distinct (shapes, strength, guidance, thresholds, ...) key owns a
+        # private multi-GB memory pool, so the cache is a small LRU (FIE_GRAPH_CACHE, default 4) and clear_memory() trims it.
+        self._graphs: "OrderedDict" = OrderedDict()
+        self.max_graphs = max(int(os.environ.get("FIE_GRAPH_CACHE", "4")), 1)
+
+    def release_graphs(self, keep: int = 0):
+        """Drop captured CUDA graphs (and their private memory pools), keeping the ``keep`` most recently used."""
+        while len(self._graphs) > max(keep, 0):
+            _, g = self._graphs.popitem(last=False)
+            g.clear()
 
     @torch.no_grad()
     def edit_batch(self, images_u8: Tensor, prompt_embeds: Tensor, pooled: Tensor, noises: Sequence[Tensor], strength: float = 0.5,
@@ -51,7 +65,18 @@ class EditEngine:
         ``use_graph`` (default: ``self.use_graphs``): replay the whole edit — ~2500 kernel launches — as ONE CUDA graph
         captured on first use for this (shapes, schedule) key; inputs are copied into the graph's static buffers and the
         returned tensors are the graph's static outputs (valid until the next call with the same key)."""
+        with torch.cuda.device(self.dev):           # kernels launch on the CURRENT device's stream: make that this engine's device
+            return self._edit_batch(images_u8, prompt_embeds, pooled, noises, strength, num_inference_steps, guidance_scale,
+                                    controlnet_conditioning_scale, canny_low, canny_high, return_latents, return_extras, use_graph)
+
+    def _edit_batch(self, images_u8, prompt_embeds, pooled, noises, strength, num_inference_steps, guidance_scale, controlnet_conditioning_scale,
+                    canny_low, canny_high, return_latents, return_extras, use_graph) -> EditOutput:
         dev = self.dev
+        if strength < 0 or strength > 1:
+            raise ValueError(f"The value of strength should in [0.0, 1.0] but is {strength}")
+        if min(int(num_inference_steps * strength), num_inference_steps) < 1:       # diffusers: get_timesteps leaves no step to run
+            raise ValueError(f"After adjusting the num_inference_steps by strength parameter: {strength}, the number of pipeline steps is 0 "
+                             "which is < 1 and not appropriate for this pipeline.")
         nz = [n.to(dev, torch.float16).permute(0, 2, 3, 1).contiguous() for n in noises]
         pe = prompt_embeds.to(dev, torch.float16)
         pl = pooled.to(dev, torch.float16)
@@ -64,7 +89,10 @@ class EditEngine:
         key = (tuple(images_u8.shape), tuple(pe.shape), tuple(pl.shape), len(nz), tuple(sorted(args.items())))
         g = self._graphs.get(key)
         if g is None:
+            self.release_graphs(keep=self.max_graphs - 1)
             g = self._capture(key, images_u8, pe, pl, nz, args)
+        else:
+            self._graphs.move_to_end(key)
         g["img"].copy_(images_u8); g["pe"].copy_(pe); g["pl"].copy_(pl)
         for d, s_ in zip(g["nz"], nz):
             d.copy_(s_)
@@ -109,7 +137,7 @@ class EditEngine:
         # ---- VAE encode -> posterior sample -> scale -> add_noise ----
         ops.stage("vae_encode")
         moments = self.vae.encode_moments(ops.preprocess_pad8(images_u8, normalize=True))
-        sa, s1 = sched.add_noise_coeffs(timesteps[0]) if timesteps else (1.0, 0.0)
+        sa, s1 = sched.add_noise_coeffs(timesteps[0])
         x32, x = ops.vae_sample_add_noise(moments, nz[0], nz[1], self.vae.cfg.scaling_factor, sa, s1)    # fp32 state, fp16 copy
         # ---- prompt conditioning (step-invariant): rows [neg]*B + [pos]*B as diffusers ----
         ops.stage("prompt_kv")

@@ -57,7 +57,28 @@ def build_parser():
     p.add_argument("--full_controlnet", action="store_true")
     p.add_argument("--skip_existing", action="store_true")
     p.add_argument("--save_comparisons", action="store_true")
+    # extensions of the B200 build
+    p.add_argument("--micro_batch", type=int, default=8, help="images per GPU per engine call (FastEditor.edit_many)")
+    p.add_argument("--io_threads", type=int, default=4, help="host threads for JPEG decode / encode")
+    add_checkpoint_args(p)
     return p
+
+
+def add_checkpoint_args(p):
+    """Real-weight folders (extension; the reference downloads from the HF hub, src/pipeline.py:89-154).  Defaults come from the
+    FIE_CHECKPOINTS / FIE_CONTROLNET / FIE_VAE / FIE_LCM_LORA environment variables; without any, synthetic weights + a warning."""
+    p.add_argument("--checkpoints", type=str, default=None, help="diffusers SDXL / SSD-1B pipeline folder (unet/ vae/ text_encoder*/ tokenizer*/)")
+    p.add_argument("--controlnet_dir", type=str, default=None, help="ControlNet-Canny folder (config.json + safetensors)")
+    p.add_argument("--vae_dir", type=str, default=None, help="VAE folder (e.g. sdxl-vae-fp16-fix); default <checkpoints>/vae")
+    p.add_argument("--unet_dir", type=str, default=None, help="UNet folder override (SSD-1B: the lcm-ssd-1b UNet)")
+    p.add_argument("--lcm_lora", type=str, default=None, help="LCM-LoRA safetensors file (SDXL)")
+
+
+def checkpoints_from_args(args):
+    from fast_image_editing_with_generative_models_b200.editor import expand_checkpoints
+    if not args.checkpoints:
+        return None           # FastEditor then consults the environment variables
+    return expand_checkpoints(args.checkpoints, args.controlnet_dir, args.vae_dir, args.lcm_lora, args.unet_dir)
 
 
 def select_entries(mapping, args):
@@ -94,17 +115,15 @@ def main(argv=None):
     say(f"\n[3/3] Initializing FastEditor ({model_suffix})...")
     device = f"cuda:{local}" if world > 1 else "cuda"
     editor = FastEditor(model_name=args.model, device=device, enable_cpu_offload=not args.no_cpu_offload,
-                        use_full_precision=args.full_precision, use_full_controlnet=args.full_controlnet, verbose=rank == 0)
+                        use_full_precision=args.full_precision, use_full_controlnet=args.full_controlnet, verbose=rank == 0,
+                        checkpoints=checkpoints_from_args(args))
     if hasattr(editor, "pipe"):
         editor.pipe.set_progress_bar_config(disable=True)
     processed = skipped = failed = 0
     total_time = 0.0
-    try:
-        from tqdm import tqdm
-        it = tqdm(mine, desc=f"Editing[{rank}]", disable=rank != 0)
-    except ImportError:
-        it = mine
-    for image_id, entry in it:
+    # ---- per-entry admission (the reference's checks, run_batch.py:185-207), then micro-batches of --micro_batch images ----
+    work = []
+    for image_id, entry in mine:
         try:
             source_filename = entry["image_path"]
             source_path = safe_join(args.source_dir, source_filename)
@@ -115,35 +134,87 @@ def main(argv=None):
             if not os.path.exists(source_path):
                 failed += 1
                 continue
-            os.makedirs(os.path.dirname(output_path), exist_ok=True)
-            source_img = Image.open(source_path).convert("RGB")
-            editing_prompt = entry.get("editing_prompt", "")
-            if not editing_prompt:
+            if not entry.get("editing_prompt", ""):
                 failed += 1
                 continue
-            t0 = time.time()
-            edited = editor.edit(image=source_img, prompt=editing_prompt, negative_prompt=args.negative_prompt, strength=args.strength,
-                                 num_inference_steps=args.steps, guidance_scale=args.guidance, controlnet_conditioning_scale=args.control_scale,
-                                 canny_low_threshold=args.canny_low, canny_high_threshold=args.canny_high, seed=args.seed)
-            total_time += time.time() - t0
-            edited.save(output_path)
-            processed += 1
-            if args.save_comparisons:
-                from run_single_image import _save_plot
-                cp = os.path.join(comparisons_dir, source_filename.replace(".jpg", ".png"))
-                os.makedirs(os.path.dirname(cp), exist_ok=True)
-                _save_plot(source_img, edited, f"Edited ({args.model.upper()})\n\"{editing_prompt[:60]}\"", cp)
-            if processed % 10 == 0:
-                editor.clear_memory()
-        except FileNotFoundError as e:
-            print(f"\n      File not found for {image_id}: {e}")
-            failed += 1
+            work.append((image_id, entry, source_path, output_path))
         except ValueError as e:
             print(f"\n      Invalid path for {image_id}: {e}")
             failed += 1
-        except Exception as e:  # per-image isolation, as the reference
+        except Exception as e:
             print(f"\n      Error processing {image_id} ({type(e).__name__}): {e}")
             failed += 1
+    mb = max(int(args.micro_batch), 1)
+    groups = [work[i:i + mb] for i in range(0, len(work), mb)]
+    edit_kw = dict(negative_prompt=args.negative_prompt, strength=args.strength, num_inference_steps=args.steps, guidance_scale=args.guidance,
+                   controlnet_conditioning_scale=args.control_scale, canny_low_threshold=args.canny_low, canny_high_threshold=args.canny_high)
+
+    def load(item):
+        return Image.open(item[2]).convert("RGB")
+
+    def save(img, item, source_img):
+        os.makedirs(os.path.dirname(item[3]), exist_ok=True)
+        img.save(item[3])
+        if args.save_comparisons:
+            from run_single_image import _save_plot
+            cp = os.path.join(comparisons_dir, item[1]["image_path"].replace(".jpg", ".png"))
+            os.makedirs(os.path.dirname(cp), exist_ok=True)
+            _save_plot(source_img, img, f"Edited ({args.model.upper()})\n\"{item[1]['editing_prompt'][:60]}\"", cp)
+
+    # JPEG decode of the next group and JPEG encode of the previous one run on host threads (PIL releases the GIL in its codecs)
+    # while the GPU edits the current group.
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=max(int(args.io_threads), 1))
+    saves = []
+    loads = [pool.submit(load, it) for it in groups[0]] if groups else []
+    for gi, group in enumerate(groups):
+        nxt = [pool.submit(load, it) for it in groups[gi + 1]] if gi + 1 < len(groups) else []
+        items, imgs = [], []
+        for it, fut in zip(group, loads):
+            try:
+                imgs.append(fut.result())
+                items.append(it)
+            except FileNotFoundError as e:
+                print(f"\n      File not found for {it[0]}: {e}")
+                failed += 1
+            except Exception as e:
+                print(f"\n      Error processing {it[0]} ({type(e).__name__}): {e}")
+                failed += 1
+        loads = nxt
+        if not items:
+            continue
+        t0 = time.time()
+        try:
+            outs = editor.edit_many(imgs, [it[1]["editing_prompt"] for it in items], seed=args.seed, micro_batch=mb, **edit_kw)
+        except Exception as e:   # per-image isolation, as the reference (run_batch.py:250-261): retry the group image by image
+            print(f"\n      Batch of {len(items)} failed ({type(e).__name__}: {e}); retrying per image")
+            outs = []
+            for it, im in zip(items, imgs):
+                try:
+                    outs.append(editor.edit(image=im, prompt=it[1]["editing_prompt"], seed=args.seed, **edit_kw))
+                except Exception as e1:
+                    print(f"\n      Error processing {it[0]} ({type(e1).__name__}): {e1}")
+                    outs.append(None)
+        total_time += time.time() - t0
+        for it, im, out in zip(items, imgs, outs):
+            if out is None:
+                failed += 1
+                continue
+            saves.append((it, pool.submit(save, out, it, im)))
+        done_before = processed + len(items)
+        if done_before // 10 != processed // 10:
+            editor.clear_memory()
+        processed += sum(o is not None for o in outs)
+        if rank == 0:
+            print(f"\r      Editing[{rank}]: {min((gi + 1) * mb, len(work))}/{len(work)}", end="", flush=True)
+    for it, fut in saves:
+        try:
+            fut.result()
+        except Exception as e:
+            print(f"\n      Error saving {it[0]} ({type(e).__name__}): {e}")
+            processed -= 1
+            failed += 1
+    pool.shutdown()
     import torch
     dev = torch.device(device)
     processed_all = int(sweep.sum_over_ranks(processed, dev))

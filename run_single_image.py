@@ -12,6 +12,7 @@ from datetime import datetime
 
 from PIL import Image
 
+from run_batch import checkpoints_from_args
 from src.pipeline import FastEditor
 
 
@@ -35,6 +36,8 @@ def build_parser():
     p.add_argument("--full_controlnet", action="store_true")
     p.add_argument("--compute_metrics", action="store_true")
     p.add_argument("--show_plot", action="store_true")
+    from run_batch import add_checkpoint_args
+    add_checkpoint_args(p)
     return p
 
 
@@ -66,7 +69,8 @@ def main(argv=None):
     print(f"      Image size: {source_img.size}")
     print("\n[2/4] Initializing FastEditor...")
     editor = FastEditor(model_name=args.model, device="cuda", enable_cpu_offload=not args.no_cpu_offload,
-                        use_full_precision=args.full_precision, use_full_controlnet=args.full_controlnet)
+                        use_full_precision=args.full_precision, use_full_controlnet=args.full_controlnet,
+                        checkpoints=checkpoints_from_args(args))
     mem = editor.get_memory_usage()
     print(f"      GPU Memory: {mem['allocated_gb']:.2f}GB allocated, {mem['reserved_gb']:.2f}GB reserved")
     print("\n[3/4] Running image editing...")

@@ -65,3 +65,57 @@ def test_lora_key_styles():
     prefixed = {"unet." + k: v for k, v in peft.items()}
     got2 = K.lora_to_peft(prefixed, list(unet.keys()))
     assert set(got2) == set(peft) and all(torch.equal(got2[k], peft[k].float()) for k in peft)
+
+
+def test_lora_with_unmapped_keys_is_an_error():
+    """A LoRA tensor that matches no UNet parameter must not be dropped silently."""
+    import pytest
+    unet = S.make_unet_params(C.tiny_unet_config())
+    bad = {"lora_unet_no_such_layer.lora_down.weight": torch.zeros(4, 8), "lora_unet_no_such_layer.lora_up.weight": torch.zeros(8, 4)}
+    with pytest.raises(ValueError, match="do not match any UNet parameter"):
+        K.lora_to_peft(bad, list(unet.keys()))
+
+
+def test_mid_block_type_null_is_rejected():
+    import pytest
+    with pytest.raises(ValueError, match="mid_block_type"):
+        K.unet_config_from_json({**SDXL_UNET, "mid_block_type": None})
+
+
+def test_clip_text_encoder_round_trip_and_env_expansion(tmp_path, monkeypatch):
+    """text_encoder / text_encoder_2 folders in the transformers layout (config.json + model.fp16.safetensors) -> CLIPTextConfig + params;
+    the published SDXL values: CLIP-L is a CLIPTextModel (projection_dim present but unused), bigG a CLIPTextModelWithProjection."""
+    from fast_image_editing_with_generative_models_b200 import text_encoder as T
+    from fast_image_editing_with_generative_models_b200.editor import checkpoints_from_env, expand_checkpoints
+    c1, c2 = T.tiny_clip_config(False, "quick_gelu"), T.tiny_clip_config(True, "gelu")
+    p1, p2 = T.make_clip_params(c1), T.make_clip_params(c2)
+    root = tmp_path / "pipe"
+    K.save_clip_dir(str(root / "text_encoder"), c1, p1, fp16=False)
+    K.save_clip_dir(str(root / "text_encoder_2"), c2, p2, fp16=False)
+    g1, q1 = K.load_clip_dir(str(root / "text_encoder"))
+    g2, q2 = K.load_clip_dir(str(root / "text_encoder_2"))
+    assert g1.projection_dim is None and g2.projection_dim == c2.projection_dim
+    assert (g1.hidden_size, g1.num_layers, g1.num_heads, g1.intermediate_size, g1.hidden_act) == (c1.hidden_size, c1.num_layers, c1.num_heads, c1.intermediate_size, "quick_gelu")
+    assert g2.hidden_act == "gelu" and set(q1) == set(p1) and set(q2) == set(p2)
+    assert all(torch.equal(q2[k], p2[k].float()) for k in p2)
+    published_l = {"architectures": ["CLIPTextModel"], "hidden_size": 768, "num_hidden_layers": 12, "num_attention_heads": 12, "intermediate_size": 3072,
+                   "hidden_act": "quick_gelu", "projection_dim": 768, "vocab_size": 49408, "max_position_embeddings": 77}
+    published_g = {"architectures": ["CLIPTextModelWithProjection"], "hidden_size": 1280, "num_hidden_layers": 32, "num_attention_heads": 20,
+                   "intermediate_size": 5120, "hidden_act": "gelu", "projection_dim": 1280, "vocab_size": 49408, "max_position_embeddings": 77}
+    a, b = K.clip_config_from_json(published_l, "l"), K.clip_config_from_json(published_g, "g")
+    ref_l, ref_g = T.clip_l_config(), T.openclip_bigg_config()
+    for got, ref in ((a, ref_l), (b, ref_g)):
+        assert (got.hidden_size, got.num_layers, got.num_heads, got.intermediate_size, got.hidden_act, got.projection_dim) == \
+               (ref.hidden_size, ref.num_layers, ref.num_heads, ref.intermediate_size, ref.hidden_act, ref.projection_dim)
+    # folder expansion used by the CLIs / environment variables
+    (root / "tokenizer").mkdir(); (root / "tokenizer_2").mkdir()
+    ck = expand_checkpoints(str(root), str(tmp_path / "cn"), lora=str(tmp_path / "lora.safetensors"))
+    assert ck["unet"].endswith("unet") and ck["vae"].endswith("vae") and ck["controlnet"].endswith("cn") and ck["lora"].endswith("lora.safetensors")
+    assert {"text_encoder", "text_encoder_2", "tokenizer", "tokenizer_2"} <= set(ck)
+    monkeypatch.delenv("FIE_CHECKPOINTS", raising=False)
+    assert checkpoints_from_env() is None
+    monkeypatch.setenv("FIE_CHECKPOINTS", str(root)); monkeypatch.setenv("FIE_CONTROLNET", str(tmp_path / "cn"))
+    assert checkpoints_from_env()["controlnet"].endswith("cn")
+    import pytest
+    with pytest.raises(ValueError, match="ControlNet"):
+        expand_checkpoints(str(root), None)

@@ -121,3 +121,62 @@ def test_edit_resizes_like_the_reference(editor):
     a = editor.edit(image=small, prompt="a rusty bicycle", seed=5)
     b = editor.edit(image=small.resize((1024, 1024), Image.LANCZOS), prompt="a rusty bicycle", seed=5)
     assert np.array_equal(np.array(a), np.array(b))
+
+
+def test_edit_many_equals_per_image_edit(editor):
+    """FastEditor.edit_many (micro-batches through the engine, pipelined host work) returns what the per-image edit() calls return:
+    same per-image generators in the reference RNG order, mixed input sizes, a ragged tail that is padded to the batch size."""
+    imgs = [_image(20, (1024, 1024)), _image(21, (1024, 1024)), _image(22, (1024, 1024)), _image(23, (512, 512)), _image(24, (640, 480))]
+    prompts = [f"prompt number {i}" for i in range(5)]
+    seeds = [3, 3, 5, 7, 9]
+    many = editor.edit_many(imgs, prompts, seeds=seeds, micro_batch=2)              # groups of 2, 2 and a ragged 1
+    assert len(many) == 5 and all(isinstance(m, Image.Image) and m.size == (1024, 1024) for m in many)
+    for im, pr, sd, got in zip(imgs, prompts, seeds, many):
+        one = editor.edit(image=im, prompt=pr, seed=sd)
+        assert np.array_equal(np.array(one), np.array(got)), "edit_many differs from edit()"
+    # one shared prompt / seed (the way run_batch.py passes --seed), default micro-batch with a padded tail of 3 -> 4
+    many2 = editor.edit_many(imgs[:3], "a rusty bicycle", seed=11)
+    one = editor.edit(image=imgs[2], prompt="a rusty bicycle", seed=11)
+    assert np.array_equal(np.array(one), np.array(many2[2]))
+    with pytest.raises(ValueError):
+        editor.edit_many(imgs[:2], ["only one prompt"])
+
+
+def test_strength_is_validated_like_diffusers(editor):
+    """diffusers' img2img check_inputs / get_timesteps raise ValueError for strength outside [0, 1] and when no step is left."""
+    img = _image(30)
+    for bad in (-0.1, 1.5):
+        with pytest.raises(ValueError, match="strength"):
+            editor.edit(image=img, prompt="x", strength=bad)
+    with pytest.raises(ValueError, match="number of pipeline steps"):
+        editor.edit(image=img, prompt="x", strength=0.1, num_inference_steps=4)
+    assert editor.edit(image=img, prompt="x", strength=0.25, seed=1).size == (1024, 1024)     # int(4 * 0.25) = 1 step: valid
+
+
+def test_graph_cache_is_bounded_and_clear_memory_trims_it(editor):
+    eng = editor.pipe.engine
+    img = _image(31)
+    for g in (1.5, 2.0, 2.5, 3.0, 3.5, 4.0):                                        # six distinct graph keys
+        editor.edit(image=img, prompt="x", guidance_scale=g, seed=1)
+    assert len(eng._graphs) <= eng.max_graphs
+    a = editor.edit(image=img, prompt="x", guidance_scale=4.0, seed=1)
+    editor.clear_memory()
+    assert len(eng._graphs) == 1                                                    # the most recently used graph survives
+    b = editor.edit(image=img, prompt="x", guidance_scale=4.0, seed=1)
+    assert np.array_equal(np.array(a), np.array(b))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_editor_on_a_non_default_device(cuda_dev):
+    """FastEditor(device="cuda:1") while cuda:0 is the current device: kernels must launch on the tensors' device and the
+    per-device function attributes (> 48 KiB shared memory) must be set there too."""
+    from src.pipeline import FastEditor
+    assert torch.cuda.current_device() == 0
+    e0 = FastEditor(model_name="ssd-1b", device="cuda:0", tiny=True, verbose=False)
+    e1 = FastEditor(model_name="ssd-1b", device="cuda:1", tiny=True, verbose=False)
+    img = _image(40)
+    a, b = e0.edit(image=img, prompt="x", seed=2), e1.edit(image=img, prompt="x", seed=2)
+    assert torch.cuda.current_device() == 0
+    # the two devices draw their noise from their own generators with the same seed: identical Philox streams
+    assert np.array_equal(np.array(a), np.array(b))
+    assert e1.get_memory_usage()["allocated_gb"] > 0
