@@ -3,12 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # N=1 directly; N>1 under torchrun (or self-spawned)
     python bench.py --impl reference ...                           # the reference's CPU path (oracle port) on host cores
+    python bench.py --config {0,1,2,3}                             # the other BASELINE.json configurations
 
-Workload (BASELINE.json configs[3], the configuration the images/s metric is quoted on): SDXL UNet (LCM-LoRA fused) +
-ControlNet-Canny small + fp16-fix VAE topology, fp16, 8 synthetic 1024x1024 images per GPU per step, 4 LCM steps at
-strength 0.5 (2 executed UNet+ControlNet evaluations), CFG 1.5, ControlNet scale 0.5, Canny 100/200.  A "step" is one
-``EditEngine.edit_batch`` over the per-GPU batch.  Images are sharded over ranks (weak scaling, no hot-path collective);
-the uint8 outputs are all-gathered over NCCL after every step.
+Default workload = BASELINE.json configs[3] (the configuration the images/s metric is quoted on): SDXL UNet (LCM-LoRA fused) +
+ControlNet-Canny small + fp16-fix VAE topology, fp16, 8 synthetic 1024x1024 images per GPU per step, 4 LCM steps at strength 0.5
+(2 executed UNet+ControlNet evaluations), CFG 1.5, ControlNet scale 0.5, Canny 100/200.  A "step" is one engine pass over the
+per-GPU batch.  Images are sharded over ranks (weak scaling, no hot-path collective); the uint8 outputs are all-gathered over
+NCCL after every step.
+
+  value  device-resident inputs, ``EditEngine.edit_batch`` (CUDA-graph replay of the whole edit)
+  e2e    the plugin call: host PIL images + prompt strings -> ``FastEditor.edit_many`` -> host PIL images; PIL->numpy->pinned->H2D,
+         both CLIP text towers, per-image ``torch.Generator`` noise, the edit, D2H and ``Image.fromarray`` are all inside the timed region
+  --config 0  the reference's own CPU case (configs[0]: SSD-1B, one image, fp32, host cores) == ``--impl reference --model ssd-1b``
+  --config 1  Canny + VAE encode/decode only, batch 32 (memory-bound kernels)
+  --config 2  SSD-1B full edit, batch 1 (latency)
 """
 from __future__ import annotations
 
@@ -25,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TFLOP_PER_IMAGE = {"sdxl": 44.45, "ssd-1b": 34.22}      # BASELINE.md section 3 (CN-small, 2 executed steps)
-CPU_SAMPLE_SIZE = 256                                     # CPU sample: one full edit at 256x256, scaled by pixel ratio
+VAE_TFLOP_PER_IMAGE = 4.887 + 10.486                     # encode + decode
+REF_BUDGET_S = float(os.environ.get("FIE_REF_BUDGET_S", "170"))   # wall budget of the timed CPU edits (at least one always runs)
 
 
 def parse():
@@ -34,12 +43,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="sdxl", choices=["sdxl", "ssd-1b"])
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--config", type=int, default=3, choices=[0, 1, 2, 3], help="BASELINE.json configs[] index (default 3: the headline)")
+    ap.add_argument("--model", default=None, choices=["sdxl", "ssd-1b"])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="launch the ~2500 kernels of an edit eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="launch the ~2000 kernels of an edit eagerly instead of replaying one CUDA graph")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-family breakdown JSON here")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == 0:
+        a.impl = "reference"
+    if a.model is None:
+        a.model = "ssd-1b" if a.config in (0, 2) else "sdxl"
+    if a.batch is None:
+        a.batch = {0: 1, 1: 32, 2: 1, 3: 8}[a.config]
+    return a
 
 
 class ClockSampler:
@@ -72,60 +89,111 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_sample(state, model: str, threads: int):
-    """One bounded sample of the reference's CPU path: the oracle restatement of the diffusers pipeline (fp32, torch CPU
-    ops, all host threads) running ONE full edit — Canny (plain-C oracle), VAE encode, 2 executed ControlNet+UNet CFG-pair
-    evaluations, VAE decode — with the full-width architecture at 256x256 instead of 1024x1024.  Returns seconds."""
+# ------------------------------------------------------------------------------------------------
+# The reference's CPU path: the fp32 oracle restatement of the diffusers pipeline on all host cores
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_edit(state, size: int, threads: int):
+    """ONE full edit of ONE image on the CPU — the reference's path as ``FastEditor(device="cpu", use_full_precision=True)`` would
+    run it: Canny (plain-C oracle of cv2.Canny), VAE encode, 2 executed ControlNet + UNet CFG-pair evaluations with the LoRA
+    applied unfused, LCM steps, VAE decode, fp32 torch CPU ops on ``threads`` threads.  -> (seconds, {stage: seconds})."""
     import numpy as np
     import torch
     from oracle import c_oracle
     from oracle import diffusion_oracle as O
     from fast_image_editing_with_generative_models_b200 import synthetic as S
     torch.set_num_threads(threads)
-    H = CPU_SAMPLE_SIZE
-    img = S.synthetic_image(0, H, H)
+    img = S.synthetic_image(0, size, size)
     ucfg = state["unet_cfg"]
     pe, pl = S.synthetic_prompt(0, ucfg.cross_attention_dim, ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim)
-    noises = S.synthetic_noises(0, 1, H // 8, H // 8)
+    noises = S.synthetic_noises(0, 1, size // 8, size // 8)
     m = O.EditModels(ucfg, state["unet"], state["cn_cfg"], state["cn"], state["vae_cfg"], state["vae"], state.get("lora"), state.get("lora_scale", 1.0))
+    marks = []
     t0 = time.perf_counter()
+    marks.append(("canny", t0))
     with torch.no_grad():
         edges = c_oracle.canny_u8(img[None], 100, 200, replicate3=True)
         O.edit_pipeline(m, torch.from_numpy(img[None]), torch.from_numpy(edges), pe.float(), pl.float(), noises, strength=0.5,
-                        num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5, dtype=torch.float32)
-    return time.perf_counter() - t0
+                        num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5, dtype=torch.float32,
+                        on_stage=lambda name: marks.append((name, time.perf_counter())))
+    t1 = time.perf_counter()
+    stages = {}
+    for (n0, a), (_, b) in zip(marks[:-1], marks[1:]):
+        stages[n0] = stages.get(n0, 0.0) + (b - a)
+    return t1 - t0, stages
+
+
+def cpu_model_name():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def timed_cpu_edits(state, max_edits: int, threads: int):
+    """One untimed 64x64 warm-up (thread pools, oneDNN primitive caches), then full 1024x1024 edits until ``max_edits`` or the wall
+    budget REF_BUDGET_S is reached (at least one).  -> (list of seconds, stage split of the first)."""
+    cpu_reference_edit(state, 64, threads)
+    times, stages0 = [], None
+    t_begin = time.perf_counter()
+    while len(times) < max(max_edits, 1):
+        t, st = cpu_reference_edit(state, 1024, threads)
+        times.append(t)
+        stages0 = stages0 or st
+        if (time.perf_counter() - t_begin) + t > REF_BUDGET_S:      # another edit would overrun the budget
+            break
+    return times, stages0
 
 
 def run_reference(a):
-    """--impl reference: the reference's own CPU implementation of the path.  diffusers is not installable here, so this
-    is the oracle port (kind "port"); rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path, MEASURED at full size.  diffusers is not installable
+    here, so this is the oracle port (kind "port"); rank 0 only.  A step of this arm is a bounded sample of
+    the GPU arm's step: ONE of its 1024x1024 images (the images of a step are independent)."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import torch
     from fast_image_editing_with_generative_models_b200 import model_zoo
     threads = os.cpu_count() or 1
     state = model_zoo.synthetic_state(a.model)
-    scale = (1024 // CPU_SAMPLE_SIZE) ** 2
-    for _ in range(min(a.warmup, 1)):
-        cpu_reference_sample(state, a.model, threads)
-    times = [cpu_reference_sample(state, a.model, threads) for _ in range(max(a.steps, 1))]
+    times, stages = timed_cpu_edits(state, a.steps, threads)
     t = sum(times) / len(times)
-    value = 1.0 / (t * scale)
-    sample = (f"one full fp32 oracle edit (Canny + VAE enc + 2x(ControlNet+UNet CFG pair) + VAE dec, {a.model} widths) at "
-              f"{CPU_SAMPLE_SIZE}x{CPU_SAMPLE_SIZE}, time scaled by the {scale}x pixel ratio to 1024x1024 (attention is sub-sampled "
-              f"quadratically, so this flatters the CPU)")
+    value = 1.0 / t
+    sample = (f"{len(times)} timed full fp32 oracle edit(s) of ONE 1024x1024 image each (Canny + VAE encode + 2 x (ControlNet + UNet CFG pair) + "
+              f"VAE decode, {a.model} + ControlNet-small widths, LoRA unfused as in the reference) on {threads} host threads "
+              f"({cpu_model_name()}), after one untimed 64x64 warm-up; {a.steps} steps requested, bounded by a {REF_BUDGET_S:.0f} s wall budget; "
+              f"nothing is extrapolated")
     line = {"impl": "reference", "metric": "1024x1024 4-step edit images/sec", "value": value, "unit": "images/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": t * scale * a.batch * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": len(times), "steps_requested": a.steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "images_per_gpu": a.batch, "strength": 0.5, "executed_steps": 2, "cfg": 1.5},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": workload_name(a), "images_per_step": 1, "strength": 0.5, "executed_steps": 2, "cfg": 1.5,
+                       "note": "a step of this arm = one image of the GPU arm's per-GPU batch (independent images)"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
+                             "seconds_per_edit": [round(x, 2) for x in times], "stages_s": {k: round(v, 2) for k, v in (stages or {}).items()}},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def workload_name(a):
-    return (f"{a.model.upper()} + LCM + ControlNet-Canny(small) + VAE full edit, fp16, {a.batch} x 1024x1024 images/GPU "
-            f"(BASELINE configs[3]), 4 LCM steps @ strength 0.5 (2 executed), CFG 1.5")
+    if a.config == 1:
+        return f"Canny + VAE encode/decode only, fp16, {a.batch} x 1024x1024 images (BASELINE configs[1])"
+    tag = {0: "configs[0], the reference's CPU case", 2: "configs[2], latency", 3: "configs[3]"}[a.config]
+    return (f"{a.model.upper()} + LCM + ControlNet-Canny(small) + VAE full edit, {'fp32' if a.config == 0 else 'fp16'}, {a.batch} x 1024x1024 "
+            f"images/GPU (BASELINE {tag}), 4 LCM steps @ strength 0.5 (2 executed), CFG 1.5")
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def latest_profile_json(pattern):
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    return json.load(open(files[-1])) if files else None
 
 
 def main():
@@ -139,11 +207,14 @@ def main():
                "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
 
+    import warnings
     import numpy as np
     import torch
     import torch.distributed as dist
+    from PIL import Image
     from fast_image_editing_with_generative_models_b200 import _lib, model_zoo, ops, sweep
     from fast_image_editing_with_generative_models_b200 import synthetic as S
+    from fast_image_editing_with_generative_models_b200.editor import FastEditor
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); the product path has no CPU fallback")
@@ -152,9 +223,16 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     B, H = a.batch, 1024
+    peaks = load_peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_hbm = float(peaks.get("hbm_gbs", 6400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kernel timed inside a long step)" if peaks else "fallback (B200_PROFILING.md sustained ~1400)"
 
     state = model_zoo.synthetic_state(a.model)
-    eng = model_zoo.build_engine(state, dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # synthetic weights are the point here ("data": "synthetic")
+        editor = FastEditor(model_name=a.model, device=f"cuda:{local}", enable_cpu_offload=False, state=state, text_encoders=True, verbose=False)
+    eng = editor.pipe.engine
     eng.use_graphs = not a.no_graph      # one CUDA graph per edit (the product default of FastEditor); --no-graph = eager launches
     ucfg = eng.unet.cfg
     pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
@@ -165,60 +243,76 @@ def main():
     imgs = torch.from_numpy(imgs_np).to(dev)
     pe_d, pl_d = pe.to(dev), pl.to(dev)
     nz_d = [n.to(dev, torch.float16) for n in noises]
-
-    def step():
-        out = eng.edit_batch(imgs, pe_d, pl_d, nz_d, strength=0.5, num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5)
-        return sweep.gather_outputs(out.images) if world > 1 else out.images
+    EDIT = dict(strength=0.5, num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return sweep.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    if a.config == 1:
+        return run_config1(a, eng, imgs, dev, rank, world, peak_tf, peak_hbm, peak_src, timed, ClockSampler(local))
+
+    def step():
+        out = eng.edit_batch(imgs, pe_d, pl_d, nz_d, **EDIT)
+        return sweep.gather_outputs(out.images) if world > 1 else out.images
+
+    W = max(a.warmup, 3)
+    for _ in range(W):
         step()
     # ---- timed region: device-resident inputs ----
     sampler = ClockSampler(local)
     sampler.start()
-    barrier()
     l0 = ops.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        step()
-    e1.record()
-    barrier()
-    ms = sweep.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms = timed(step, a.steps, 0)
     launches = ops.LAUNCHES - l0
     clocks = sampler.stop()
     value = world * B * a.steps / (ms * 1e-3)
 
-    # ---- end-to-end: host (pinned) buffers in, host images out, copies inside the timed region ----
-    host_imgs = torch.from_numpy(imgs_np).pin_memory()
-    host_noise = [n.to(torch.float16).pin_memory() for n in noises]
-    host_pe, host_pl = pe.pin_memory(), pl.pin_memory()
-    host_out = torch.empty((B, H, H, 3), dtype=torch.uint8).pin_memory()
+    # ---- end-to-end through the plugin API: FastEditor.edit_many on host PIL images and prompt strings -> host PIL images ----
+    pil = [Image.fromarray(imgs_np[i]) for i in range(B)]
+    call = [0]
 
-    def step_e2e():
-        d_img = host_imgs.to(dev, non_blocking=True)
-        d_nz = [n.to(dev, non_blocking=True) for n in host_noise]
-        out = eng.edit_batch(d_img, host_pe.to(dev, non_blocking=True), host_pl.to(dev, non_blocking=True), d_nz, strength=0.5,
-                             num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5)
-        host_out.copy_(out.images, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller gets the images on the host
-        return host_out
+    def e2e_call(n_batches):
+        """One public-API call over n_batches x B images (the way run_batch.py drives a sweep): new prompts every call, so both CLIP
+        towers run for every image; per-image generators; outputs come back as PIL images."""
+        call[0] += 1
+        images = pil * n_batches
+        prompts = [f"edit {call[0]}: make image {j} look like a watercolour painting" for j in range(len(images))]
+        outs = editor.edit_many(images, prompts, negative_prompt="", seeds=list(range(len(images))), micro_batch=B, **EDIT)
+        assert len(outs) == len(images) and outs[-1].size == (H, H)
+        return outs
 
-    step_e2e()
-    barrier()
-    e0.record()
-    for _ in range(a.steps):
-        step_e2e()
-    e1.record()
-    barrier()
-    ms_e2e = sweep.max_over_ranks(e0.elapsed_time(e1), dev)
-    h2d = host_imgs.numel() + sum(n.numel() * 2 for n in host_noise) + host_pe.numel() * 2 + host_pl.numel() * 2
-    d2h = host_out.numel()
-    e2e = {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    e2e_call(1)
+    ms_e2e = timed(lambda: e2e_call(a.steps), 1, 0)                 # ONE call over steps x B images: host work pipelined under the GPU
+    ms_e2e_1 = timed(lambda: e2e_call(1), max(min(a.steps, 3), 1), 0) / max(min(a.steps, 3), 1)   # one B-image call at a time: nothing overlaps
+    tok = 2 * 77 * 4                                                 # int32 token ids of the two towers (neg + pos)
+    h2d = B * H * H * 3 + B * tok
+    d2h = B * H * H * 3
+    e2e = {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "api": f"FastEditor.edit_many({a.steps * B} PIL images, {a.steps * B} prompt strings, seeds) -> PIL images, micro-batches of {B}; "
+                  "PIL->numpy->pinned->H2D, CLIP text towers, per-image torch.Generator noise, D2H and Image.fromarray inside the timed region",
+           "ms_per_step": ms_e2e / a.steps,
+           "single_call": {"images_per_call": B, "ms_per_call": ms_e2e_1, "value": world * B / (ms_e2e_1 * 1e-3),
+                           "note": "one edit_many call per step: host staging and PIL conversion are not overlapped with GPU work"}}
+    # batch-1 latency of the reference's own call, FastEditor.edit (host PIL in -> host PIL out)
+    lat = None
+    if world == 1:
+        editor.edit(image=pil[0], prompt="warm-up", seed=0, **EDIT)
+        ms1 = timed(lambda: editor.edit(image=pil[0], prompt=f"latency probe {call[0]}", seed=0, **EDIT), 5, 1) / 5
+        lat = {"api": "FastEditor.edit (1 PIL image -> 1 PIL image)", "model": a.model, "ms_per_edit": ms1}
 
     # ---- per-kernel-family attribution (one instrumented step, after the timed regions) ----
     eng.edit_batch(imgs, pe_d, pl_d, nz_d, strength=0.5, use_graph=False)      # untimed eager step: fills the caching allocator outside the graph pool
@@ -229,27 +323,17 @@ def main():
     fam = ops.profile_summary()
     stages = ops.stage_summary()
     ops.PROFILE = None
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained; kernel timed inside a long step)" if peaks else "fallback (B200_PROFILING.md sustained ~1400)"
     TC = ("gemm", "conv3x3", "conv_up2x")        # every launch of k_gemm_conv with a FLOP count (conv_up2x = 4 phase launches per call)
     tc_ms = sum(fam[k]["ms"] for k in TC if k in fam)
     tc_flop = sum(fam[k]["work"] for k in TC if k in fam)
     tc_calls = sum(fam[k]["calls"] * (4 if k == "conv_up2x" else 1) for k in TC if k in fam)
     total_ms = sum(d["ms"] for d in fam.values())
     achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-    traffic, traffic_src, tensor_pct = None, None, None
-    try:            # DRAM bytes per launch from the committed ncu --set full capture (profiles/); None if absent
-        import glob
-        tj = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))[-1]))   # latest committed capture
-        traffic, traffic_src = tj["dram_bytes_per_launch_avg"], tj["source"]
-        tensor_pct = tj.get("tensor_pipe_active_pct_time_weighted")
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    tj = latest_profile_json("r*_gemm_traffic.json")          # DRAM bytes per launch from the committed ncu --set full capture
+    if tj:
+        traffic, traffic_src = tj.get("dram_bytes_per_launch_avg"), tj.get("source")
+    tp = latest_profile_json("r*_tensor_pipe_step.json")     # whole-step ncu pass: time-weighted sm__pipe_tensor_cycles_active over ALL launches
     roofline = {"kernel": "k_gemm_conv (tcgen05 GEMM / implicit-GEMM conv3x3)", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches_per_step": tc_calls,
                 "share_of_step": tc_ms / total_ms if total_ms else None,
@@ -259,34 +343,95 @@ def main():
     if a.profile_out and rank == 0:
         json.dump(breakdown, open(a.profile_out, "w"), indent=1)
 
-    # ---- CPU baseline (rank 0, single-GPU run only) ----
+    # ---- CPU baseline (rank 0, single-GPU run only): ONE measured full-size fp32 edit of one image of this workload ----
     cpu_baseline = None
     if world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        scale = (1024 // CPU_SAMPLE_SIZE) ** 2
-        t = cpu_reference_sample(state, a.model, threads)
-        cpu_baseline = {"value": 1.0 / (t * scale), "unit": "images/s", "cores": threads, "kind": "port",
-                        "sample": f"one full fp32 oracle edit at {CPU_SAMPLE_SIZE}x{CPU_SAMPLE_SIZE} ({t:.1f} s), scaled by the {scale}x pixel ratio"}
+        times, st = timed_cpu_edits(state, 1, threads)
+        cpu_baseline = {"value": 1.0 / times[0], "unit": "images/s", "cores": threads, "kind": "port", "cpu": cpu_model_name(),
+                        "sample": f"one full fp32 oracle edit of ONE 1024x1024 image of this workload ({a.model}, {times[0]:.1f} s measured, not extrapolated) "
+                                  f"on {threads} host threads after a 64x64 warm-up",
+                        "stages_s": {k: round(v, 2) for k, v in st.items()}}
 
     if rank == 0:
+        upe = stages.get("unet_step", 0.0) / 2.0 if stages else None
         line = {"metric": "1024x1024 4-step edit images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
-                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": W, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
                 "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world, "strength": 0.5, "executed_steps": 2,
                            "cfg": 1.5, "parallelism": f"dp{world} (independent images, NCCL all-gather of uint8 outputs)",
-                           "weights": "seeded random-init of the named architectures", "launch": "eager" if a.no_graph else "cuda-graph replay of the whole edit", "l2": "inputs larger than L2 (5 GB weights + GB-scale activations per step)"},
+                           "weights": "seeded random-init of the named architectures", "launch": "eager" if a.no_graph else "cuda-graph replay of the whole edit",
+                           "l2": "inputs larger than L2 (5 GB weights + GB-scale activations per step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "image_roofline": {"tflop_per_image": TFLOP_PER_IMAGE[a.model], "achieved_tflops_per_gpu": value / world * TFLOP_PER_IMAGE[a.model],
                                    "frac_of_peak": value / world * TFLOP_PER_IMAGE[a.model] / peak_tf},
                 # the other two quantities BASELINE.json's metric names: UNet step time and tensor-pipe utilisation
-                "unet_step_ms": (stages.get("unet_step", 0.0) / 2.0) if stages else None,          # per executed step, CFG batch of 2 x images_per_gpu rows
+                "unet_step_ms": upe,          # per executed step, CFG batch of 2 x images_per_gpu rows
                 "stages_ms": {k: round(v, 3) for k, v in stages.items()},
-                "tensor_pipe": {"achieved_over_measured_peak": achieved / peak_tf, "ncu_sm__pipe_tensor_cycles_active_pct": tensor_pct,
-                                "ncu_source": traffic_src},
+                "tensor_pipe": {"achieved_over_measured_peak": achieved / peak_tf,
+                                "ncu_sm__pipe_tensor_cycles_active_pct": tp.get("tensor_pipe_active_pct_time_weighted") if tp else None,
+                                "ncu_unet_step_pct": tp.get("unet_step_tensor_pipe_active_pct") if tp else None,
+                                "ncu_source": tp.get("source") if tp else None},
+                "latency_batch1": lat,
                 "breakdown": breakdown}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_config1(a, eng, imgs, dev, rank, world, peak_tf, peak_hbm, peak_src, timed, sampler):
+    """BASELINE configs[1]: Canny + VAE encode + VAE decode only, batch 32 of 1024x1024 images — the memory-bound kernels (Canny,
+    GroupNorm) beside the VAE convolutions.  The batch is processed in chunks of 8 images (activation memory), a step = all 32."""
+    import torch
+    from fast_image_editing_with_generative_models_b200 import ops
+    B = imgs.shape[0]
+    CH = 8
+    vae = eng.vae
+    lat = [torch.randn((CH, 128, 128, 4), device=dev, generator=torch.Generator(dev).manual_seed(i)).half() for i in range(B // CH)]
+
+    def step():
+        edges = ops.canny(imgs, 100, 200, out_channels=3)
+        outs = []
+        for c in range(B // CH):
+            vae.encode_moments(ops.preprocess_pad8(imgs[c * CH:(c + 1) * CH], True))
+            outs.append(ops.postprocess(vae.decode(lat[c])))
+        return edges, outs
+
+    W = max(a.warmup, 3)
+    for _ in range(W):
+        step()
+    sampler.start()
+    l0 = ops.LAUNCHES
+    ms = timed(step, a.steps, 0)
+    launches = ops.LAUNCHES - l0
+    clocks = sampler.stop()
+    ops.PROFILE = []
+    step()
+    fam = ops.profile_summary()
+    ops.PROFILE = None
+    TC = ("gemm", "conv3x3", "conv_up2x")
+    tc_ms = sum(fam[k]["ms"] for k in TC if k in fam)
+    tc_flop = sum(fam[k]["work"] for k in TC if k in fam)
+    tc_calls = sum(fam[k]["calls"] * (4 if k == "conv_up2x" else 1) for k in TC if k in fam)
+    achieved = tc_flop / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
+    hbm = {}
+    for k in ("canny", "groupnorm"):
+        if k in fam and fam[k]["ms"] > 0:
+            gbs = fam[k]["work"] / (fam[k]["ms"] * 1e-3) / 1e9
+            hbm[k] = {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "ms": round(fam[k]["ms"], 3), "calls": fam[k]["calls"]}
+    value = world * B * a.steps / (ms * 1e-3)
+    if rank == 0:
+        line = {"metric": "1024x1024 Canny + VAE encode/decode images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": W,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": workload_name(a), "images_per_gpu": B, "chunk": CH, "l2": "inputs larger than L2"},
+                "clocks": clocks, "e2e": None, "gpu_launches": int(launches),
+                "roofline": {"kernel": "k_gemm_conv (VAE convolutions)", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                             "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src, "launches_per_step": tc_calls},
+                "hbm_rooflines": hbm, "cpu_baseline": None,
+                "image_roofline": {"tflop_per_image": VAE_TFLOP_PER_IMAGE, "achieved_tflops_per_gpu": value / world * VAE_TFLOP_PER_IMAGE,
+                                   "frac_of_peak": value / world * VAE_TFLOP_PER_IMAGE / peak_tf},
+                "breakdown": {k: {"calls": d["calls"], "ms": round(d["ms"], 3)} for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}}
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -145,7 +145,69 @@ __global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ st
     else { out[o * 3] = v; out[o * 3 + 1] = v; out[o * 3 + 2] = v; }
 }
 
+// ---- optional integer Gaussian pre-stage (DEFAULT OFF: the reference calls cv2.Canny without a blur, src/pipeline.py:205) ----
+// Bit-exact with cv2.GaussianBlur(img, (5, 5), 0) on uint8: OpenCV's fixed-point path uses the exact kernel [1 4 6 4 1] / 16 per
+// axis in 8.8 / 16.16 fixed point with one final rounding, which equals (sum_ij w_i w_j p_ij + 128) >> 8 with integer weights
+// (sum 256); border BORDER_REFLECT_101.  Horizontal pass into shared memory (16-bit), vertical pass out; C interleaved channels.
+constexpr int GW = 128, GH = 16;
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+template <int C>
+__global__ void __launch_bounds__(256) k_gauss5(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W) {
+    __shared__ uint8_t  sp[GH + 4][(GW + 4) * C];
+    __shared__ uint16_t sh[GH + 4][GW * C];
+    const int img = blockIdx.z, x0 = blockIdx.x * GW, y0 = blockIdx.y * GH, tid = threadIdx.x;
+    const uint8_t* s = src + (size_t)img * H * W * C;
+    for (int i = tid; i < (GH + 4) * (GW + 4); i += 256) {
+        const int ly = i / (GW + 4), lx = i % (GW + 4);
+        const int y = reflect101(y0 + ly - 2, H), x = reflect101(x0 + lx - 2, W);
+#pragma unroll
+        for (int c = 0; c < C; ++c) sp[ly][lx * C + c] = __ldg(s + ((size_t)y * W + x) * C + c);
+    }
+    __syncthreads();
+    for (int i = tid; i < (GH + 4) * GW * C; i += 256) {
+        const int ly = i / (GW * C), e = i % (GW * C);
+        sh[ly][e] = (uint16_t)(sp[ly][e] + 4 * sp[ly][e + C] + 6 * sp[ly][e + 2 * C] + 4 * sp[ly][e + 3 * C] + sp[ly][e + 4 * C]);
+    }
+    __syncthreads();
+    for (int i = tid; i < GH * GW * C; i += 256) {
+        const int ly = i / (GW * C), e = i % (GW * C);
+        const int y = y0 + ly, x = x0 + e / C;
+        if (y >= H || x >= W) continue;
+        const int v = sh[ly][e] + 4 * sh[ly + 1][e] + 6 * sh[ly + 2][e] + 4 * sh[ly + 3][e] + sh[ly + 4][e];
+        dst[((size_t)img * H + y) * W * C + (size_t)x0 * C + e] = (uint8_t)((v + 128) >> 8);
+    }
+}
+
 }  // namespace fie
+
+extern "C" int fie_gaussian_blur5_u8(const void* src, void* dst, int n, int h, int w, int channels, void* stream_) {
+    using namespace fie;
+    FIE_REQUIRE(n >= 0 && h > 0 && w > 0 && n <= 65535, "fie_gaussian_blur5_u8: bad shape n=%d h=%d w=%d", n, h, w);
+    FIE_REQUIRE(channels == 1 || channels == 3, "fie_gaussian_blur5_u8: channels must be 1 or 3");
+    if (n == 0) return FIE_OK;
+    FIE_REQUIRE(src && dst && src != dst, "fie_gaussian_blur5_u8: null pointer or in-place call");
+    dim3 grid(ceil_div(w, GW), ceil_div(h, GH), n);
+    if (channels == 1) k_gauss5<1><<<grid, 256, 0, (cudaStream_t)stream_>>>((const uint8_t*)src, (uint8_t*)dst, h, w);
+    else k_gauss5<3><<<grid, 256, 0, (cudaStream_t)stream_>>>((const uint8_t*)src, (uint8_t*)dst, h, w);
+    return check_launch("fie_gaussian_blur5_u8");
+}
+
+extern "C" int fie_rgb_to_gray_u8(const void* rgb, void* gray, int n, int h, int w, void* stream_) {
+    using namespace fie;
+    FIE_REQUIRE(n >= 0 && h > 0 && w > 0, "fie_rgb_to_gray_u8: bad shape");
+    if (n == 0) return FIE_OK;
+    FIE_REQUIRE(rgb && gray, "fie_rgb_to_gray_u8: null pointer");
+    FIE_REQUIRE((reinterpret_cast<uintptr_t>(rgb) & 3) == 0 && (reinterpret_cast<uintptr_t>(gray) & 3) == 0, "fie_rgb_to_gray_u8: pointers must be 4-byte aligned");
+    const size_t px = (size_t)n * h * w;
+    const long long n4 = (long long)((px + 3) / 4);
+    int blocks = (int)((n4 + 255) / 256); if (blocks > device_sm_count() * 16) blocks = device_sm_count() * 16;
+    k_gray<<<blocks, 256, 0, (cudaStream_t)stream_>>>((const uint8_t*)rgb, (uint8_t*)gray, n4, (long long)px);
+    return check_launch("fie_rgb_to_gray_u8");
+}
 
 extern "C" size_t fie_canny_workspace_bytes(int n, int h, int w) {
     size_t px = (size_t)n * h * w;

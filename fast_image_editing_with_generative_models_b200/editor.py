@@ -174,35 +174,46 @@ class FastEditor:
     def _encode_prompt(self, prompt: str, negative_prompt: str):
         """-> (prompt_embeds [2,77,D], pooled [2,P]) with row 0 = negative, row 1 = positive (the empty negative prompt is ENCODED,
         as in the reference: it is passed explicitly, src/pipeline.py:263)."""
-        key = (prompt, negative_prompt)
-        hit = self._prompt_cache.get(key)
-        if hit is not None:
-            self._prompt_cache.move_to_end(key)
-            return hit
-        val = self._encode_prompt_uncached(prompt, negative_prompt)
-        self._prompt_cache[key] = val
-        while len(self._prompt_cache) > 64:
-            self._prompt_cache.popitem(last=False)
-        return val
+        pe, pl = self._encode_prompts([prompt], [negative_prompt])
+        return pe[0], pl[0]
 
-    def _encode_prompt_uncached(self, prompt: str, negative_prompt: str):
-        ucfg = self._engine.unet.cfg
-        if self._prompt_encoder is not None:
-            return self._prompt_encoder(prompt, negative_prompt)
-        if self._text is not None:
-            if self._tokenizers is not None:
-                ids1, ids2 = (torch.tensor(t([negative_prompt, prompt]), dtype=torch.int64) for t in self._tokenizers)
-                return self._text.encode(ids1, ids2)
-            from .text_encoder import pseudo_token_ids
-            ids = torch.stack([pseudo_token_ids(negative_prompt, self._text_vocab), pseudo_token_ids(prompt, self._text_vocab)])
-            return self._text.encode(ids, ids)          # ([neg, pos] x 77 x 2048, [neg, pos] x 1280)
-        pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
-        pos = S.synthetic_prompt(zlib.crc32(prompt.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)
-        neg = S.synthetic_prompt(zlib.crc32(negative_prompt.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)
-        return torch.stack([neg[0][1], pos[0][1]]), torch.stack([neg[1][1], pos[1][1]])
+    def _encode_prompts(self, prompts: Sequence[str], negs: Sequence[str]):
+        """Batched ``encode_prompt``: -> (prompt_embeds [B,2,77,D], pooled [B,2,P]) on the device.  Every distinct text runs through the
+        two CLIP towers ONCE per call (all texts of the micro-batch in one pass; a tower treats sequences independently), and a small
+        LRU keeps recent texts — the negative prompt is the same string for a whole sweep."""
+        dev = self._dev
+        if self._prompt_encoder is not None:                      # user hook: (prompt, negative) -> ([2,77,D], [2,P])
+            enc = [self._prompt_encoder(p, n) for p, n in zip(prompts, negs)]
+            return (torch.stack([e[0].to(dev, torch.float16) for e in enc]), torch.stack([e[1].to(dev, torch.float16) for e in enc]))
+        cache = self._prompt_cache
+        todo = [t for t in dict.fromkeys(list(negs) + list(prompts)) if t not in cache]
+        if todo:
+            if self._text is not None:
+                if self._tokenizers is not None:
+                    ids1, ids2 = (torch.tensor(t(todo), dtype=torch.int64) for t in self._tokenizers)
+                else:
+                    from .text_encoder import pseudo_token_ids
+                    ids1 = ids2 = torch.stack([pseudo_token_ids(t, self._text_vocab) for t in todo])
+                hid, pooled = self._text.encode(ids1, ids2)          # [T,77,2048], [T,1280]
+                for i, t in enumerate(todo):
+                    cache[t] = (hid[i], pooled[i])
+            else:
+                ucfg = self._engine.unet.cfg
+                pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+                for t in todo:                                       # no text encoder: deterministic embeddings seeded by the text
+                    e = S.synthetic_prompt(zlib.crc32(t.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)
+                    cache[t] = (e[0][1].to(dev, torch.float16), e[1][1].to(dev, torch.float16))
+        pe = torch.stack([torch.stack([cache[n][0], cache[p][0]]) for p, n in zip(prompts, negs)])
+        pl = torch.stack([torch.stack([cache[n][1], cache[p][1]]) for p, n in zip(prompts, negs)])
+        for t in list(negs) + list(prompts):
+            cache.move_to_end(t)
+        while len(cache) > 64:
+            cache.popitem(last=False)
+        return pe, pl
 
-    def preprocess_image(self, image, low_threshold=100, high_threshold=200):
-        """PIL image (RGB, or 2-D gray array) -> PIL RGB Canny edge map (reference ``src/pipeline.py:183-210``)."""
+    def preprocess_image(self, image, low_threshold=100, high_threshold=200, *, gaussian_blur=False):
+        """PIL image (RGB, or 2-D gray array) -> PIL RGB Canny edge map (reference ``src/pipeline.py:183-210``).
+        ``gaussian_blur`` (extension, default off as in the reference): cv2.GaussianBlur(gray, (5, 5), 0) before cv2.Canny."""
         image_np = np.ascontiguousarray(np.array(image))
         if image_np.dtype != np.uint8 or image_np.ndim not in (2, 3):
             raise ValueError("preprocess_image expects an 8-bit RGB or gray image")
@@ -210,7 +221,7 @@ class FastEditor:
             image_np = np.ascontiguousarray(image_np[..., :3])
         with torch.cuda.device(self._dev):
             d = torch.from_numpy(image_np[None]).to(self._dev)
-            edges = ops.canny(d, int(np.floor(low_threshold)), int(np.floor(high_threshold)), out_channels=3)
+            edges = ops.canny(d, int(np.floor(low_threshold)), int(np.floor(high_threshold)), out_channels=3, gaussian_blur=gaussian_blur)
             return Image.fromarray(edges[0].cpu().numpy())
 
     # ---- argument checks shared by edit / edit_many (diffusers img2img check_inputs + get_timesteps) ----
@@ -246,7 +257,7 @@ class FastEditor:
         return img
 
     def edit(self, image, prompt, negative_prompt="", strength=0.80, num_inference_steps=4, guidance_scale=1.5,
-             controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200, seed=None):
+             controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200, seed=None, *, canny_gaussian_blur=False):
         """Edit an image with a text prompt, preserving structure via Canny conditioning -> PIL RGB 1024x1024."""
         n_exec = self._executed_steps(strength, num_inference_steps)
         with torch.cuda.device(self._dev):
@@ -255,12 +266,14 @@ class FastEditor:
             noises = self._draw_noises(seed, n_exec)
             out = self._engine.edit_batch(img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
                                           guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
-                                          canny_low=int(np.floor(canny_low_threshold)), canny_high=int(np.floor(canny_high_threshold)))
+                                          canny_low=int(np.floor(canny_low_threshold)), canny_high=int(np.floor(canny_high_threshold)),
+                                          canny_blur=canny_gaussian_blur)
             return Image.fromarray(out.images[0].cpu().numpy())
 
     def edit_many(self, images: Sequence, prompts: Union[str, Sequence[str]], negative_prompt: Union[str, Sequence[str]] = "", strength=0.80,
                   num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200,
-                  seed=None, seeds: Optional[Sequence[Optional[int]]] = None, micro_batch: Optional[int] = None) -> List[Image.Image]:
+                  seed=None, seeds: Optional[Sequence[Optional[int]]] = None, micro_batch: Optional[int] = None,
+                  canny_gaussian_blur: bool = False) -> List[Image.Image]:
         """Batched ``edit``: ``[edit(images[i], prompts[i], ..., seed=seeds[i]) for i]`` — same per-image semantics (each image gets its
         own generator seeded with ``seeds[i]``, or ``seed`` for all, drawing in the reference's order; the results are the ones the
         per-image calls give) but run in micro-batches of ``micro_batch`` (default 8) images per engine call.
@@ -308,16 +321,14 @@ class FastEditor:
                 else:
                     parts = [self._to_device_1024(images[i]) for i in idx]
                     d_img = torch.cat(parts + [parts[-1]] * (pad_to - nb), 0)
-                enc = [self._encode_prompt(prompts[i], negs[i]) for i in idx]
-                enc += [enc[-1]] * (pad_to - nb)
-                pe = torch.stack([e[0].to(self._dev, torch.float16) for e in enc])      # [B,2,77,D]
-                pl = torch.stack([e[1].to(self._dev, torch.float16) for e in enc])      # [B,2,P]
+                pad = [idx[-1]] * (pad_to - nb)
+                pe, pl = self._encode_prompts([prompts[i] for i in idx + pad], [negs[i] for i in idx + pad])      # [B,2,77,D], [B,2,P]
                 per_img = [self._draw_noises(seeds[i], n_exec) for i in idx]
                 per_img += [per_img[-1]] * (pad_to - nb)
                 noises = [torch.cat([p[d] for p in per_img], 0) for d in range(len(per_img[0]))]
                 out = self._engine.edit_batch(d_img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
                                               guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
-                                              canny_low=lo, canny_high=hi)
+                                              canny_low=lo, canny_high=hi, canny_blur=canny_gaussian_blur)
                 host_out[:nb].copy_(out.images[:nb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)

@@ -34,7 +34,7 @@ def synthetic_state(model_name: str, full_controlnet: bool = False, tiny: bool =
                 lora=lora, lora_scale=1.0)
 
 
-def build_engine(state: Dict, device="cuda"):
+def build_engine(state: Dict, device="cuda", pack_on_host: bool = False):
     from .pipeline import EditEngine
     return EditEngine(state["unet"], state["unet_cfg"], state["cn"], state["cn_cfg"], state["vae"], state["vae_cfg"], device,
-                      state.get("lora"), state.get("lora_scale", 1.0))
+                      state.get("lora"), state.get("lora_scale", 1.0), pack_on_host=pack_on_host)

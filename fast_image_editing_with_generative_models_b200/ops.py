@@ -99,9 +99,13 @@ def _req(t: torch.Tensor, dtype, name: str):
         raise _lib.FieError(f"{name}: expected a contiguous tensor")
 
 
-def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: int = 1) -> torch.Tensor:
-    """uint8 [N,H,W,3] (RGB) or [N,H,W] (gray) -> uint8 edges [N,H,W] or [N,H,W,3] (0/255); == cv2.Canny."""
+def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: int = 1, gaussian_blur: bool = False) -> torch.Tensor:
+    """uint8 [N,H,W,3] (RGB) or [N,H,W] (gray) -> uint8 edges [N,H,W] or [N,H,W,3] (0/255); == cv2.Canny.
+    ``gaussian_blur`` (default off, as in the reference): gray -> cv2.GaussianBlur(gray, (5, 5), 0) -> Canny."""
     _req(img_u8, torch.uint8, "canny")
+    if gaussian_blur:
+        gray = rgb_to_gray(img_u8) if img_u8.dim() == 4 else img_u8
+        img_u8 = gaussian_blur5(gray)
     in_ch = 3 if img_u8.dim() == 4 else 1
     n, h, w = img_u8.shape[:3]
     L = _lib.lib()
@@ -111,6 +115,30 @@ def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: i
     with _prof("canny", float(n) * h * w * (in_ch + out_channels), "B"):
         check(L.fie_canny_u8(_p(img_u8), _p(out), n, h, w, in_ch, out_channels, int(low), int(high), _p(ws), ws_bytes, _stream()), "fie_canny_u8")
     _count(4 if in_ch == 3 else 3)
+    return out
+
+
+def rgb_to_gray(img_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 [N,H,W,3] -> uint8 [N,H,W]; == cv2.cvtColor(img, cv2.COLOR_RGB2GRAY)."""
+    _req(img_u8, torch.uint8, "rgb_to_gray")
+    n, h, w, c = img_u8.shape
+    if c != 3:
+        raise _lib.FieError("rgb_to_gray: RGB input expected")
+    out = torch.empty((n, h, w), dtype=torch.uint8, device=img_u8.device)
+    check(_lib.lib().fie_rgb_to_gray_u8(_p(img_u8), _p(out), n, h, w, _stream()), "fie_rgb_to_gray_u8")
+    _count()
+    return out
+
+
+def gaussian_blur5(img_u8: torch.Tensor) -> torch.Tensor:
+    """uint8 [N,H,W] or [N,H,W,3] -> same shape; bit-exact with cv2.GaussianBlur(img, (5, 5), 0)."""
+    _req(img_u8, torch.uint8, "gaussian_blur5")
+    c = img_u8.shape[3] if img_u8.dim() == 4 else 1
+    n, h, w = img_u8.shape[:3]
+    out = torch.empty_like(img_u8)
+    with _prof("gaussian_blur5", 2.0 * img_u8.numel(), "B"):
+        check(_lib.lib().fie_gaussian_blur5_u8(_p(img_u8), _p(out), n, h, w, c, _stream()), "fie_gaussian_blur5_u8")
+    _count()
     return out
 
 

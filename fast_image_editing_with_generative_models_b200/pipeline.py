@@ -28,18 +28,49 @@ class EditOutput:
     extras: Optional[Dict] = None
 
 
+def _move_to(obj, dev, seen=None):
+    """Recursively moves every tensor reachable from ``obj`` (attributes, lists, tuples, dicts) to ``dev``; returns the moved object."""
+    seen = set() if seen is None else seen
+    if isinstance(obj, Tensor):
+        return obj.to(dev)
+    if isinstance(obj, torch.device):
+        return dev
+    if isinstance(obj, (list, tuple)):
+        out = [_move_to(v, dev, seen) for v in obj]
+        if isinstance(obj, list):
+            obj[:] = out
+            return obj
+        return tuple(out)
+    if isinstance(obj, dict):
+        for k in list(obj):
+            obj[k] = _move_to(obj[k], dev, seen)
+        return obj
+    if hasattr(obj, "__dict__") and not isinstance(obj, type) and type(obj).__module__.startswith(__name__.rsplit(".", 1)[0]) and id(obj) not in seen:
+        seen.add(id(obj))
+        for k, v in list(vars(obj).items()):
+            setattr(obj, k, _move_to(v, dev, seen))
+    return obj
+
+
 class EditEngine:
     """Owns the packed weights of one (UNet, ControlNet, VAE) triple on one GPU and runs batched edits."""
 
     def __init__(self, unet_params, unet_cfg: UNetConfig, cn_params, cn_cfg: ControlNetConfig, vae_params, vae_cfg: VAEConfig,
-                 device="cuda", lora=None, lora_scale: float = 1.0):
+                 device="cuda", lora=None, lora_scale: float = 1.0, pack_on_host: bool = False):
+        """Load-time weight packing (layout transforms, LoRA fuse, LayerNorm fold; cold path, reference ``src/pipeline.py:45-181``)
+        uses plain torch tensor ops: by default on the GPU (ATen / cuBLAS kernels, seconds for SDXL), with ``pack_on_host`` on the
+        CPU followed by plain H2D copies — then no library kernel is ever launched on the device, only ours (``smoke()``)."""
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("EditEngine runs on CUDA (sm_100a) only; there is no CPU path")
         with torch.cuda.device(self.dev):
-            self.unet = UNet(unet_params, unet_cfg, self.dev, lora, lora_scale)
-            self.cn = ControlNet(cn_params, cn_cfg, self.dev)
-            self.vae = VAE(vae_params, vae_cfg, self.dev)
+            pdev = torch.device("cpu") if pack_on_host else self.dev
+            self.unet = UNet(unet_params, unet_cfg, pdev, lora, lora_scale)
+            self.cn = ControlNet(cn_params, cn_cfg, pdev)
+            self.vae = VAE(vae_params, vae_cfg, pdev)
+            if pack_on_host:
+                for m in (self.unet, self.cn, self.vae):
+                    _move_to(m, self.dev)
         self.sched = LCMSchedule()
         self.use_graphs = False           # opt-in: replay each edit as one CUDA graph (see edit_batch)
         # captured graphs, least recently used first.  Every distinct (shapes, strength, guidance, thresholds, ...) key owns a
@@ -57,7 +88,7 @@ class EditEngine:
     def edit_batch(self, images_u8: Tensor, prompt_embeds: Tensor, pooled: Tensor, noises: Sequence[Tensor], strength: float = 0.5,
                    num_inference_steps: int = 4, guidance_scale: float = 1.5, controlnet_conditioning_scale: float = 0.5,
                    canny_low: int = 100, canny_high: int = 200, return_latents: bool = False, return_extras: bool = False,
-                   use_graph: Optional[bool] = None) -> EditOutput:
+                   use_graph: Optional[bool] = None, canny_blur: bool = False) -> EditOutput:
         """images_u8: uint8 [B,H,W,3] (CUDA, H and W multiples of 8; 1024 for the reference path).
         prompt_embeds [2,77,D] / pooled [2,P] (row 0 negative, row 1 positive; shared by the batch) or per image
         [B,2,77,D] / [B,2,P].  noises: [xi, n, z1, ...] each [B,4,h,w] (reference RNG order).
@@ -67,10 +98,10 @@ class EditEngine:
         returned tensors are the graph's static outputs (valid until the next call with the same key)."""
         with torch.cuda.device(self.dev):           # kernels launch on the CURRENT device's stream: make that this engine's device
             return self._edit_batch(images_u8, prompt_embeds, pooled, noises, strength, num_inference_steps, guidance_scale,
-                                    controlnet_conditioning_scale, canny_low, canny_high, return_latents, return_extras, use_graph)
+                                    controlnet_conditioning_scale, canny_low, canny_high, return_latents, return_extras, use_graph, canny_blur)
 
     def _edit_batch(self, images_u8, prompt_embeds, pooled, noises, strength, num_inference_steps, guidance_scale, controlnet_conditioning_scale,
-                    canny_low, canny_high, return_latents, return_extras, use_graph) -> EditOutput:
+                    canny_low, canny_high, return_latents, return_extras, use_graph, canny_blur) -> EditOutput:
         dev = self.dev
         if strength < 0 or strength > 1:
             raise ValueError(f"The value of strength should in [0.0, 1.0] but is {strength}")
@@ -82,7 +113,7 @@ class EditEngine:
         pl = pooled.to(dev, torch.float16)
         images_u8 = images_u8.to(dev)
         args = dict(strength=strength, num_inference_steps=num_inference_steps, guidance_scale=guidance_scale,
-                    controlnet_conditioning_scale=controlnet_conditioning_scale, canny_low=canny_low, canny_high=canny_high)
+                    controlnet_conditioning_scale=controlnet_conditioning_scale, canny_low=canny_low, canny_high=canny_high, canny_blur=bool(canny_blur))
         graph = self.use_graphs if use_graph is None else use_graph
         if not graph or return_extras or ops.PROFILE is not None:
             return self._edit_core(images_u8, pe, pl, nz, return_latents=return_latents, return_extras=return_extras, **args)
@@ -121,7 +152,8 @@ class EditEngine:
 
     def _edit_core(self, images_u8: Tensor, pe: Tensor, pl: Tensor, nz: List[Tensor], strength: float = 0.5,
                    num_inference_steps: int = 4, guidance_scale: float = 1.5, controlnet_conditioning_scale: float = 0.5,
-                   canny_low: int = 100, canny_high: int = 200, return_latents: bool = False, return_extras: bool = False) -> EditOutput:
+                   canny_low: int = 100, canny_high: int = 200, canny_blur: bool = False, return_latents: bool = False,
+                   return_extras: bool = False) -> EditOutput:
         """The edit itself; every tensor is already on the device (fp16, noises NHWC) — nothing here touches the host."""
         B, H, W, _ = images_u8.shape
         sched = self.sched
@@ -130,7 +162,7 @@ class EditEngine:
         nrow = 2 if do_cfg else 1
         # ---- Canny control image + conditioning embedding (step-invariant) ----
         ops.stage("canny+cond_embedding")
-        edges3 = ops.canny(images_u8, canny_low, canny_high, out_channels=3)
+        edges3 = ops.canny(images_u8, canny_low, canny_high, out_channels=3, gaussian_blur=canny_blur)     # blur: opt-in, the reference has none
         cond_emb = self.cn.cond_embedding(ops.preprocess_pad8(edges3, normalize=False))
         if do_cfg:
             cond_emb = torch.cat([cond_emb, cond_emb], 0)

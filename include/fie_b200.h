@@ -40,6 +40,14 @@ size_t fie_canny_workspace_bytes(int n, int h, int w);
 int fie_canny_u8(const void* img, void* edges, int n, int h, int w, int in_channels, int out_channels,
                  int low, int high, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- optional Canny pre-stage (DEFAULT OFF in the path: the reference's cv2.Canny call, src/pipeline.py:205, has no blur;
+ * BASELINE.json's north_star lists a Gaussian stage, so it exists as an opt-in: FastEditor.preprocess_image(..., gaussian_blur=True)) ----
+ * fie_rgb_to_gray_u8:    uint8 [n,h,w,3] -> uint8 [n,h,w], == cv2.cvtColor(RGB2GRAY) (15-bit fixed point), src/pipeline.py:200
+ * fie_gaussian_blur5_u8: uint8 [n,h,w,channels] (1 or 3) -> same shape, bit-exact with cv2.GaussianBlur(img, (5, 5), 0)
+ *                        (integer kernel [1 4 6 4 1]^2 / 256, one rounding, BORDER_REFLECT_101); dst != src. */
+int fie_rgb_to_gray_u8(const void* rgb, void* gray, int n, int h, int w, void* stream);
+int fie_gaussian_blur5_u8(const void* src, void* dst, int n, int h, int w, int channels, void* stream);
+
 /* ---- Lanczos resize: replaces image.resize((1024, 1024), Image.LANCZOS) at reference src/pipeline.py:251 ----
  * uint8 [n,h,w,3] -> uint8 [n,oh,ow,3], bit-identical to Pillow: a horizontal then a vertical fixed-point pass (a pass is skipped when
  * that size does not change).  bounds_* int32 [out,2] = (first input index, count), coeff_* int32 [out,ksize] = 2^22 fixed-point

@@ -16,6 +16,8 @@ def _lib():
     lib = ctypes.CDLL(_SO)
     lib.fie_oracle_canny_u8.restype = ctypes.c_int
     lib.fie_oracle_canny_u8.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 7
+    lib.fie_oracle_gaussian_blur5_u8.restype = ctypes.c_int
+    lib.fie_oracle_gaussian_blur5_u8.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4
     return lib
 
 
@@ -29,4 +31,16 @@ def canny_u8(img: np.ndarray, low=100, high=200, replicate3=False) -> np.ndarray
     rc = _lib().fie_oracle_canny_u8(img.ctypes.data, out.ctypes.data, n, h, w, ch, int(np.floor(low)), int(np.floor(high)), int(replicate3))
     if rc:
         raise RuntimeError(f"fie_oracle_canny_u8 failed rc={rc}")
+    return out
+
+
+def gaussian_blur5_u8(img: np.ndarray) -> np.ndarray:
+    """img: [N,H,W] or [N,H,W,C] uint8 -> same shape; restates cv2.GaussianBlur(img, (5, 5), 0)."""
+    img = np.ascontiguousarray(img)
+    assert img.dtype == np.uint8 and img.ndim in (3, 4)
+    n, h, w = img.shape[:3]
+    out = np.empty_like(img)
+    rc = _lib().fie_oracle_gaussian_blur5_u8(img.ctypes.data, out.ctypes.data, n, h, w, img.shape[3] if img.ndim == 4 else 1)
+    if rc:
+        raise RuntimeError(f"fie_oracle_gaussian_blur5_u8 failed rc={rc}")
     return out

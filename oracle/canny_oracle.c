@@ -82,3 +82,41 @@ int fie_oracle_canny_u8(const uint8_t* img, uint8_t* out, int n, int h, int w, i
     free(gray); free(mag); free(gx); free(gy); free(st); free(stack);
     return 0;
 }
+
+
+/* Optional Gaussian pre-stage (default OFF in the path; see include/fie_b200.h): restates cv2.GaussianBlur(img, (5, 5), 0) for
+ * uint8 — OpenCV's fixed-point separable filter with the exact kernel [1 4 6 4 1]/16 per axis and a single final rounding,
+ * i.e. (sum_ij w_i w_j p_ij + 128) >> 8, BORDER_REFLECT_101.  PINNED against cv2 4.13.0 (tests/test_canny_oracle.py).
+ * img/out: [n][h][w][channels] u8. */
+static int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+int fie_oracle_gaussian_blur5_u8(const uint8_t* img, uint8_t* out, int n, int h, int w, int channels)
+{
+    static const int k[5] = {1, 4, 6, 4, 1};
+    if (n < 0 || h <= 0 || w <= 0 || channels <= 0) return 1;
+    const size_t row = (size_t)w * channels;
+    int32_t* tmp = (int32_t*)malloc((size_t)h * row * sizeof(int32_t));
+    if (!tmp) return 2;
+    for (int im = 0; im < n; ++im) {
+        const uint8_t* src = img + (size_t)im * h * row;
+        uint8_t* dst = out + (size_t)im * h * row;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+                for (int c = 0; c < channels; ++c) {
+                    int acc = 0;
+                    for (int i = 0; i < 5; ++i) acc += k[i] * src[(size_t)y * row + (size_t)reflect101(x + i - 2, w) * channels + c];
+                    tmp[(size_t)y * row + (size_t)x * channels + c] = acc;
+                }
+        for (int y = 0; y < h; ++y)
+            for (size_t e = 0; e < row; ++e) {
+                int acc = 0;
+                for (int j = 0; j < 5; ++j) acc += k[j] * tmp[(size_t)reflect101(y + j - 2, h) * row + e];
+                dst[(size_t)y * row + e] = (uint8_t)((acc + 128) >> 8);
+            }
+    }
+    free(tmp);
+    return 0;
+}

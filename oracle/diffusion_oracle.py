@@ -376,13 +376,16 @@ class EditModels:
 
 def edit_pipeline(m: EditModels, image_u8: Tensor, edges_u8: Tensor, prompt_embeds: Tensor, pooled: Tensor,
                   noises: Sequence[Tensor], strength=0.5, num_inference_steps=4, guidance_scale=1.5,
-                  controlnet_conditioning_scale=0.5, dtype=torch.float32, return_all=False):
+                  controlnet_conditioning_scale=0.5, dtype=torch.float32, return_all=False, on_stage=None):
     """StableDiffusionXLControlNetImg2ImgPipeline.__call__ restated.
 
     image_u8/edges_u8: uint8 [B,H,W,3]; prompt_embeds [2,77,D] (row 0 negative, row 1 positive), pooled [2,P]
     (shared by all images of the batch); noises: [xi, n, z1, ...] each [B,4,H/8,W/8] (RNG order of the
     reference generator: posterior sample, init noise, then one per non-final executed step).
+    on_stage(name): optional callback at the start of each stage (bench.py's CPU stage split).
     """
+    mark = on_stage or (lambda name: None)
+    mark("vae_encode")
     dev = image_u8.device
     B, H, W, _ = image_u8.shape
     do_cfg = guidance_scale > 1
@@ -413,7 +416,9 @@ def edit_pipeline(m: EditModels, image_u8: Tensor, edges_u8: Tensor, prompt_embe
     for k, t in enumerate(timesteps):
         x2 = torch.cat([x] * nrow)
         tt = torch.tensor([t], device=dev)
+        mark("controlnet_step")
         down, mid = controlnet_forward(m.cn, m.cn_cfg, x2, tt, ctx, te, tids, cond, controlnet_conditioning_scale)
+        mark("unet_step")
         eps = unet_forward(m.unet, m.unet_cfg, x2, tt, ctx, te, tids, down, mid, lora)
         if do_cfg:
             e_u, e_c = eps.chunk(2)
@@ -428,9 +433,11 @@ def edit_pipeline(m: EditModels, image_u8: Tensor, edges_u8: Tensor, prompt_embe
         x = sched.step(eps, step_index, x, z)
     out["latents"] = x
     out["eps"] = eps_list
+    mark("vae_decode")
     img = vae_decode(m.vae, m.vae_cfg, x / m.vae_cfg.scaling_factor)
     out["decoded"] = img
     out["image_u8"] = postprocess_image(img)
+    mark("end")
     return out if return_all else out["image_u8"]
 
 

@@ -53,3 +53,23 @@ def test_empty_and_flat_inputs():
     flat = np.full((1, 40, 50, 3), 77, np.uint8)
     assert c_oracle.canny_u8(flat).sum() == 0
     assert c_oracle.canny_u8(np.zeros((0, 8, 8, 3), np.uint8)).shape == (0, 8, 8)
+
+
+def test_gaussian_oracle_matches_golden_and_live_cv2():
+    """The optional Gaussian pre-stage: plain-C restatement of cv2.GaussianBlur(img, (5, 5), 0) against the committed cv2 CRCs
+    (incl. 1-, 2- and 3-pixel-wide images where BORDER_REFLECT_101 wraps more than once) and against cv2 itself."""
+    import zlib
+    from tests.util import gauss_golden_cases
+    n = 0
+    for src, blur_crc, edges_crc in gauss_golden_cases():
+        blur = c_oracle.gaussian_blur5_u8(src[None])[0]
+        assert zlib.crc32(blur.tobytes()) == blur_crc, src.shape
+        if edges_crc is not None:
+            assert zlib.crc32(c_oracle.canny_u8(blur[None], 100, 200)[0].tobytes()) == edges_crc
+        n += 1
+    assert n >= 10
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for shape in [(64, 64), (37, 53, 3), (4, 6), (300, 200, 3)]:
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        assert np.array_equal(c_oracle.gaussian_blur5_u8(a[None])[0], cv2.GaussianBlur(a, (5, 5), 0))

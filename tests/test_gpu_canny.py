@@ -55,3 +55,26 @@ def test_canny_edge_cases(cuda_dev):
     assert ops.canny(empty).shape == (0, 8, 8)
     with pytest.raises(_lib.FieError):
         ops.canny(torch.zeros((1, 8, 8, 3), dtype=torch.uint8))   # CPU tensor: no fallback
+
+
+def test_gaussian_prestage_matches_cv2_golden(cuda_dev):
+    """Optional (default-off) integer Gaussian pre-stage: fie_gaussian_blur5_u8 == cv2.GaussianBlur(img, (5, 5), 0) bit for bit
+    (committed cv2 CRCs + the plain-C oracle), and ops.canny(gaussian_blur=True) == cv2.Canny of the blurred gray image."""
+    import zlib
+    from fast_image_editing_with_generative_models_b200 import ops
+    from oracle.canny_oracle import rgb_to_gray
+    from tests.util import gauss_golden_cases
+    for src, blur_crc, edges_crc in gauss_golden_cases():
+        d = torch.from_numpy(src[None]).to(cuda_dev)
+        blur = ops.gaussian_blur5(d).cpu().numpy()[0]
+        assert zlib.crc32(blur.tobytes()) == blur_crc, src.shape
+        if edges_crc is not None:
+            assert zlib.crc32(ops.canny(d, 100, 200, gaussian_blur=True).cpu().numpy()[0].tobytes()) == edges_crc
+    imgs = np.stack([synthetic_image(s, 1024, 1024, "shapes" if s % 2 == 0 else "noise") for s in range(3)])
+    d = torch.from_numpy(imgs).to(cuda_dev)
+    assert np.array_equal(ops.gaussian_blur5(d).cpu().numpy(), c_oracle.gaussian_blur5_u8(imgs))
+    gray = np.stack([rgb_to_gray(i) for i in imgs])
+    assert np.array_equal(ops.rgb_to_gray(d).cpu().numpy(), gray)
+    ref = c_oracle.canny_u8(c_oracle.gaussian_blur5_u8(gray), 100, 200)
+    assert np.array_equal(ops.canny(d, 100, 200, gaussian_blur=True).cpu().numpy(), ref)
+    assert not np.array_equal(ops.canny(d, 100, 200).cpu().numpy(), ref)                       # the default path has no blur
