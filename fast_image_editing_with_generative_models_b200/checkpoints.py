@@ -169,7 +169,9 @@ def load_state(unet_dir: str, controlnet_dir: str, vae_dir: str, lora_file: Opti
         from safetensors.torch import load_file
         lora = lora_to_peft(load_file(lora_file), list(unet.keys()))
     return dict(unet_cfg=unet_config_from_json(ucfg_d, os.path.basename(os.path.normpath(unet_dir))), unet=unet,
-                cn_cfg=controlnet_config_from_json(ccfg_d), cn=cn, vae_cfg=vae_config_from_json(vcfg_d), vae=vae, lora=lora, lora_scale=lora_scale)
+                cn_cfg=controlnet_config_from_json(ccfg_d), cn=cn, vae_cfg=vae_config_from_json(vcfg_d), vae=vae, lora=lora, lora_scale=lora_scale,
+                # real VAE checkpoints produce attention logits in the hundreds: keep them in fp32 between the passes (engine._VAEAttention)
+                vae_scores_f32=True)
 
 
 # ---- writing the same layout (used by the tests and to export synthetic models) ----

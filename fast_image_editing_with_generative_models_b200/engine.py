@@ -416,50 +416,59 @@ class _VAEAttention:
 
     def __init__(self, pk: _Packer, pre: str, groups: int, eps: float):
         self.groups, self.eps = groups, eps
+        self.scores_f32 = False       # set by VAE(..., attention_scores_f32=True): fp32 logits between the passes
         self.norm = pk.norm(pre + ".group_norm")
         self.q, self.k, self.v, self.o = (pk.linear(f"{pre}.{n}") for n in ("to_q", "to_k", "to_v", "to_out.0"))
 
-    # rows of fp32 scores materialised at a time.  Measured: L2-resident 1024-row chunks (64 MiB) lose more in the P V GEMM
-    # (M = 1024, N = 512 is 8 tiles on 74 CTA pairs) than they save in HBM traffic: 37 ms vs 21 ms per SDXL batch-8 edit.
-    CHUNK = int(os.environ.get("FIE_VAE_CHUNK", "4096"))
-    # fp16 scores (scaled in the GEMM epilogue, softmax in place): half the score traffic; measured parity unchanged (1.5e-2)
+    # Query rows whose scores are materialised at a time (0 = the whole image: 512 MiB of fp16 scores at 1024^2).  Measured: small
+    # L2-resident chunks lose more in the P V GEMM (M = 1024, N = 512 is 8 tiles on 74 CTA pairs) than they save in HBM traffic; with a
+    # whole image per pass the P V product runs as 128 tiles.
+    CHUNK = int(os.environ.get("FIE_VAE_CHUNK", "0"))
+    # fp16 scores (scaled in the GEMM epilogue, exp-only softmax in place, 1 / rowsum applied in fp32 by the P V epilogue): half the
+    # score traffic, parity unchanged on the synthetic weights (1.5e-2).  fp32 scores (``scores_f32``) keep the logits in fp32 between
+    # the passes like diffusers' SDPA: the safe default for REAL checkpoints, whose VAE logits reach the hundreds.
     F16_SCORES = os.environ.get("FIE_VAE_F16_SCORES", "1") == "1"
-    # softmax without its division: the P V GEMM scales its rows by 1 / rowsum in fp32 (FIE_VAE_DEFER_NORM=0: normalise in the softmax)
-    DEFER_NORM = os.environ.get("FIE_VAE_DEFER_NORM", "1") == "1"
 
     def __call__(self, x: Tensor, chunk: Optional[int] = None) -> Tensor:
-        chunk = chunk or self.CHUNK
+        chunk = self.CHUNK if chunk is None else chunk
         n, hh, ww, c = x.shape
         ntok = hh * ww
         hn = ops.groupnorm(x, self.norm[0], self.norm[1], self.eps, False, self.groups).view(n, ntok, c)
         xr = x.view(n, ntok, c)
         out = torch.empty_like(xr)
         scale = 1.0 / math.sqrt(c)
+        f32 = self.scores_f32 or not self.F16_SCORES
         for i in range(n):
             q = ops.gemm(hn[i], self.q[0], col_bias=self.q[1])
             k = ops.gemm(hn[i], self.k[0], col_bias=self.k[1])
             vt = ops.gemm(self.v[0], hn[i], m_bias=self.v[1])                 # V^T [c, ntok]
-            o = torch.empty((ntok, c), dtype=torch.float16, device=x.device)
-            for r0 in range(0, ntok, chunk):
-                r1 = min(r0 + chunk, ntok)
-                if self.F16_SCORES and self.DEFER_NORM and ntok % 4 == 0 and ntok <= 16384:
-                    s = ops.gemm(q[r0:r1], k, scale=scale)                     # [rows, ntok] fp16, already scaled
-                    p, inv = ops.softmax_rows_exp(s, 1.0, out=s)               # exp only, in place; 1 / rowsum on the side
-                    ops.gemm(p, vt, out=o[r0:r1], row_scale=inv)               # ... applied in fp32 by the P V epilogue
-                    continue
-                if self.F16_SCORES:
-                    s = ops.gemm(q[r0:r1], k, scale=scale)                     # [rows, ntok] fp16, already scaled
-                    p = ops.softmax_rows(s, 1.0, out=s)                        # in place
-                else:
-                    s = ops.gemm(q[r0:r1], k, out_f32=True)                    # [rows, ntok] fp32
-                    p = ops.softmax_rows(s, scale)
-                ops.gemm(p, vt, out=o[r0:r1])
+            if ops.PROFILE is None and ntok % 8 == 0:
+                o = ops.attention_vae(q, k, vt, scale, f32_scores=f32, chunk_rows=chunk)       # one C-ABI call: fie_attn_vae_d512_f16
+            else:
+                o = self._attention_unfused(q, k, vt, ntok, c, scale, chunk or ntok, f32)      # same passes, one profiled call each
             ops.gemm(o, self.o[0], col_bias=self.o[1], residual=xr[i], out=out[i])
         return out.view(n, hh, ww, c)       # (per-image GEMMs: the statistics of this output are left to the GroupNorm kernel)
 
+    @staticmethod
+    def _attention_unfused(q, k, vt, ntok, c, scale, chunk, f32):
+        o = torch.empty((ntok, c), dtype=torch.float16, device=q.device)
+        for r0 in range(0, ntok, chunk):
+            r1 = min(r0 + chunk, ntok)
+            if not f32 and ntok % 4 == 0 and ntok <= 16384:
+                s = ops.gemm(q[r0:r1], k, scale=scale)                     # [rows, ntok] fp16, already scaled
+                p, inv = ops.softmax_rows_exp(s, 1.0, out=s)               # exp only, in place; 1 / rowsum on the side
+                ops.gemm(p, vt, out=o[r0:r1], row_scale=inv)               # ... applied in fp32 by the P V epilogue
+            elif not f32:
+                s = ops.gemm(q[r0:r1], k, scale=scale)
+                ops.gemm(ops.softmax_rows(s, 1.0, out=s), vt, out=o[r0:r1])
+            else:
+                s = ops.gemm(q[r0:r1], k, out_f32=True)                    # [rows, ntok] fp32
+                ops.gemm(ops.softmax_rows(s, scale), vt, out=o[r0:r1])
+        return o
+
 
 class VAE:
-    def __init__(self, params: Params, cfg: VAEConfig, device):
+    def __init__(self, params: Params, cfg: VAEConfig, device, attention_scores_f32: bool = False):
         pk = _Packer(params, device)
         self.cfg, self.dev = cfg, device
         g, eps = cfg.norm_groups, cfg.norm_eps
@@ -499,6 +508,7 @@ class VAE:
         for blk in (self.e_mid, self.d_mid):
             blk[0].out_gn = g; blk[2].out_gn = g
         self.gn_groups = g
+        self.e_mid[1].scores_f32 = self.d_mid[1].scores_f32 = bool(attention_scores_f32)
 
     def encode_moments(self, xp8: Tensor) -> Tensor:
         """xp8: zero-padded [N,H+2,W+8,8] fp16 image in [-1,1] (ops.preprocess_pad8) -> moments [N,H/8,W/8,2L] fp16."""

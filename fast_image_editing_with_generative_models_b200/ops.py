@@ -494,6 +494,35 @@ def attention_d64(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, b: int, hea
     return out
 
 
+_VAE_WS = {}
+
+
+def attention_vae(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None, f32_scores: bool = False,
+                  chunk_rows: int = 0) -> torch.Tensor:
+    """softmax(scale q k^T) v for ONE image of the VAE mid-block attention (1 head): q, k [ntok, d] fp16, vt [d, ntok] fp16 (V transposed)
+    -> [ntok, d].  One C-ABI call (fie_attn_vae_d512_f16); the score workspace is cached per (device, shape)."""
+    for t in (q, k, vt):
+        _req(t, torch.float16, "attention_vae")
+    ntok, d = q.shape
+    if out is None:
+        out = torch.empty((ntok, d), dtype=torch.float16, device=q.device)
+    L = _lib.lib()
+    nbytes = L.fie_attn_vae_workspace_bytes(ntok, int(chunk_rows), int(f32_scores))
+    key = (str(q.device), nbytes)
+    ws = _VAE_WS.get(key)
+    if ws is None or torch.cuda.is_current_stream_capturing():
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)       # (inside a graph capture: owned by the graph's pool)
+        if not torch.cuda.is_current_stream_capturing():
+            _VAE_WS.clear()
+            _VAE_WS[key] = ws
+    with _prof("vae_attention", 4.0 * ntok * ntok * d, "FLOP", f"ntok{ntok} d{d} f32{int(f32_scores)}"):
+        check(L.fie_attn_vae_d512_f16(_p(q), q.stride(0), _p(k), k.stride(0), _p(vt), _p(out), out.stride(0), ntok, d, float(scale), int(f32_scores),
+                                      int(chunk_rows), _p(ws), nbytes, _stream()), "fie_attn_vae_d512_f16")
+    nchunks = 1 if chunk_rows <= 0 else -(-ntok // chunk_rows)
+    _count(3 * nchunks)
+    return out
+
+
 def vae_sample_add_noise(moments: torch.Tensor, xi: torch.Tensor, noise: torch.Tensor, scaling: float, sqrt_a: float, sqrt_1ma: float):
     """moments [N,H,W,>=8] fp16, xi/noise [N,H,W,4] fp16 -> noisy latents [N,H,W,4] as (fp32 state, fp16 copy for the UNet)."""
     _req(moments, torch.float16, "vae_sample_add_noise")

@@ -56,7 +56,7 @@ class EditEngine:
     """Owns the packed weights of one (UNet, ControlNet, VAE) triple on one GPU and runs batched edits."""
 
     def __init__(self, unet_params, unet_cfg: UNetConfig, cn_params, cn_cfg: ControlNetConfig, vae_params, vae_cfg: VAEConfig,
-                 device="cuda", lora=None, lora_scale: float = 1.0, pack_on_host: bool = False):
+                 device="cuda", lora=None, lora_scale: float = 1.0, pack_on_host: bool = False, vae_scores_f32: bool = False):
         """Load-time weight packing (layout transforms, LoRA fuse, LayerNorm fold; cold path, reference ``src/pipeline.py:45-181``)
         uses plain torch tensor ops: by default on the GPU (ATen / cuBLAS kernels, seconds for SDXL), with ``pack_on_host`` on the
         CPU followed by plain H2D copies — then no library kernel is ever launched on the device, only ours (``smoke()``)."""
@@ -67,7 +67,7 @@ class EditEngine:
             pdev = torch.device("cpu") if pack_on_host else self.dev
             self.unet = UNet(unet_params, unet_cfg, pdev, lora, lora_scale)
             self.cn = ControlNet(cn_params, cn_cfg, pdev)
-            self.vae = VAE(vae_params, vae_cfg, pdev)
+            self.vae = VAE(vae_params, vae_cfg, pdev, attention_scores_f32=vae_scores_f32)   # fp32 VAE attention logits: real checkpoints
             if pack_on_host:
                 for m in (self.unet, self.cn, self.vae):
                     _move_to(m, self.dev)

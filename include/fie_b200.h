@@ -192,6 +192,16 @@ int fie_conv3x3_cin4_f16(const void* x, const float* wgt, const float* bias, voi
 int fie_conv3x3_c8_f16(const void* xp, const void* wgt, void* out, long long ldd, int n, int h, int w, int cout,
                        int cout_valid, const fie_epilogue* ep, void* stream);
 
+/* ---- VAE mid-block attention: 1 head, d = C (512), ntok = H*W tokens (16 384 at 1024^2) — SURVEY 8(b) `fie_attn_vae_d512` ----
+ * Replaces Attention / AttnProcessor2_0 of the AutoencoderKL UNetMidBlock2D.  q, k: fp16 [ntok, d]; vt: fp16 [d, ntok] (V transposed, so
+ * that P V is a K-major GEMM); out: fp16 [ntok, d].  One call = softmax(scale q k^T) v for one image, computed as three passes of the
+ * tcgen05 GEMM / row-softmax kernels over `chunk_rows` query rows at a time (<= 0: the whole image; csrc/attn_vae.cu explains why this is
+ * not a single flash kernel at d = 512).  f32_scores = 1 keeps the logits in fp32 between the passes (safe for real checkpoints whose
+ * logits reach the hundreds); 0 stores them as fp16 (half the traffic).  workspace: fie_attn_vae_workspace_bytes(...), 256-byte aligned. */
+size_t fie_attn_vae_workspace_bytes(int ntok, int chunk_rows, int f32_scores);
+int fie_attn_vae_d512_f16(const void* q, long long ldq, const void* k, long long ldk, const void* vt, void* out, long long ldo,
+                          int ntok, int d, float scale, int f32_scores, int chunk_rows, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Flash attention, head_dim 64 (tcgen05): replaces F.scaled_dot_product_attention in AttnProcessor2_0 ----
  * q: fp16 rows [b*nq, ldq] (head h at columns h*64..), k/v: [b*nkv, ldk/ldv], out: [b*nq, ldo]. No mask. */
 int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,

@@ -131,13 +131,21 @@ def test_edit_many_equals_per_image_edit(editor):
     seeds = [3, 3, 5, 7, 9]
     many = editor.edit_many(imgs, prompts, seeds=seeds, micro_batch=2)              # groups of 2, 2 and a ragged 1
     assert len(many) == 5 and all(isinstance(m, Image.Image) and m.size == (1024, 1024) for m in many)
-    for im, pr, sd, got in zip(imgs, prompts, seeds, many):
-        one = editor.edit(image=im, prompt=pr, seed=sd)
-        assert np.array_equal(np.array(one), np.array(got)), "edit_many differs from edit()"
+    def close(a, b, what):
+        # same inputs, same per-image noise; only the batch size differs.  The kernels are deterministic for a given shape but not
+        # bitwise batch-invariant (the fp32 partial sums behind the integer GroupNorm statistics are split differently), so: equal up to
+        # a few LSB — a wrong seed / prompt / image pairing would differ by tens of grey levels everywhere.
+        d = np.abs(np.array(a).astype(np.int16) - np.array(b).astype(np.int16))
+        print(f"\n{what}: max |d| {int(d.max())}, mean |d| {float(d.mean()):.4f}, differing px {float((d > 0).mean()):.4f}")
+        assert d.max() <= 6 and d.mean() < 0.1, what
+
+    for j, (im, pr, sd, got) in enumerate(zip(imgs, prompts, seeds, many)):
+        close(editor.edit(image=im, prompt=pr, seed=sd), got, f"edit_many[{j}] vs edit()")
     # one shared prompt / seed (the way run_batch.py passes --seed), default micro-batch with a padded tail of 3 -> 4
     many2 = editor.edit_many(imgs[:3], "a rusty bicycle", seed=11)
-    one = editor.edit(image=imgs[2], prompt="a rusty bicycle", seed=11)
-    assert np.array_equal(np.array(one), np.array(many2[2]))
+    close(editor.edit(image=imgs[2], prompt="a rusty bicycle", seed=11), many2[2], "padded tail")
+    again = editor.edit_many(imgs[:3], "a rusty bicycle", seed=11)
+    assert all(np.array_equal(np.array(a), np.array(b)) for a, b in zip(many2, again)), "edit_many must be deterministic for a given batch shape"
     with pytest.raises(ValueError):
         editor.edit_many(imgs[:2], ["only one prompt"])
 
@@ -178,5 +186,5 @@ def test_editor_on_a_non_default_device(cuda_dev):
     a, b = e0.edit(image=img, prompt="x", seed=2), e1.edit(image=img, prompt="x", seed=2)
     assert torch.cuda.current_device() == 0
     # the two devices draw their noise from their own generators with the same seed: identical Philox streams
-    assert np.array_equal(np.array(a), np.array(b))
+    assert np.array_equal(np.array(a), np.array(b))          # same shapes, same kernels, integer statistics: bit-identical across devices
     assert e1.get_memory_usage()["allocated_gb"] > 0

@@ -542,3 +542,39 @@ def test_conv_and_groupnorm_write_only_their_output(cuda_dev):
     assert bool((arena[:64] == 1234.0).all()) and bool((arena[-64:] == 1234.0).all())
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), wt.view(cout, 3, 3, cin).permute(0, 3, 1, 2).float(), padding=1).permute(0, 2, 3, 1)
     assert rel_err(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("ntok,chunk", [(16384, 0), (16384, 4096), (4096, 0), (1000, 384)])
+def test_attn_vae_d512_matches_fp32_sdpa(cuda_dev, ntok, chunk):
+    """fie_attn_vae_d512_f16: softmax(q k^T / sqrt(512)) v for the VAE mid-block attention vs fp32
+    F.scaled_dot_product_attention, at the path's size (16 384 tokens) and ragged ones, fp16 and fp32 scores."""
+    import torch.nn.functional as F
+    from fast_image_editing_with_generative_models_b200 import ops
+    d = 512
+    g = torch.Generator("cpu").manual_seed(ntok + chunk)
+    q, k, v = (torch.randn((ntok, d), generator=g).to(cuda_dev).half() for _ in range(3))
+    ref = F.scaled_dot_product_attention(q.float()[None, None], k.float()[None, None], v.float()[None, None])[0, 0]
+    vt = v.t().contiguous()
+    for f32 in (False, True):
+        out = ops.attention_vae(q, k, vt, d ** -0.5, f32_scores=f32, chunk_rows=chunk).float()
+        err = float((out - ref).abs().max())
+        assert err < 2e-3 * max(1.0, float(ref.abs().max())), (f32, err)
+
+
+def test_attn_vae_large_logits_need_fp32_scores(cuda_dev):
+    """Logits in the hundreds (what real SDXL-VAE checkpoints produce): fp16 scores quantise them to 0.125-0.25 before the
+    exponential; the fp32-score mode (the default when real checkpoints are loaded) stays at fp16-output accuracy."""
+    import torch.nn.functional as F
+    from fast_image_editing_with_generative_models_b200 import ops
+    ntok, d = 2048, 512
+    g = torch.Generator("cpu").manual_seed(5)
+    q = (torch.randn((ntok, d), generator=g) * 4.0).to(cuda_dev).half()
+    k = (torch.randn((ntok, d), generator=g) * 4.0).to(cuda_dev).half()
+    v = torch.randn((ntok, d), generator=g).to(cuda_dev).half()
+    ref = F.scaled_dot_product_attention(q.float()[None, None], k.float()[None, None], v.float()[None, None])[0, 0]
+    assert float((q.float() @ k.float().t() * d ** -0.5).abs().max()) > 60           # the regime in question
+    vt = v.t().contiguous()
+    e32 = float((ops.attention_vae(q, k, vt, d ** -0.5, f32_scores=True).float() - ref).abs().max())
+    e16 = float((ops.attention_vae(q, k, vt, d ** -0.5, f32_scores=False).float() - ref).abs().max())
+    print("large-logit VAE attention: max-abs error fp32 scores", e32, "fp16 scores", e16)
+    assert e32 < 5e-3 and e32 <= e16
