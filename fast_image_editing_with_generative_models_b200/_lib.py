@@ -32,6 +32,11 @@ SIGNATURES = {
     "fie_canny_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "fie_rgb_to_gray_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "fie_gaussian_blur5_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "fie_jpeg_header_bytes": (c_int, []),
+    "fie_jpeg_write_header": (c_int, [c_void_p, c_int, c_int, c_int]),
+    "fie_jpeg_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "fie_jpeg_max_bytes": (c_size_t, [c_int, c_int]),
+    "fie_jpeg_encode_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fie_resample_lanczos_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     "fie_preprocess_u8_to_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "fie_preprocess_u8_to_f16_pad8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -273,10 +273,14 @@ class FastEditor:
     def edit_many(self, images: Sequence, prompts: Union[str, Sequence[str]], negative_prompt: Union[str, Sequence[str]] = "", strength=0.80,
                   num_inference_steps=4, guidance_scale=1.5, controlnet_conditioning_scale=0.5, canny_low_threshold=100, canny_high_threshold=200,
                   seed=None, seeds: Optional[Sequence[Optional[int]]] = None, micro_batch: Optional[int] = None,
-                  canny_gaussian_blur: bool = False) -> List[Image.Image]:
+                  canny_gaussian_blur: bool = False, output: str = "pil", jpeg_quality: int = 75) -> List:
         """Batched ``edit``: ``[edit(images[i], prompts[i], ..., seed=seeds[i]) for i]`` — same per-image semantics (each image gets its
         own generator seeded with ``seeds[i]``, or ``seed`` for all, drawing in the reference's order; the results are the ones the
         per-image calls give) but run in micro-batches of ``micro_batch`` (default 8) images per engine call.
+
+        ``output="jpeg"``: returns the edited images as JPEG files (``bytes``, what ``image.save("x.jpg")`` would write — byte-identical
+        to Pillow's encoder at ``jpeg_quality``), encoded on the GPU: ~0.1-0.3 MB instead of 3 MB per image cross PCIe and the host
+        does no pixel work at all.
 
         The host side is pipelined: while the GPU runs micro-batch *i* (one CUDA-graph replay), the host converts the outputs of
         micro-batch *i-1* to PIL images and stages the inputs of *i+1* (pinned buffers, asynchronous copies)."""
@@ -290,6 +294,8 @@ class FastEditor:
             seeds = [seed] * n
         if len(seeds) != n:
             raise ValueError("edit_many: seeds must have one entry per image")
+        if output not in ("pil", "jpeg"):
+            raise ValueError("edit_many: output must be 'pil' or 'jpeg'")
         n_exec = self._executed_steps(strength, num_inference_steps)
         mb = int(micro_batch or self.MICRO_BATCH)
         lo, hi = int(np.floor(canny_low_threshold)), int(np.floor(canny_high_threshold))
@@ -303,6 +309,16 @@ class FastEditor:
             def finalize(p):
                 idx, host_out, ev = p
                 ev.synchronize()
+                if output == "jpeg":
+                    files, sizes, files_d = host_out
+                    for j, i in enumerate(idx):
+                        n_ = int(sizes[j])
+                        if n_ <= files.shape[1]:
+                            results[i] = files[j, :n_].numpy().tobytes()
+                        else:                                      # larger than the copied prefix: fetch this one file exactly
+                            results[i] = files_d[j, :n_].cpu().numpy().tobytes()
+                        self._jpeg_prefix = min(files_d.shape[1], max(self._jpeg_prefix, -(-(n_ * 5 // 4) // 65536) * 65536))
+                    return
                 for j, i in enumerate(idx):
                     results[i] = Image.fromarray(host_out[j].numpy().copy())
 
@@ -329,7 +345,24 @@ class FastEditor:
                 out = self._engine.edit_batch(d_img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
                                               guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
                                               canny_low=lo, canny_high=hi, canny_blur=canny_gaussian_blur)
-                host_out[:nb].copy_(out.images[:nb], non_blocking=True)
+                if output == "jpeg":
+                    # Encode on the GPU.  The file sizes are not known on the host yet, so a prefix of every file buffer is copied whose
+                    # length adapts to the largest file seen so far (+25 %, starting at 1/8 of the worst case); a file that does not
+                    # fit is fetched exactly in finalize().
+                    files_d, sizes_d = ops.jpeg_encode(out.images[:nb], jpeg_quality)
+                    pre = min(files_d.shape[1], self.__dict__.setdefault("_jpeg_prefix", max(files_d.shape[1] // 8, 1 << 16)))
+                    key = ("jpeg", k & 1, nb, pre)
+                    pinned = self.__dict__.setdefault("_pinned", {})
+                    if key not in pinned:
+                        for old in [q for q in pinned if isinstance(q, tuple) and q[:2] == key[:2]]:
+                            del pinned[old]
+                        pinned[key] = (torch.empty((nb, pre), dtype=torch.uint8).pin_memory(), torch.empty((nb,), dtype=torch.int32).pin_memory())
+                    hf, hs = pinned[key]
+                    hf.copy_(files_d[:, :pre], non_blocking=True)
+                    hs.copy_(sizes_d, non_blocking=True)
+                    host_out = (hf, hs, files_d)
+                else:
+                    host_out[:nb].copy_(out.images[:nb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 if pending is not None:

@@ -142,6 +142,41 @@ def gaussian_blur5(img_u8: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_JPEG_WS = {}
+
+
+def jpeg_encode(img_u8: torch.Tensor, quality: int = 75):
+    """uint8 [N,H,W,3] (CUDA) -> (uint8 [N, stride] buffer of N JPEG files, int32 [N] file sizes), byte-identical to
+    ``PIL.Image.fromarray(img).save(f, "JPEG", quality=quality)`` (baseline, 4:2:0).  See :func:`jpeg_bytes` for the host side."""
+    _req(img_u8, torch.uint8, "jpeg_encode")
+    n, h, w, c = img_u8.shape
+    if c != 3:
+        raise _lib.FieError("jpeg_encode: RGB images expected")
+    L = _lib.lib()
+    stride = L.fie_jpeg_max_bytes(h, w)
+    nbytes = L.fie_jpeg_workspace_bytes(n, h, w)
+    key = (str(img_u8.device), n, h, w)
+    ws = _JPEG_WS.get(key)
+    if ws is None:
+        _JPEG_WS.clear()
+        ws = _JPEG_WS[key] = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=img_u8.device)
+    out = torch.empty((n, stride), dtype=torch.uint8, device=img_u8.device)
+    sizes = torch.empty((n,), dtype=torch.int32, device=img_u8.device)
+    with _prof("jpeg_encode", float(img_u8.numel()), "B"):
+        check(L.fie_jpeg_encode_u8(_p(img_u8), n, h, w, int(quality), _p(out), stride, _p(sizes), _p(ws), nbytes, _stream()), "fie_jpeg_encode_u8")
+    _count(7)
+    return out, sizes
+
+
+def jpeg_bytes(img_u8: torch.Tensor, quality: int = 75):
+    """-> list of N ``bytes`` objects (the JPEG files).  Two small D2H copies: the sizes, then only the used prefix of the buffer."""
+    out, sizes = jpeg_encode(img_u8, quality)
+    sz = sizes.cpu().tolist()
+    m = max(sz) if sz else 0
+    host = out[:, :m].cpu().numpy()
+    return [host[i, :sz[i]].tobytes() for i in range(len(sz))]
+
+
 _RS_TABLES = {}
 
 

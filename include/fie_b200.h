@@ -48,6 +48,19 @@ int fie_canny_u8(const void* img, void* edges, int n, int h, int w, int in_chann
 int fie_rgb_to_gray_u8(const void* rgb, void* gray, int n, int h, int w, void* stream);
 int fie_gaussian_blur5_u8(const void* src, void* dst, int n, int h, int w, int channels, void* stream);
 
+/* ---- Baseline JPEG encode: replaces `edited.save(output_path)` (PIL -> libjpeg) at reference run_batch.py:224 /
+ * run_single_image.py:114 ----
+ * rgb: uint8 [n,h,w,3] on the device -> n complete JPEG files (JFIF, baseline sequential, 4:2:0, Annex K Huffman tables, `quality` as in
+ * libjpeg / Pillow; default 75), image i at out + i * out_stride with its byte length in out_sizes[i] (device int32).  BYTE-IDENTICAL to
+ * Pillow's Image.save(f, "JPEG", quality=quality) for the same pixels.  Integer only.  out_stride >= fie_jpeg_max_bytes(h, w);
+ * workspace: fie_jpeg_workspace_bytes(n, h, w), 256-byte aligned.  fie_jpeg_write_header writes the 623 header bytes (host memory). */
+int    fie_jpeg_header_bytes(void);
+int    fie_jpeg_write_header(unsigned char* dst, int h, int w, int quality);
+size_t fie_jpeg_workspace_bytes(int n, int h, int w);
+size_t fie_jpeg_max_bytes(int h, int w);
+int    fie_jpeg_encode_u8(const void* rgb, int n, int h, int w, int quality, void* out, size_t out_stride, int* out_sizes,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Lanczos resize: replaces image.resize((1024, 1024), Image.LANCZOS) at reference src/pipeline.py:251 ----
  * uint8 [n,h,w,3] -> uint8 [n,oh,ow,3], bit-identical to Pillow: a horizontal then a vertical fixed-point pass (a pass is skipped when
  * that size does not change).  bounds_* int32 [out,2] = (first input index, count), coeff_* int32 [out,ksize] = 2^22 fixed-point

@@ -60,6 +60,8 @@ def build_parser():
     # extensions of the B200 build
     p.add_argument("--micro_batch", type=int, default=8, help="images per GPU per engine call (FastEditor.edit_many)")
     p.add_argument("--io_threads", type=int, default=4, help="host threads for JPEG decode / encode")
+    p.add_argument("--no_gpu_jpeg", action="store_true", help="encode *.jpg outputs with PIL on the host instead of the GPU encoder "
+                   "(the files are byte-identical either way)")
     add_checkpoint_args(p)
     return p
 
@@ -154,7 +156,14 @@ def main(argv=None):
 
     def save(img, item, source_img):
         os.makedirs(os.path.dirname(item[3]), exist_ok=True)
-        img.save(item[3])
+        if isinstance(img, (bytes, bytearray)):        # already a JPEG file, encoded on the GPU (byte-identical to PIL's encoder)
+            with open(item[3], "wb") as f:
+                f.write(img)
+            if args.save_comparisons:
+                import io
+                img = Image.open(io.BytesIO(img)).convert("RGB")
+        else:
+            img.save(item[3])
         if args.save_comparisons:
             from run_single_image import _save_plot
             cp = os.path.join(comparisons_dir, item[1]["image_path"].replace(".jpg", ".png"))
@@ -185,7 +194,9 @@ def main(argv=None):
             continue
         t0 = time.time()
         try:
-            outs = editor.edit_many(imgs, [it[1]["editing_prompt"] for it in items], seed=args.seed, micro_batch=mb, **edit_kw)
+            as_jpeg = (not args.no_gpu_jpeg) and all(it[3].lower().endswith((".jpg", ".jpeg")) for it in items)
+            outs = editor.edit_many(imgs, [it[1]["editing_prompt"] for it in items], seed=args.seed, micro_batch=mb,
+                                    **({"output": "jpeg"} if as_jpeg else {}), **edit_kw)
         except Exception as e:   # per-image isolation, as the reference (run_batch.py:250-261): retry the group image by image
             print(f"\n      Batch of {len(items)} failed ({type(e).__name__}: {e}); retrying per image")
             outs = []

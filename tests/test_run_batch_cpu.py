@@ -12,7 +12,7 @@ class FakeEditor:
     instances = []
 
     def __init__(self, **kw):
-        self.kw, self.batches, self.singles = kw, [], []
+        self.kw, self.batches, self.singles, self.outputs = kw, [], [], []
         self.fail_batch_with = None
         self.fail_prompt = None
         FakeEditor.instances.append(self)
@@ -21,7 +21,17 @@ class FakeEditor:
         self.batches.append(list(prompts))
         if self.fail_batch_with is not None and any(self.fail_batch_with in p for p in prompts):
             raise RuntimeError("boom (batch)")
-        return [Image.new("RGB", (1024, 1024), (i, 0, 0)) for i, _ in enumerate(images)]
+        outs = [Image.new("RGB", (1024, 1024), (i, 0, 0)) for i, _ in enumerate(images)]
+        self.outputs.append(kw.get("output", "pil"))
+        if kw.get("output") == "jpeg":                    # the GPU encoder's contract: the bytes PIL's own save() would write
+            import io
+            files = []
+            for o in outs:
+                b = io.BytesIO()
+                o.save(b, "JPEG")
+                files.append(b.getvalue())
+            return files
+        return outs
 
     def edit(self, image, prompt, **kw):
         self.singles.append(prompt)
@@ -100,3 +110,11 @@ def test_selection_filters(monkeypatch, dataset):
     assert sum(len(b) for b in ed.batches) == 3
     ed, _ = _run(monkeypatch, dataset, extra=["--image_ids", "002", "007"])
     assert ed.batches == [["prompt 2", "prompt 7"]]
+
+
+def test_jpg_outputs_are_written_from_gpu_encoded_bytes(monkeypatch, dataset):
+    ed, outdir = _run(monkeypatch, dataset)
+    assert set(ed.outputs) == {"jpeg"}                                               # *.jpg targets: files arrive already encoded
+    assert Image.open(outdir / "a" / "img03.jpg").size == (1024, 1024)
+    ed, _ = _run(monkeypatch, dataset, extra=["--no_gpu_jpeg"])
+    assert set(ed.outputs) == {"pil"}
