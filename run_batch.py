@@ -60,6 +60,7 @@ def build_parser():
     # extensions of the B200 build
     p.add_argument("--micro_batch", type=int, default=8, help="images per GPU per engine call (FastEditor.edit_many)")
     p.add_argument("--io_threads", type=int, default=4, help="host threads for JPEG decode / encode")
+    p.add_argument("--summary_json", type=str, default=None, help="rank 0 writes the run's counters and timings here (sweep benchmarks)")
     p.add_argument("--no_gpu_jpeg", action="store_true", help="encode *.jpg outputs with PIL on the host instead of the GPU encoder "
                    "(the files are byte-identical either way)")
     add_checkpoint_args(p)
@@ -240,6 +241,12 @@ def main(argv=None):
         say(f"Total time: {wall:.2f}s ({wall / 60:.1f} minutes) on {world} GPU(s)")
     else:
         say("\nWARNING: No images were successfully processed!")
+    if args.summary_json and rank == 0:
+        with open(args.summary_json, "w") as f:
+            json.dump({"model": args.model, "world": world, "processed": processed_all, "skipped": skipped_all, "failed": failed_all,
+                       "seconds_edit_max_over_ranks": wall, "seconds_edit_sum_over_ranks": time_all,
+                       "images_per_s": processed_all / wall if wall > 0 else None, "micro_batch": mb, "gpu_jpeg": not args.no_gpu_jpeg,
+                       "strength": args.strength, "steps": args.steps, "guidance": args.guidance}, f)
     say(f"\nOutputs saved to:\n  - Edited images: {edited_dir}")
     editor.clear_memory()
     say("\nDone!")
