@@ -2,12 +2,13 @@
 // (aperture 3, L1 gradient, no blur) as called by the reference at src/pipeline.py:200,205.
 //
 // Stages (all integer):
-//   k_gray      u8 RGB -> u8 gray, 15-bit fixed point (4 px / thread, 3x32-bit loads -> 1x32-bit store)
-//   k_nms       gray tile + 2-px halo staged in shared memory -> Sobel (replicate border), L1 magnitude
-//               (0 outside the image), integer-tangent NMS, double threshold -> state {0,1 weak,2 strong}
-//               and union-find parent init (strong pixels get the smaller label so they win the root)
-//   k_union     lock-free union-find over 8-connected candidate pixels (atomicMin on roots)
+//   k_nms       RGB (-> gray on the fly, 15-bit fixed point) tile + 2-px halo staged in shared memory -> Sobel (replicate border), L1 magnitude
+//               (0 outside the image), integer-tangent NMS, double threshold -> state {0,1 weak,2 strong}; then the connected components
+//               of the candidates INSIDE the 64 x 32 tile by a lock-free union-find in shared memory (strong pixels get the smaller
+//               label so they win the root); global memory receives depth-1 trees (parent = the tile-local root)
+//   k_seams     global lock-free union-find (atomicMin on roots), but only over the pixel pairs that straddle a tile seam
 //   k_finalize  edge = candidate whose root is a strong pixel -> 0/255 (optionally replicated x3)
+//   (k_gray     RGB -> gray as a separate plane: only for the optional Gaussian pre-stage / fie_rgb_to_gray_u8)
 // The hysteresis result is the unique closure of strong pixels through candidates, so the union-find
 // formulation is bit-exact with OpenCV's stack-based flood fill without any host round trip.
 #include "fie_common.cuh"
@@ -43,20 +44,46 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ rgb, u
     }
 }
 
-constexpr int TW = 64, TH = 16;   // output tile per CTA (256 threads, 4 px each)
+constexpr int TW = 64, TH = 32;   // output tile per CTA (256 threads, 8 px each)
 
-__global__ void __launch_bounds__(256) k_nms(const uint8_t* __restrict__ gray, uint8_t* __restrict__ state,
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* P, uint32_t idx) {
+    uint32_t v = ((volatile const uint32_t*)P)[idx];
+    while ((v & kIdxMask) != idx) { idx = v & kIdxMask; v = ((volatile const uint32_t*)P)[idx]; }
+    return v;   // root's label value (strong roots have kWeakBit clear)
+}
+__device__ __forceinline__ void uf_union(uint32_t* P, uint32_t i, uint32_t j) {
+    uint32_t a = uf_find(P, i), b = uf_find(P, j);
+    while ((a & kIdxMask) != (b & kIdxMask)) {
+        if (a > b) { uint32_t t = a; a = b; b = t; }
+        uint32_t old = atomicMin(&P[b & kIdxMask], a);
+        if (old == b) break;
+        b = uf_find(P, old & kIdxMask);
+        a = uf_find(P, a & kIdxMask);
+    }
+}
+
+// Tile kernel: (RGB -> gray on the fly, IN_CH = 3) -> Sobel / L1 magnitude / integer-tangent NMS / double threshold, then the connected
+// components of the candidates INSIDE the tile by a lock-free union-find in shared memory (strong pixels carry the smaller label, so a
+// component's root is strong iff the component contains a strong pixel).  Global memory only sees the dense state byte and, for candidates,
+// parent[pixel] = the global index of the tile-local root (+ weak bit): every tile-local component leaves as a depth-1 tree, and the global
+// union-find (k_seams) only has to join components across tile seams.
+template <int IN_CH>
+__global__ void __launch_bounds__(256) k_nms(const uint8_t* __restrict__ src, uint8_t* __restrict__ state,
                                              uint32_t* __restrict__ parent, int H, int W, int low, int high) {
     __shared__ uint8_t  sg[TH + 4][TW + 4 + 4];
     __shared__ int16_t  sdx[TH + 2][TW + 2], sdy[TH + 2][TW + 2], smg[TH + 2][TW + 2];
+    __shared__ uint32_t slab[TH * TW];           // local union-find: label = local index | weak bit
+    __shared__ uint8_t  sst[TH * TW];
     const int img = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const uint8_t* g = gray + (size_t)img * H * W;
+    const uint8_t* g = src + (size_t)img * H * W * IN_CH;
     const int tid = threadIdx.x;
     for (int i = tid; i < (TH + 4) * (TW + 4); i += 256) {
         int ly = i / (TW + 4), lx = i % (TW + 4);
         int y = min(max(y0 + ly - 2, 0), H - 1), x = min(max(x0 + lx - 2, 0), W - 1);   // BORDER_REPLICATE
-        sg[ly][lx] = __ldg(g + (size_t)y * W + x);
+        const uint8_t* p = g + ((size_t)y * W + x) * IN_CH;
+        if (IN_CH == 3) sg[ly][lx] = (uint8_t)((9798u * __ldg(p) + 19235u * __ldg(p + 1) + 3735u * __ldg(p + 2) + 16384u) >> 15);   // cv2 RGB2GRAY
+        else sg[ly][lx] = __ldg(p);
     }
     __syncthreads();
     for (int i = tid; i < (TH + 2) * (TW + 2); i += 256) {
@@ -79,57 +106,83 @@ __global__ void __launch_bounds__(256) k_nms(const uint8_t* __restrict__ gray, u
     for (int i = tid; i < TH * TW; i += 256) {
         int ly = i / TW, lx = i % TW;
         int y = y0 + ly, x = x0 + lx;
-        if (y >= H || x >= W) continue;
-        int cy = ly + 1, cx = lx + 1;
-        int m = smg[cy][cx];
         uint8_t s = 0;
-        if (m > low) {
-            int dx = sdx[cy][cx], dy = sdy[cy][cx];
-            int ax = abs(dx), ay = abs(dy) << 15;          // <= 1020<<15 < 2^31
-            int t22 = ax * TG22;                           // <= 1020*13573 < 2^31
-            long long t67 = (long long)t22 + ((long long)ax << 16);
-            bool keep;
-            if (ay < t22) keep = m > smg[cy][cx - 1] && m >= smg[cy][cx + 1];
-            else if ((long long)ay > t67) keep = m > smg[cy - 1][cx] && m >= smg[cy + 1][cx];
-            else { int sg_ = ((dx ^ dy) < 0) ? -1 : 1; keep = m > smg[cy - 1][cx - sg_] && m > smg[cy + 1][cx + sg_]; }
-            if (keep) s = (m > high) ? 2 : 1;
+        if (y < H && x < W) {
+            int cy = ly + 1, cx = lx + 1;
+            int m = smg[cy][cx];
+            if (m > low) {
+                int dx = sdx[cy][cx], dy = sdy[cy][cx];
+                int ax = abs(dx), ay = abs(dy) << 15;          // <= 1020<<15 < 2^31
+                int t22 = ax * TG22;                           // <= 1020*13573 < 2^31
+                long long t67 = (long long)t22 + ((long long)ax << 16);
+                bool keep;
+                if (ay < t22) keep = m > smg[cy][cx - 1] && m >= smg[cy][cx + 1];
+                else if ((long long)ay > t67) keep = m > smg[cy - 1][cx] && m >= smg[cy + 1][cx];
+                else { int sg_ = ((dx ^ dy) < 0) ? -1 : 1; keep = m > smg[cy - 1][cx - sg_] && m > smg[cy + 1][cx + sg_]; }
+                if (keep) s = (m > high) ? 2 : 1;
+            }
         }
-        size_t o = (size_t)img * H * W + (size_t)y * W + x;
+        sst[i] = s;
+        slab[i] = (uint32_t)i | (s == 2 ? 0u : kWeakBit);
+    }
+    __syncthreads();
+    // tile-local unions with the W, NW, N, NE neighbours (each 8-connected pair once)
+    for (int i = tid; i < TH * TW; i += 256) {
+        if (!sst[i]) continue;
+        const int ly = i / TW, lx = i % TW;
+        if (lx > 0 && sst[i - 1]) uf_union(slab, i, i - 1);
+        if (ly > 0) {
+            if (lx > 0 && sst[i - TW - 1]) uf_union(slab, i, i - TW - 1);
+            if (sst[i - TW]) uf_union(slab, i, i - TW);
+            if (lx < TW - 1 && sst[i - TW + 1]) uf_union(slab, i, i - TW + 1);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * TW; i += 256) {
+        const int ly = i / TW, lx = i % TW;
+        const int y = y0 + ly, x = x0 + lx;
+        if (y >= H || x >= W) continue;
+        const size_t o = (size_t)img * H * W + (size_t)y * W + x;
+        const uint8_t s = sst[i];
         state[o] = s;
-        if (s) parent[o] = (uint32_t)(y * W + x) | (s == 2 ? 0u : kWeakBit);
+        if (s) {
+            const uint32_t r = uf_find(slab, (uint32_t)i);            // root label: local index | weak bit of the whole local component
+            const uint32_t rl = r & kIdxMask;
+            parent[o] = (uint32_t)((y0 + (int)(rl / TW)) * W + x0 + (int)(rl % TW)) | (r & kWeakBit);
+        }
     }
 }
 
-__device__ __forceinline__ uint32_t uf_find(const uint32_t* P, uint32_t idx) {
-    uint32_t v = ((volatile const uint32_t*)P)[idx];
-    while ((v & kIdxMask) != idx) { idx = v & kIdxMask; v = ((volatile const uint32_t*)P)[idx]; }
-    return v;   // root's label value (strong roots have kWeakBit clear)
-}
-__device__ __forceinline__ void uf_union(uint32_t* P, uint32_t i, uint32_t j) {
-    uint32_t a = uf_find(P, i), b = uf_find(P, j);
-    while ((a & kIdxMask) != (b & kIdxMask)) {
-        if (a > b) { uint32_t t = a; a = b; b = t; }
-        uint32_t old = atomicMin(&P[b & kIdxMask], a);
-        if (old == b) break;
-        b = uf_find(P, old & kIdxMask);
-        a = uf_find(P, a & kIdxMask);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_union(const uint8_t* __restrict__ state, uint32_t* __restrict__ parent, int H, int W) {
-    const int img = blockIdx.z;
-    int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= W || y >= H) return;
+// Joins the tile-local components across the tile seams (global lock-free union-find on the per-image parent array): one thread per
+// pixel on the left side of a vertical seam or the upper side of a horizontal seam, united with its up-to-three candidate neighbours on
+// the other side.  Every 8-connected pair that straddles a seam is covered exactly once.
+__global__ void __launch_bounds__(256) k_seams(const uint8_t* __restrict__ state, uint32_t* __restrict__ parent, int H, int W) {
+    const int img = blockIdx.y;
+    const int nvs = (W - 1) / TW, nhs = (H - 1) / TH;               // vertical / horizontal seams inside the image
+    const long long nv = (long long)nvs * H, nh = (long long)nhs * W;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nv + nh) return;
     const uint8_t* s = state + (size_t)img * H * W;
     uint32_t* P = parent + (size_t)img * H * W;
-    if (!s[(size_t)y * W + x]) return;
-    uint32_t me = y * W + x;
-    if (x > 0 && s[(size_t)y * W + x - 1]) uf_union(P, me, me - 1);
-    if (y > 0) {
-        const uint8_t* r = s + (size_t)(y - 1) * W;
-        if (x > 0 && r[x - 1]) uf_union(P, me, me - W - 1);
-        if (r[x]) uf_union(P, me, me - W);
-        if (x < W - 1 && r[x + 1]) uf_union(P, me, me - W + 1);
+    if (t < nv) {
+        const int k = (int)(t / H) + 1, y = (int)(t % H);
+        const int x = k * TW - 1;                                   // left pixel; neighbours at column x + 1
+        if (!s[(size_t)y * W + x]) return;
+        const uint32_t me = (uint32_t)(y * W + x);
+        for (int d = -1; d <= 1; ++d) {
+            const int yy = y + d;
+            if (yy >= 0 && yy < H && s[(size_t)yy * W + x + 1]) uf_union(P, me, (uint32_t)(yy * W + x + 1));
+        }
+    } else {
+        const long long u = t - nv;
+        const int k = (int)(u / W) + 1, x = (int)(u % W);
+        const int y = k * TH - 1;                                   // upper pixel; neighbours in row y + 1
+        if (!s[(size_t)y * W + x]) return;
+        const uint32_t me = (uint32_t)(y * W + x);
+        for (int d = -1; d <= 1; ++d) {
+            const int xx = x + d;
+            if (xx >= 0 && xx < W && s[(size_t)(y + 1) * W + xx]) uf_union(P, me, (uint32_t)((y + 1) * W + xx));
+        }
     }
 }
 
@@ -232,17 +285,13 @@ extern "C" int fie_canny_u8(const void* img, void* edges, int n, int h, int w, i
     uint8_t* gray = (uint8_t*)workspace;
     uint8_t* state = gray + pxr;
     uint32_t* parent = (uint32_t*)(state + pxr);
-    const uint8_t* g = (const uint8_t*)img;
-    if (in_channels == 3) {
-        long long n4 = (long long)((px + 3) / 4);
-        int blocks = (int)((n4 + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-        k_gray<<<blocks, 256, 0, stream>>>((const uint8_t*)img, gray, n4, (long long)px);
-        g = gray;
-    }
+    (void)gray;                                   // (the gray plane is no longer materialised: k_nms<3> converts on the fly)
     dim3 g1(ceil_div(w, TW), ceil_div(h, TH), n);
-    k_nms<<<g1, 256, 0, stream>>>(g, state, parent, h, w, low, high);
+    if (in_channels == 3) k_nms<3><<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
+    else k_nms<1><<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
+    const long long seam_px = (long long)((w - 1) / TW) * h + (long long)((h - 1) / TH) * w;
+    if (seam_px > 0) k_seams<<<dim3((unsigned)((seam_px + 255) / 256), n), 256, 0, stream>>>(state, parent, h, w);
     dim3 g2(ceil_div(w, 64), ceil_div(h, 4), n);
-    k_union<<<g2, 256, 0, stream>>>(state, parent, h, w);
     k_finalize<<<g2, 256, 0, stream>>>(state, parent, (uint8_t*)edges, h, w, out_channels);
     return check_launch("fie_canny_u8");
 }

@@ -7,6 +7,7 @@
 //   LayerNorm: one warp per row, row kept in registers, two-pass mean / variance in fp32.
 // Replaces F.group_norm / F.silu / F.layer_norm in diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock.
 #include "fie_common.cuh"
+#include <stdlib.h>
 
 namespace fie {
 
@@ -127,6 +128,90 @@ __global__ void __launch_bounds__(512, 2) k_gn_apply(GNArgs a) {
     for (; r < r1; r += step) dst[r * a.cv] = apply(__ldg(src + r * stride));
 }
 
+// ---- Single-pass GroupNorm for slabs that fit in shared memory (the UNet / ControlNet norms: 10..80 channels per group over
+// 1024..16384 pixels = 80 KB .. 1.3 MB per (image, group)) ----
+// One thread-block CLUSTER per (image, group): each CTA loads its share of the group's rows into shared memory ONCE (one global read),
+// the cluster reduces the mean and then the centred sum of squares over distributed shared memory (two-pass variance: no E[x^2] - mean^2
+// cancellation, deterministic, independent of the batch size), and every CTA normalises its rows out of shared memory (one global
+// write).  Replaces memset + k_gn_stats + k_gn_apply (two reads, one write, integer atomics) for these shapes, whose channel counts per
+// group (10, 20, 30, 40, 60, 80) do not fit the producer-epilogue statistics either.
+struct GNSlabArgs {
+    const __half2* x0; const __half2* x1; __half2* out;
+    int c0h, c1h, ch;          // channel PAIRS per source / total
+    int cpgh;                  // channel pairs per group
+    long long hw; int rows_per_cta;
+    const float* gamma; const float* beta; float eps; int silu;
+};
+
+__device__ __forceinline__ float cluster_sum(float v, float* slots /* [32 warps + 8 ranks] */, int nranks, uint32_t rank) {
+    // CTA reduction (warp shuffles + shared memory), then every rank reads all ranks' partials over DSMEM in rank order
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) slots[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float t = lane < nw ? slots[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) slots[32 + rank] = t;           // this CTA's partial, published at slot 32 + own rank
+    }
+    if (nranks == 1) { __syncthreads(); return slots[32 + rank]; }
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    float tot = 0.f;
+    for (int r = 0; r < nranks; ++r) {
+        uint32_t remote; float pv;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(&slots[32 + r])), "r"(r));
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(pv) : "r"(remote) : "memory");
+        tot += pv;
+    }
+    // the partial slots are rewritten by the next reduction: nobody may still be reading them
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    return tot;
+}
+
+__global__ void __launch_bounds__(512, 1) k_gn_slab(GNSlabArgs a, int nranks) {
+    extern __shared__ __align__(16) uint8_t gn_smem[];
+    __shared__ float slots[48];
+    __half2* slab = reinterpret_cast<__half2*>(gn_smem);              // [rows_per_cta][cpgh]
+    uint32_t rank = 0;
+    if (nranks > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int group = blockIdx.x / nranks, img = blockIdx.y;
+    const long long r0 = (long long)rank * a.rows_per_cta;
+    const long long r1 = min(r0 + (long long)a.rows_per_cta, a.hw);
+    const int nrows = (int)max(r1 - r0, 0ll);
+    const int items = nrows * a.cpgh;
+    const int cbase = group * a.cpgh;                                   // first channel pair of the group
+    // ---- load: item = (row, channel pair); consecutive threads walk a row's pairs, then the next row ----
+    float s = 0.f;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int r = i / a.cpgh, c = cbase + (i - r * a.cpgh);
+        const long long row = (long long)img * a.hw + r0 + r;
+        const __half2 v = c < a.c0h ? __ldg(a.x0 + row * a.c0h + c) : __ldg(a.x1 + row * a.c1h + (c - a.c0h));
+        slab[i] = v;
+        const float2 f = __half22float2(v);
+        s += f.x + f.y;
+    }
+    const float cnt = (float)a.hw * (float)(2 * a.cpgh);
+    const float mean = cluster_sum(s, slots, nranks, rank) / cnt;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const float2 f = __half22float2(slab[i]);
+        const float d0 = f.x - mean, d1 = f.y - mean;
+        q = fmaf(d0, d0, fmaf(d1, d1, q));
+    }
+    const float var = cluster_sum(q, slots, nranks, rank) / cnt;
+    const float rstd = rsqrtf(var + a.eps);
+    // ---- apply from shared memory ----
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int r = i / a.cpgh, cl = i - r * a.cpgh, c = cbase + cl;
+        const float2 f = __half22float2(slab[i]);
+        const float2 ga = __ldg(reinterpret_cast<const float2*>(a.gamma) + c), be = __ldg(reinterpret_cast<const float2*>(a.beta) + c);
+        float y0 = fmaf((f.x - mean) * rstd, ga.x, be.x), y1 = fmaf((f.y - mean) * rstd, ga.y, be.y);
+        if (a.silu) silu2(y0, y1);
+        a.out[((long long)img * a.hw + r0 + r) * a.ch + c] = __floats2half2_rn(y0, y1);
+    }
+}
+
 // ---- LayerNorm: a warp owns a strided set of rows; gamma / beta live in shared memory (one global read per CTA instead of
 // four 128-bit loads per data vector and row), and the next row is already in flight while the current one is reduced ----
 template <int MAXV>
@@ -199,6 +284,39 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
     FIE_REQUIRE(n > 0 && n <= 65535 && hw > 0 && c0 > 0 && (c0 % 8) == 0 && (c1 % 8) == 0, "fie_groupnorm_f16: channels must be multiples of 8");
     FIE_REQUIRE(groups > 0 && groups <= 64 && (c % groups) == 0, "fie_groupnorm_f16: bad groups");
     FIE_REQUIRE(c / 8 <= 512, "fie_groupnorm_f16: too many channels (%d)", c);
+    // single-pass cluster kernel: the group's slab of every image fits in the shared memory of <= 8 CTAs (UNet / ControlNet norms)
+    {
+        static int slab_mode = -1;                      // FIE_GN_SLAB=0: always the two-kernel path
+        if (slab_mode < 0) { const char* e = getenv("FIE_GN_SLAB"); slab_mode = e ? atoi(e) : 1; }
+        const int cpg = c / groups;
+        const long long slab_bytes = hw * cpg * 2;
+        constexpr long long kCtaBytes = 192 * 1024;
+        if (slab_mode && !stats_ready && (cpg % 2) == 0 && (c0 % 2) == 0 && (c1 % 2) == 0 && slab_bytes <= 8 * kCtaBytes && hw >= 64 &&
+            ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 7) == 0) {
+            int nranks = 1; while ((long long)nranks * kCtaBytes < slab_bytes) nranks <<= 1;
+            GNSlabArgs g;
+            g.x0 = (const __half2*)x0; g.x1 = (const __half2*)x1; g.out = (__half2*)out;
+            g.c0h = c0 / 2; g.c1h = c1 / 2; g.ch = c / 2; g.cpgh = cpg / 2; g.hw = hw;
+            g.rows_per_cta = (int)((hw + nranks - 1) / nranks);
+            g.gamma = gamma; g.beta = beta; g.eps = eps; g.silu = fuse_silu;
+            const size_t smem = (size_t)g.rows_per_cta * g.cpgh * sizeof(__half2);
+            static bool attr_dev[kMaxDevices] = {false};
+            bool& attr = attr_dev[current_device()];
+            if (!attr) {
+                cudaError_t e = cudaFuncSetAttribute(k_gn_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtaBytes + 1024);
+                if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gn_slab): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+                attr = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(groups * nranks), (unsigned)n); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nranks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_gn_slab, g, nranks);
+            if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_gn_slab): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
+            return check_launch("fie_groupnorm_f16 (slab)");
+        }
+    }
     GNArgs a;
     a.x0 = (const uint4*)x0; a.x1 = (const uint4*)x1; a.out = (uint4*)out;
     a.c0v = c0 / 8; a.c1v = c1 / 8; a.cv = c / 8; a.hw = hw; a.groups = groups; a.cpg = c / groups;

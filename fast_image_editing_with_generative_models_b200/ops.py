@@ -114,7 +114,7 @@ def canny(img_u8: torch.Tensor, low: int = 100, high: int = 200, out_channels: i
     out = torch.empty((n, h, w, 3) if out_channels == 3 else (n, h, w), dtype=torch.uint8, device=img_u8.device)
     with _prof("canny", float(n) * h * w * (in_ch + out_channels), "B"):
         check(L.fie_canny_u8(_p(img_u8), _p(out), n, h, w, in_ch, out_channels, int(low), int(high), _p(ws), ws_bytes, _stream()), "fie_canny_u8")
-    _count(4 if in_ch == 3 else 3)
+    _count(3)
     return out
 
 

@@ -578,3 +578,29 @@ def test_attn_vae_large_logits_need_fp32_scores(cuda_dev):
     e16 = float((ops.attention_vae(q, k, vt, d ** -0.5, f32_scores=False).float() - ref).abs().max())
     print("large-logit VAE attention: max-abs error fp32 scores", e32, "fp16 scores", e16)
     assert e32 < 5e-3 and e32 <= e16
+
+
+@pytest.mark.parametrize("n,hw,c0,c1,silu", [(2, 1024, 1280, 0, True), (2, 1024, 1280, 1280, True), (2, 4096, 640, 0, False), (2, 4096, 1280, 640, True),
+                                             (2, 16384, 320, 0, True), (1, 16384, 640, 320, True), (2, 16384, 320, 320, True), (3, 1000, 320, 0, True),
+                                             (2, 16384, 512, 0, False)])
+def test_groupnorm_single_pass_cluster_kernel(cuda_dev, n, hw, c0, c1, silu, monkeypatch):
+    """k_gn_slab: the UNet / ControlNet norms (10..80 channels per group; concatenated skip sources whose boundary falls INSIDE a
+    group; clusters of 1, 2, 4 and 8 CTAs; a row count that does not divide by the cluster size) against fp32 torch, and against the
+    two-kernel path it replaces.  A large common offset checks the two-pass variance (no E[x^2] - mean^2 cancellation)."""
+    ops = _ops()
+    x0 = (_rand((n, hw, c0), cuda_dev, 40) * 1.5 + 0.3).half()
+    x1 = (_rand((n, hw, c1), cuda_dev, 41) * 0.7 - 0.2).half() if c1 else None
+    c = c0 + c1
+    gamma = _rand((c,), cuda_dev, 42) * 0.1 + 1
+    beta = _rand((c,), cuda_dev, 43) * 0.1
+    out = ops.groupnorm(x0, gamma, beta, 1e-5, silu, 32, x1)
+    xc = torch.cat([x0, x1], dim=-1) if c1 else x0
+    ref = F.group_norm(xc.float().permute(0, 2, 1), 32, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 1)
+    assert float((out.float() - ref).abs().max()) < 8e-3
+    assert torch.equal(out, ops.groupnorm(x0, gamma, beta, 1e-5, silu, 32, x1)), "must be deterministic"
+    # large mean, small spread: fp32 E[x^2] - mean^2 would lose the variance; the two-pass form does not
+    xo = (x0.float() * 0.05 + 60.0).half()
+    out_o = ops.groupnorm(xo, gamma[:c0], beta[:c0], 1e-5, False, 32)
+    ref_o = F.group_norm(xo.float().permute(0, 2, 1), 32, gamma[:c0], beta[:c0], 1e-5).permute(0, 2, 1)
+    assert float((out_o.float() - ref_o).abs().max()) < 2e-2
