@@ -322,7 +322,16 @@ class FastEditor:
                 for j, i in enumerate(idx):
                     results[i] = Image.fromarray(host_out[j].numpy().copy())
 
+            trace = getattr(self, "_trace", None)          # scripts/e2e_probe.py: host seconds per phase
+            import time as _time
+
+            def mark(name, t0):
+                if trace is not None:
+                    trace.append((name, _time.perf_counter() - t0))
+                return _time.perf_counter()
+
             for k, b0 in enumerate(range(0, n, mb)):
+                t_ = _time.perf_counter()
                 idx = list(range(b0, min(b0 + mb, n)))
                 nb = len(idx)
                 pad_to = mb if nb * 2 >= mb else 1 << (nb - 1).bit_length()       # ragged tail: reuse the full-size graph, or the next power of two
@@ -337,14 +346,18 @@ class FastEditor:
                 else:
                     parts = [self._to_device_1024(images[i]) for i in idx]
                     d_img = torch.cat(parts + [parts[-1]] * (pad_to - nb), 0)
+                t_ = mark("stage images (PIL->pinned->H2D)", t_)
                 pad = [idx[-1]] * (pad_to - nb)
                 pe, pl = self._encode_prompts([prompts[i] for i in idx + pad], [negs[i] for i in idx + pad])      # [B,2,77,D], [B,2,P]
+                t_ = mark("encode prompts (launch)", t_)
                 per_img = [self._draw_noises(seeds[i], n_exec) for i in idx]
                 per_img += [per_img[-1]] * (pad_to - nb)
                 noises = [torch.cat([p[d] for p in per_img], 0) for d in range(len(per_img[0]))]
+                t_ = mark("noise draws (launch)", t_)
                 out = self._engine.edit_batch(d_img, pe, pl, noises, strength=strength, num_inference_steps=num_inference_steps,
                                               guidance_scale=guidance_scale, controlnet_conditioning_scale=controlnet_conditioning_scale,
                                               canny_low=lo, canny_high=hi, canny_blur=canny_gaussian_blur)
+                t_ = mark("edit_batch (graph launch)", t_)
                 if output == "jpeg":
                     # Encode on the GPU.  The file sizes are not known on the host yet, so a prefix of every file buffer is copied whose
                     # length adapts to the largest file seen so far (+25 %, starting at 1/8 of the worst case); a file that does not
@@ -365,8 +378,10 @@ class FastEditor:
                     host_out[:nb].copy_(out.images[:nb], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
+                t_ = mark("D2H enqueue", t_)
                 if pending is not None:
                     finalize(pending)                    # host work of the previous micro-batch overlaps this one's GPU time
+                t_ = mark("finalize previous (wait + PIL)", t_)
                 pending = (idx, host_out, ev)
             if pending is not None:
                 finalize(pending)
