@@ -202,7 +202,7 @@ class FastEditor:
                 pooled_dim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
                 for t in todo:                                       # no text encoder: deterministic embeddings seeded by the text
                     e = S.synthetic_prompt(zlib.crc32(t.encode("utf-8")) % (1 << 30), ucfg.cross_attention_dim, pooled_dim)
-                    cache[t] = (e[0][1].to(dev, torch.float16), e[1][1].to(dev, torch.float16))
+                    cache[t] = tuple(v.to(torch.float16).pin_memory().to(dev, non_blocking=True) for v in (e[0][1], e[1][1]))   # (async: see text_encoder.forward)
         pe = torch.stack([torch.stack([cache[n][0], cache[p][0]]) for p, n in zip(prompts, negs)])
         pl = torch.stack([torch.stack([cache[n][1], cache[p][1]]) for p, n in zip(prompts, negs)])
         for t in list(negs) + list(prompts):
@@ -251,7 +251,7 @@ class FastEditor:
         """PIL image of any size -> uint8 [1,1024,1024,3] on the GPU; ``image.resize((1024, 1024), Image.LANCZOS)`` of the reference
         (src/pipeline.py:251) runs on the GPU, bit-identical to Pillow."""
         arr = np.ascontiguousarray(np.array(image.convert("RGB")))
-        img = torch.from_numpy(arr[None]).to(self._dev, non_blocking=True)
+        img = torch.from_numpy(arr[None]).pin_memory().to(self._dev, non_blocking=True)      # pinned staging: the copy does not block the host
         if img.shape[1] != self.OUT_SIZE or img.shape[2] != self.OUT_SIZE:
             img = ops.resize_lanczos(img, self.OUT_SIZE, self.OUT_SIZE)
         return img

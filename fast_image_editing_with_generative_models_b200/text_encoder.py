@@ -103,6 +103,10 @@ class CLIPTextEncoder:
         cfg = self.cfg
         b, t = ids.shape
         c, heads = cfg.hidden_size, cfg.num_heads
+        if not ids.is_cuda:
+            # through PyTorch's pinned-host cache, asynchronously: a pageable H2D copy would make the host wait for everything already
+            # queued on the stream (the previous micro-batch's whole edit) and serialise FastEditor.edit_many's pipeline
+            ids = ids.to(torch.int32).pin_memory().to(self.dev, non_blocking=True)
         ids = ids.to(self.dev)
         h = ops.embed_tokens(ids.to(torch.int32).contiguous(), self.tok, self.pos)          # [b*t, c]
         penultimate = h
