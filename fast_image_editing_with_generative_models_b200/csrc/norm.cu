@@ -8,6 +8,7 @@
 // Replaces F.group_norm / F.silu / F.layer_norm in diffusers ResnetBlock2D, Transformer2DModel, BasicTransformerBlock.
 #include "fie_common.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace fie {
 
@@ -169,46 +170,83 @@ __device__ __forceinline__ float cluster_sum(float v, float* slots /* [32 warps 
     return tot;
 }
 
-__global__ void __launch_bounds__(512, 1) k_gn_slab(GNSlabArgs a, int nranks) {
+// VEC = channel pairs per memory access (2: 64-bit accesses when the group width is a multiple of 4 channels, else 1: 32-bit).
+// Thread (rsub, v) owns vector v of the rows rsub, rsub + step, ...: UNROLL independent loads are in flight per thread (one CTA per SM:
+// the latency has to be covered by instruction-level parallelism, not by occupancy).
+template <int VEC>
+__global__ void __launch_bounds__(1024, 1) k_gn_slab(GNSlabArgs a, int nranks) {
     extern __shared__ __align__(16) uint8_t gn_smem[];
     __shared__ float slots[48];
-    __half2* slab = reinterpret_cast<__half2*>(gn_smem);              // [rows_per_cta][cpgh]
+    typedef typename std::conditional<VEC == 2, uint2, uint32_t>::type vec_t;
+    constexpr int UNROLL = 8;
+    vec_t* slab = reinterpret_cast<vec_t*>(gn_smem);                   // [rows_per_cta][vpr]
     uint32_t rank = 0;
     if (nranks > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const int group = blockIdx.x / nranks, img = blockIdx.y;
     const long long r0 = (long long)rank * a.rows_per_cta;
-    const long long r1 = min(r0 + (long long)a.rows_per_cta, a.hw);
-    const int nrows = (int)max(r1 - r0, 0ll);
-    const int items = nrows * a.cpgh;
-    const int cbase = group * a.cpgh;                                   // first channel pair of the group
-    // ---- load: item = (row, channel pair); consecutive threads walk a row's pairs, then the next row ----
+    const int nrows = (int)max(min(r0 + (long long)a.rows_per_cta, a.hw) - r0, 0ll);
+    const int vpr = a.cpgh / VEC;                                       // vectors per row of the group
+    const int step = blockDim.x / vpr;                                  // rows covered by the CTA per sweep
+    const int v = threadIdx.x % vpr, rsub = threadIdx.x / vpr;
+    const bool active = rsub < step;
+    const int c = group * a.cpgh + v * VEC;                             // first channel pair of this thread's vector
+    const bool first = c < a.c0h;                                       // (c0 is a multiple of 8 channels: a vector never straddles the sources)
+    const vec_t* src = first ? reinterpret_cast<const vec_t*>(a.x0 + ((long long)img * a.hw + r0) * a.c0h + c)
+                             : reinterpret_cast<const vec_t*>(a.x1 + ((long long)img * a.hw + r0) * a.c1h + (c - a.c0h));
+    const long long sstride = (first ? a.c0h : a.c1h) / VEC;            // row stride of the source in vectors
+    auto sum2 = [](vec_t u, float& s) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { const float2 f = __half22float2(h[j]); s += f.x + f.y; }
+    };
+    // ---- load (one global read) ----
     float s = 0.f;
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int r = i / a.cpgh, c = cbase + (i - r * a.cpgh);
-        const long long row = (long long)img * a.hw + r0 + r;
-        const __half2 v = c < a.c0h ? __ldg(a.x0 + row * a.c0h + c) : __ldg(a.x1 + row * a.c1h + (c - a.c0h));
-        slab[i] = v;
-        const float2 f = __half22float2(v);
-        s += f.x + f.y;
+    if (active) {
+        int r = rsub;
+        for (; r + (UNROLL - 1) * step < nrows; r += UNROLL * step) {
+            vec_t u[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) u[k] = __ldg(src + (long long)(r + k * step) * sstride);
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) { slab[(r + k * step) * vpr + v] = u[k]; sum2(u[k], s); }
+        }
+        for (; r < nrows; r += step) { const vec_t u = __ldg(src + (long long)r * sstride); slab[r * vpr + v] = u; sum2(u, s); }
     }
     const float cnt = (float)a.hw * (float)(2 * a.cpgh);
     const float mean = cluster_sum(s, slots, nranks, rank) / cnt;
     float q = 0.f;
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const float2 f = __half22float2(slab[i]);
-        const float d0 = f.x - mean, d1 = f.y - mean;
-        q = fmaf(d0, d0, fmaf(d1, d1, q));
-    }
+    if (active)
+        for (int r = rsub; r < nrows; r += step) {                       // own elements only: no barrier needed after the load loop
+            const vec_t u = slab[r * vpr + v];
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) { const float2 f = __half22float2(h[j]); const float d0 = f.x - mean, d1 = f.y - mean; q = fmaf(d0, d0, fmaf(d1, d1, q)); }
+        }
     const float var = cluster_sum(q, slots, nranks, rank) / cnt;
     const float rstd = rsqrtf(var + a.eps);
-    // ---- apply from shared memory ----
-    for (int i = threadIdx.x; i < items; i += blockDim.x) {
-        const int r = i / a.cpgh, cl = i - r * a.cpgh, c = cbase + cl;
-        const float2 f = __half22float2(slab[i]);
-        const float2 ga = __ldg(reinterpret_cast<const float2*>(a.gamma) + c), be = __ldg(reinterpret_cast<const float2*>(a.beta) + c);
-        float y0 = fmaf((f.x - mean) * rstd, ga.x, be.x), y1 = fmaf((f.y - mean) * rstd, ga.y, be.y);
-        if (a.silu) silu2(y0, y1);
-        a.out[((long long)img * a.hw + r0 + r) * a.ch + c] = __floats2half2_rn(y0, y1);
+    // ---- apply from shared memory (one global write): y = x * sc + sh ----
+    if (active) {
+        float sc[2 * VEC], sh[2 * VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            const float2 ga = __ldg(reinterpret_cast<const float2*>(a.gamma) + c + j), be = __ldg(reinterpret_cast<const float2*>(a.beta) + c + j);
+            sc[2 * j] = rstd * ga.x; sc[2 * j + 1] = rstd * ga.y;
+            sh[2 * j] = fmaf(-mean, sc[2 * j], be.x); sh[2 * j + 1] = fmaf(-mean, sc[2 * j + 1], be.y);
+        }
+        vec_t* dst = reinterpret_cast<vec_t*>(a.out + ((long long)img * a.hw + r0) * a.ch + c);
+        const long long dstride = a.ch / VEC;
+        for (int r = rsub; r < nrows; r += step) {
+            vec_t u = slab[r * vpr + v];
+            __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float2 f = __half22float2(h[j]);
+                float y0 = fmaf(f.x, sc[2 * j], sh[2 * j]), y1 = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+                if (a.silu) silu2(y0, y1);
+                h[j] = __floats2half2_rn(y0, y1);
+            }
+            dst[(long long)r * dstride] = u;
+        }
     }
 }
 
@@ -303,16 +341,19 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
             static bool attr_dev[kMaxDevices] = {false};
             bool& attr = attr_dev[current_device()];
             if (!attr) {
-                cudaError_t e = cudaFuncSetAttribute(k_gn_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtaBytes + 1024);
+                cudaError_t e = cudaFuncSetAttribute(k_gn_slab<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtaBytes + 1024);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gn_slab<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtaBytes + 1024);
                 if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_gn_slab): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
                 attr = true;
             }
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(groups * nranks), (unsigned)n); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+            cfg.gridDim = dim3((unsigned)(groups * nranks), (unsigned)n); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = nranks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            cudaError_t e = cudaLaunchKernelEx(&cfg, k_gn_slab, g, nranks);
+            // 64-bit accesses need 4-channel-aligned groups and sources (c0 % 8 == 0 is already required; c1 likewise)
+            const bool vec2 = (cpg % 4) == 0;
+            cudaError_t e = vec2 ? cudaLaunchKernelEx(&cfg, k_gn_slab<2>, g, nranks) : cudaLaunchKernelEx(&cfg, k_gn_slab<1>, g, nranks);
             if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_gn_slab): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
             return check_launch("fie_groupnorm_f16 (slab)");
         }
