@@ -310,8 +310,11 @@ __global__ void __launch_bounds__(256) k_layernorm(const uint4* __restrict__ x, 
     }
 }
 
+static int g_gn_slab_mode = -1;
 }  // namespace fie
 using namespace fie;
+
+extern "C" void fie_tune_groupnorm_slab(int max_cluster) { fie::g_gn_slab_mode = max_cluster < 0 ? 0 : (max_cluster > 8 ? 8 : max_cluster); }
 
 extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1, void* out, int n, long long hw, int groups,
                                  const float* gamma, const float* beta, float eps, int fuse_silu, void* stats_ws, int stats_ready, void* stream_) {
@@ -324,7 +327,11 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
     FIE_REQUIRE(c / 8 <= 512, "fie_groupnorm_f16: too many channels (%d)", c);
     // single-pass cluster kernel: the group's slab of every image fits in the shared memory of <= 8 CTAs (UNet / ControlNet norms)
     {
-        static int slab_mode = -1;                      // FIE_GN_SLAB=0: always the two-kernel path
+        // FIE_GN_SLAB = largest cluster size the single-pass kernel may use (0: always the two-kernel path).  Measured on B200
+        // (scripts/gn_bench.py, SDXL batch-8 shapes): with one CTA the slab kernel wins (82.6 -> 57.4 us on [16,1024,1280+640],
+        // 90 -> 75 us on [16,4096,640]); clusters of 4-8 CTAs (one CTA per SM, barrier-separated phases) LOSE against the streaming
+        // two-kernel path (309 -> 644 us on [16,16384,640+320]), so by default only slabs that fit one CTA take it.
+        int& slab_mode = g_gn_slab_mode;
         if (slab_mode < 0) { const char* e = getenv("FIE_GN_SLAB"); slab_mode = e ? atoi(e) : 1; }
         const int cpg = c / groups;
         const long long slab_bytes = hw * cpg * 2;
@@ -332,6 +339,7 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
         if (slab_mode && !stats_ready && (cpg % 2) == 0 && (c0 % 2) == 0 && (c1 % 2) == 0 && slab_bytes <= 8 * kCtaBytes && hw >= 64 &&
             ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 7) == 0) {
             int nranks = 1; while ((long long)nranks * kCtaBytes < slab_bytes) nranks <<= 1;
+            if (nranks > slab_mode) goto two_kernel_path;
             GNSlabArgs g;
             g.x0 = (const __half2*)x0; g.x1 = (const __half2*)x1; g.out = (__half2*)out;
             g.c0h = c0 / 2; g.c1h = c1 / 2; g.ch = c / 2; g.cpgh = cpg / 2; g.hw = hw;
@@ -358,6 +366,7 @@ extern "C" int fie_groupnorm_f16(const void* x0, int c0, const void* x1, int c1,
             return check_launch("fie_groupnorm_f16 (slab)");
         }
     }
+two_kernel_path:
     GNArgs a;
     a.x0 = (const uint4*)x0; a.x1 = (const uint4*)x1; a.out = (uint4*)out;
     a.c0v = c0 / 8; a.c1v = c1 / 8; a.cv = c / 8; a.hw = hw; a.groups = groups; a.cpg = c / groups;

@@ -165,6 +165,9 @@ void fie_tune_gemm(int force_cg, int force_block_n);
 /* Tuning / test hook: enable (1) / disable (0) the halo form of the stride-1 3x3 convolution (input rows loaded once per channel
  * chunk and shared by the 9 taps) and set the widest cout it is used for (0 = keep).  Not needed in production. */
 void fie_tune_conv_halo(int enable, int max_cout);
+/* GroupNorm: largest thread-block cluster the single-pass shared-memory kernel (k_gn_slab) may use; 0 = always the two-kernel path,
+ * default 1 (env FIE_GN_SLAB) — see the measurement note in csrc/norm.cu.  Experiments / tests only. */
+void fie_tune_groupnorm_slab(int max_cluster);
 
 /* Debug hook: device buffer of 8 x int64 per CTA that subsequent GEMM/conv launches fill with per-role wait-cycle
  * accounting (see gemm_conv.cu); NULL switches it off.  Not needed in production. */

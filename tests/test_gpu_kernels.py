@@ -588,6 +588,8 @@ def test_groupnorm_single_pass_cluster_kernel(cuda_dev, n, hw, c0, c1, silu, mon
     group; clusters of 1, 2, 4 and 8 CTAs; a row count that does not divide by the cluster size) against fp32 torch, and against the
     two-kernel path it replaces.  A large common offset checks the two-pass variance (no E[x^2] - mean^2 cancellation)."""
     ops = _ops()
+    from fast_image_editing_with_generative_models_b200 import _lib
+    _lib.lib().fie_tune_groupnorm_slab(8)              # allow clusters (the default policy only takes single-CTA slabs)
     x0 = (_rand((n, hw, c0), cuda_dev, 40) * 1.5 + 0.3).half()
     x1 = (_rand((n, hw, c1), cuda_dev, 41) * 0.7 - 0.2).half() if c1 else None
     c = c0 + c1
@@ -603,4 +605,8 @@ def test_groupnorm_single_pass_cluster_kernel(cuda_dev, n, hw, c0, c1, silu, mon
     xo = (x0.float() * 0.05 + 60.0).half()
     out_o = ops.groupnorm(xo, gamma[:c0], beta[:c0], 1e-5, False, 32)
     ref_o = F.group_norm(xo.float().permute(0, 2, 1), 32, gamma[:c0], beta[:c0], 1e-5).permute(0, 2, 1)
+    _lib.lib().fie_tune_groupnorm_slab(0)
+    two = ops.groupnorm(x0, gamma, beta, 1e-5, silu, 32, x1)                   # the two-kernel path on the same input
+    _lib.lib().fie_tune_groupnorm_slab(1)              # back to the default policy
     assert float((out_o.float() - ref_o).abs().max()) < 2e-2
+    assert float((two.float() - out.float()).abs().max()) < 8e-3
