@@ -129,6 +129,9 @@ class FastEditor:
                           f"the {model_name} architecture — outputs are not meaningful edits", RuntimeWarning, stacklevel=2)
             self._say("[FastEditor] WARNING: generating seeded synthetic weights (no checkpoints given) — outputs are NOT meaningful edits")
             state = model_zoo.synthetic_state(model_name, use_full_controlnet, tiny)
+        if use_full_precision:
+            # the one fp32 lever the engine has: VAE mid-block attention logits kept in fp32 between the passes (engine._VAEAttention)
+            state = dict(state, vae_scores_f32=True)
         with torch.cuda.device(self._dev):
             self._engine = model_zoo.build_engine(state, self._dev)
         self._engine.use_graphs = True      # every edit has the same shapes: replay it as one CUDA graph after the first call
@@ -386,6 +389,17 @@ class FastEditor:
             if pending is not None:
                 finalize(pending)
         return results  # type: ignore[return-value]
+
+    def warm_up(self, micro_batch: Optional[int] = None, **edit_kwargs) -> float:
+        """Runs one dummy micro-batch with the given ``edit`` arguments so that the CUDA graph for that shape / schedule is captured and
+        the pinned staging buffers exist before the first real call (sweeps call this during initialisation).  Returns the seconds spent."""
+        import time
+        t0 = time.perf_counter()
+        mb = int(micro_batch or self.MICRO_BATCH)
+        dummy = [Image.new("RGB", (self.OUT_SIZE, self.OUT_SIZE), (127, 127, 127))] * mb
+        self.edit_many(dummy, "warm-up", seed=0, micro_batch=mb, **edit_kwargs)
+        torch.cuda.synchronize(self._dev)
+        return time.perf_counter() - t0
 
     def _host_buffers(self, mb: int):
         """Two (input, output) pairs of pinned uint8 staging buffers [mb,1024,1024,3] (allocated once per micro-batch size)."""
