@@ -78,12 +78,34 @@ __global__ void __launch_bounds__(256) k_nms(const uint8_t* __restrict__ src, ui
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const uint8_t* g = src + (size_t)img * H * W * IN_CH;
     const int tid = threadIdx.x;
-    for (int i = tid; i < (TH + 4) * (TW + 4); i += 256) {
-        int ly = i / (TW + 4), lx = i % (TW + 4);
-        int y = min(max(y0 + ly - 2, 0), H - 1), x = min(max(x0 + lx - 2, 0), W - 1);   // BORDER_REPLICATE
-        const uint8_t* p = g + ((size_t)y * W + x) * IN_CH;
-        if (IN_CH == 3) sg[ly][lx] = (uint8_t)((9798u * __ldg(p) + 19235u * __ldg(p + 1) + 3735u * __ldg(p + 2) + 16384u) >> 15);   // cv2 RGB2GRAY
-        else sg[ly][lx] = __ldg(p);
+    constexpr int RAW_W = ((TW + 4) * 3 + 3) / 4 + 2;               // 32-bit words that cover one tile row of RGB bytes at any alignment
+    __shared__ uint32_t sraw[IN_CH == 3 ? TH + 4 : 1][IN_CH == 3 ? RAW_W : 1];
+    const bool fast_rgb = IN_CH == 3 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+    if (fast_rgb) {
+        // coalesced 32-bit loads of the tile's RGB rows into shared memory, then the gray conversion reads bytes from there
+        const long long row_bytes = (long long)W * 3;
+        const long long a0 = ((long long)(x0 - 2) * 3) & ~3ll;       // first staged byte of a row (may be negative: left of the image)
+        for (int i = tid; i < (TH + 4) * RAW_W; i += 256) {
+            const int ly = i / RAW_W, wi = i - ly * RAW_W;
+            const int y = min(max(y0 + ly - 2, 0), H - 1);           // BORDER_REPLICATE (rows)
+            const long long off = a0 + 4ll * wi;
+            sraw[ly][wi] = (off >= 0 && off + 4 <= row_bytes) ? __ldg(reinterpret_cast<const uint32_t*>(g + (size_t)y * row_bytes + off)) : 0u;
+        }
+        __syncthreads();
+        for (int i = tid; i < (TH + 4) * (TW + 4); i += 256) {
+            const int ly = i / (TW + 4), lx = i % (TW + 4);
+            const int x = min(max(x0 + lx - 2, 0), W - 1);           // BORDER_REPLICATE (columns): always inside the staged window
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(sraw[ly]) + ((long long)x * 3 - a0);
+            sg[ly][lx] = (uint8_t)((9798u * p[0] + 19235u * p[1] + 3735u * p[2] + 16384u) >> 15);   // cv2 RGB2GRAY
+        }
+    } else {
+        for (int i = tid; i < (TH + 4) * (TW + 4); i += 256) {
+            int ly = i / (TW + 4), lx = i % (TW + 4);
+            int y = min(max(y0 + ly - 2, 0), H - 1), x = min(max(x0 + lx - 2, 0), W - 1);   // BORDER_REPLICATE
+            const uint8_t* p = g + ((size_t)y * W + x) * IN_CH;
+            if (IN_CH == 3) sg[ly][lx] = (uint8_t)((9798u * __ldg(p) + 19235u * __ldg(p + 1) + 3735u * __ldg(p + 2) + 16384u) >> 15);   // cv2 RGB2GRAY
+            else sg[ly][lx] = __ldg(p);
+        }
     }
     __syncthreads();
     for (int i = tid; i < (TH + 2) * (TW + 2); i += 256) {
@@ -186,14 +208,36 @@ __global__ void __launch_bounds__(256) k_seams(const uint8_t* __restrict__ state
     }
 }
 
+// 4 pixels per thread when the row width allows it: one 32-bit state load, one (1 channel) or three (3 channels) 32-bit stores.
 __global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ state, const uint32_t* __restrict__ parent,
                                                   uint8_t* __restrict__ out, int H, int W, int out_channels) {
     const int img = blockIdx.z;
-    int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const uint32_t* P = parent + (size_t)img * H * W;
+    if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
+        const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
+        if (x >= W || y >= H) return;
+        const size_t o = (size_t)img * H * W + (size_t)y * W + x;
+        const uint32_t st = *reinterpret_cast<const uint32_t*>(state + o);
+        uint32_t e = 0;                                             // 4 edge bytes
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((st >> (8 * k)) & 0xFFu) { const uint32_t r = uf_find(P, (uint32_t)(y * W + x + k)); if (!(r & kWeakBit)) e |= 0xFFu << (8 * k); }
+        if (out_channels == 1) *reinterpret_cast<uint32_t*>(out + o) = e;
+        else {
+            // bytes e0 e0 e0 e1 | e1 e1 e2 e2 | e2 e3 e3 e3
+            const uint32_t e0 = e & 0xFFu, e1 = (e >> 8) & 0xFFu, e2 = (e >> 16) & 0xFFu, e3 = e >> 24;
+            uint32_t* d = reinterpret_cast<uint32_t*>(out + o * 3);
+            d[0] = e0 | (e0 << 8) | (e0 << 16) | (e1 << 24);
+            d[1] = e1 | (e1 << 8) | (e2 << 16) | (e2 << 24);
+            d[2] = e2 | (e3 << 8) | (e3 << 16) | (e3 << 24);
+        }
+        return;
+    }
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= W || y >= H) return;
-    size_t o = (size_t)img * H * W + (size_t)y * W + x;
+    const size_t o = (size_t)img * H * W + (size_t)y * W + x;
     uint8_t v = 0;
-    if (state[o]) { uint32_t r = uf_find(parent + (size_t)img * H * W, y * W + x); v = (r & kWeakBit) ? 0 : 255; }
+    if (state[o]) { uint32_t r = uf_find(P, y * W + x); v = (r & kWeakBit) ? 0 : 255; }
     if (out_channels == 1) out[o] = v;
     else { out[o * 3] = v; out[o * 3 + 1] = v; out[o * 3 + 2] = v; }
 }
@@ -291,7 +335,8 @@ extern "C" int fie_canny_u8(const void* img, void* edges, int n, int h, int w, i
     else k_nms<1><<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
     const long long seam_px = (long long)((w - 1) / TW) * h + (long long)((h - 1) / TH) * w;
     if (seam_px > 0) k_seams<<<dim3((unsigned)((seam_px + 255) / 256), n), 256, 0, stream>>>(state, parent, h, w);
-    dim3 g2(ceil_div(w, 64), ceil_div(h, 4), n);
+    const bool fin4 = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(edges)) & 3) == 0;
+    dim3 g2(ceil_div(fin4 ? w / 4 : w, 64), ceil_div(h, 4), n);
     k_finalize<<<g2, 256, 0, stream>>>(state, parent, (uint8_t*)edges, h, w, out_channels);
     return check_launch("fie_canny_u8");
 }
