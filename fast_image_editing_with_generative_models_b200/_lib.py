@@ -57,6 +57,12 @@ SIGNATURES = {
     "fie_attention_trace": (None, [c_void_p]),
     "fie_tune_conv_halo": (None, [c_int, c_int]),
     "fie_tune_groupnorm_slab": (None, [c_int]),
+    "fie_pack_conv3x3_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "fie_pack_conv3x3_c8_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "fie_pack_conv_up2x_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fie_pack_rows_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fie_fold_layernorm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "fie_fuse_lora_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_ll, c_void_p]),
     "fie_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll, c_ll, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv3x3_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),
     "fie_conv_up2x_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Epilogue), c_void_p]),

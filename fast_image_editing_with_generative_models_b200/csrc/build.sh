@@ -4,7 +4,7 @@ set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../libfie_b200.so"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-SRCS="capi.cu canny.cu resize.cu elementwise.cu norm.cu conv_small.cu gemm_conv.cu attention.cu attn_vae.cu jpeg.cu"
+SRCS="capi.cu canny.cu resize.cu elementwise.cu norm.cu conv_small.cu gemm_conv.cu attention.cu attn_vae.cu jpeg.cu pack.cu"
 mkdir -p "$HERE/_obj"
 pids=()
 for s in $SRCS; do

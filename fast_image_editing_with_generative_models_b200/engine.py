@@ -22,7 +22,7 @@ import torch
 
 from . import ops
 from .configs import ControlNetConfig, UNetConfig, VAEConfig, skip_channels
-from .weights import fold_layernorm, fuse_lora, pack_conv3x3, pack_conv3x3_c8, pack_conv_up2x, pack_geglu
+from .weights import cast_f16, fold_layernorm, fuse_lora, pack_conv3x3, pack_conv3x3_c8, pack_conv_up2x, pack_geglu
 
 Tensor = torch.Tensor
 Params = Dict[str, Tensor]
@@ -61,7 +61,7 @@ class _Packer:
         return (self.prefix + name + ".weight") in self.p
 
     def linear(self, name: str) -> Tuple[Tensor, Optional[Tensor]]:
-        return self.w(name).to(torch.float16).contiguous(), self.b(name)
+        return cast_f16(self.w(name)), self.b(name)
 
     def conv3(self, name: str, pad_cout_to=None, pad_cin_to=None) -> Tuple[Tensor, Optional[Tensor]]:
         w = pack_conv3x3(self.w(name), pad_cout_to, pad_cin_to)
@@ -78,7 +78,7 @@ class _Packer:
 
     def conv1(self, name: str) -> Tuple[Tensor, Optional[Tensor]]:
         w = self.w(name)
-        return w.reshape(w.shape[0], w.shape[1]).to(torch.float16).contiguous(), self.b(name)
+        return cast_f16(w.reshape(w.shape[0], w.shape[1])), self.b(name)
 
     def cin4(self, name: str) -> Tuple[Tensor, Optional[Tensor]]:
         """[Cout, Cin<=4, 3, 3] -> fp32 [Cout, 3, 3, 4] for the CUDA-core conv_in kernel."""
@@ -156,7 +156,7 @@ class TransformerBlock:
         wqkv = torch.cat([pk.w(f"{pre}.attn1.{n}") for n in ("to_q", "to_k", "to_v")], 0)
         self.wo1 = pk.linear(pre + ".attn1.to_out.0")
         self.kv_off = sum(t.shape[0] for t in kv_slot)
-        kv_slot.append(torch.cat([pk.w(pre + ".attn2.to_k"), pk.w(pre + ".attn2.to_v")], 0).to(torch.float16))
+        kv_slot.append(cast_f16(torch.cat([pk.w(pre + ".attn2.to_k"), pk.w(pre + ".attn2.to_v")], 0)))
         self.wo2 = pk.linear(pre + ".attn2.to_out.0")
         self.wf = pk.linear(pre + ".ff.net.2")
         if self.fold:
@@ -165,7 +165,7 @@ class TransformerBlock:
             self.wg, self.bg = pack_geglu(*fold_layernorm(pk.w(pre + ".ff.net.0.proj"), pk.b(pre + ".ff.net.0.proj"), *ln3))
         else:
             self.ln1, self.ln2, self.ln3 = ln1, ln2, ln3
-            self.wqkv = wqkv.to(torch.float16).contiguous()
+            self.wqkv = cast_f16(wqkv)
             self.wq2 = pk.linear(pre + ".attn2.to_q")[0]
             self.wg, self.bg = pack_geglu(*pk.linear(pre + ".ff.net.0.proj"))
 

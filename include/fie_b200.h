@@ -218,6 +218,25 @@ size_t fie_attn_vae_workspace_bytes(int ntok, int chunk_rows, int f32_scores);
 int fie_attn_vae_d512_f16(const void* q, long long ldq, const void* k, long long ldk, const void* vt, void* out, long long ldo,
                           int ntok, int d, float scale, int f32_scores, int chunk_rows, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Load-time weight transforms (SURVEY 8(b) `fie_pack_weights_*`): the cold path of FastEditor.__init__ — what from_pretrained +
+ * load_lora_weights prepare at reference src/pipeline.py:89-161 — on the GPU without library kernels.  fp32 master tensors in diffusers'
+ * layouts in, the layouts of DESIGN.md section 2 out.
+ *   fie_pack_conv3x3_f16     w [cout,cin,3,3] -> fp16 [cout_pad][3][3][cin_pad] (zero padded): B operand of fie_conv3x3_f16
+ *   fie_pack_conv3x3_c8_f16  w [cout,cin<=8,3,3] -> fp16 [cout_pad][3][2][64]: hi / lo parts for fie_conv3x3_c8_f16
+ *   fie_pack_conv_up2x_f16   w [cout,cin,3,3] -> fp16 [4][cout][2][2][cin]: phase filters for fie_conv_up2x_f16
+ *   fie_pack_rows_f16        w [n,k] (+ bias [n]) -> fp16 [n,k] (+ fp32 bias) with an optional row permutation perm[n] (device int32)
+ *   fie_fold_layernorm_f16   LayerNorm(gamma, beta over k) followed by Linear(w [n,k], bias) -> centred fp16 weights + fp32 bias for a GEMM
+ *                            with fie_epilogue.ln_stats_in (bias / beta may be NULL)
+ *   fie_fuse_lora_f32        w [cout, cols] += scale * lora_b [cout, rank] x lora_a [rank, cols], fp32 in place (LCM-LoRA fuse; a conv
+ *                            weight is viewed as [cout, cin*k*k], its LoRA A as [rank, cin*k*k]) */
+int fie_pack_conv3x3_f16(const float* w, void* out, int cout, int cin, int cout_pad, int cin_pad, void* stream);
+int fie_pack_conv3x3_c8_f16(const float* w, void* out, int cout, int cin, int cout_pad, void* stream);
+int fie_pack_conv_up2x_f16(const float* w, void* out, int cout, int cin, void* stream);
+int fie_pack_rows_f16(const float* w, const float* bias, const int* perm, void* out_w, float* out_bias, int n, int k, void* stream);
+int fie_fold_layernorm_f16(const float* w, const float* bias, const float* gamma, const float* beta, void* out_w, float* out_bias,
+                           int n, int k, void* stream);
+int fie_fuse_lora_f32(float* w, const float* lora_a, const float* lora_b, float scale, int cout, int rank, long long cols, void* stream);
+
 /* ---- Flash attention, head_dim 64 (tcgen05): replaces F.scaled_dot_product_attention in AttnProcessor2_0 ----
  * q: fp16 rows [b*nq, ldq] (head h at columns h*64..), k/v: [b*nkv, ldk/ldv], out: [b*nq, ldo]. No mask. */
 int fie_attention_d64_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,

@@ -610,3 +610,36 @@ def test_groupnorm_single_pass_cluster_kernel(cuda_dev, n, hw, c0, c1, silu, mon
     _lib.lib().fie_tune_groupnorm_slab(1)              # back to the default policy
     assert float((out_o.float() - ref_o).abs().max()) < 2e-2
     assert float((two.float() - out.float()).abs().max()) < 8e-3
+
+
+def test_native_weight_packing_matches_the_torch_transforms(cuda_dev):
+    """csrc/pack.cu (SURVEY 8(b) fie_pack_weights_*): the load-time transforms as CUDA kernels against weights.py's torch
+    implementations on CPU tensors — layouts bit-exact, the fp32 reductions (LayerNorm fold, LoRA fuse) to fp32 rounding."""
+    from fast_image_editing_with_generative_models_b200 import weights as Wt
+    g = torch.Generator("cpu").manual_seed(7)
+    rn = lambda *s: torch.randn(s, generator=g)
+    w = rn(70, 24, 3, 3)
+    for pads in ((None, None), (96, 64)):
+        assert torch.equal(Wt.pack_conv3x3(w.to(cuda_dev), *pads).cpu(), Wt.pack_conv3x3(w, *pads))
+    w8 = rn(40, 3, 3, 3) / 5
+    assert torch.equal(Wt.pack_conv3x3_c8(w8.to(cuda_dev), 64).cpu(), Wt.pack_conv3x3_c8(w8, 64))
+    w4 = rn(33, 4, 3, 3)
+    assert torch.equal(Wt.pack_conv3x3_c8(w4.to(cuda_dev)).cpu(), Wt.pack_conv3x3_c8(w4))
+    wu = rn(48, 64, 3, 3)
+    assert torch.equal(Wt.pack_conv_up2x(wu.to(cuda_dev)).cpu(), Wt.pack_conv_up2x(wu))
+    wl = rn(130, 96)
+    assert torch.equal(Wt.cast_f16(wl.to(cuda_dev)).cpu(), wl.half())
+    # LayerNorm fold: rows centred after the gamma product; bias = b + W beta
+    wf, bf, ga, be = rn(200, 640) / 25, rn(200), 1 + 0.3 * rn(640), 0.2 * rn(640)
+    for b_, be_ in ((bf, be), (None, be), (bf, None), (None, None)):
+        w16, bias = Wt.fold_layernorm(wf.to(cuda_dev), None if b_ is None else b_.to(cuda_dev), ga.to(cuda_dev), None if be_ is None else be_.to(cuda_dev))
+        r16, rb = Wt.fold_layernorm(wf, b_, ga, be_)
+        assert w16.dtype == torch.float16 and bias.dtype == torch.float32
+        assert float((w16.cpu().float() - r16.float()).abs().max()) <= 2 ** -11 * float(r16.float().abs().max())      # at most one fp16 ulp (fp32 mean order)
+        assert float((bias.cpu() - rb).abs().max()) < 1e-5 * max(1.0, float(rb.abs().max()))
+    # LoRA fuse: linear and convolution (A [r,in,k,k], B [out,r,1,1]), ragged sizes
+    for shape_w, shape_a, shape_b in (((100, 70), (8, 70), (100, 8)), ((45, 20, 3, 3), (64, 20, 3, 3), (45, 64, 1, 1)), ((33, 17, 1, 1), (4, 17, 1, 1), (33, 4, 1, 1))):
+        w0, a0, b0 = rn(*shape_w), rn(*shape_a), rn(*shape_b)
+        got = Wt.fuse_lora(w0.to(cuda_dev), a0.to(cuda_dev), b0.to(cuda_dev), 0.75).cpu()
+        ref = Wt.fuse_lora(w0, a0, b0, 0.75)
+        assert got.shape == ref.shape and float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max()) * 8
