@@ -539,6 +539,9 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (cpar + 2 * j >= nchunks) break;
+                    // the last tile column may extend past N (N = 512 with 96-wide tiles): those chunks hold no output channels, and
+                    // their (zero) sums would be added past the last group -- past the END of the statistics buffer for the last image
+                    if (nb * ncols_tile + (cpar + 2 * j) * 32 >= p.n_store) break;
                     const int g = (nb * ncols_tile + (cpar + 2 * j) * 32) / p.gn_cpg + (stages ? (lane >> (5 - stages)) : 0);
                     atomicAdd(st + g * 2, (unsigned long long)__float2ll_rn(gn_s[j] * 1048576.0f));
                     atomicAdd(st + g * 2 + 1, (unsigned long long)__float2ll_rn(gn_q[j] * 1048576.0f));
