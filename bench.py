@@ -307,6 +307,19 @@ def main():
            "ms_per_step": ms_e2e / a.steps,
            "single_call": {"images_per_call": B, "ms_per_call": ms_e2e_1, "value": world * B / (ms_e2e_1 * 1e-3),
                            "note": "one edit_many call per step: host staging and PIL conversion are not overlapped with GPU work"}}
+    # the same call returning JPEG files encoded on the GPU (what run_batch.py writes for *.jpg targets): D2H shrinks to the file bytes
+    def e2e_jpeg(n_batches):
+        call[0] += 1
+        images = pil * n_batches
+        prompts = [f"edit {call[0]}: make image {j} look like a watercolour painting" for j in range(len(images))]
+        files = editor.edit_many(images, prompts, negative_prompt="", seeds=list(range(len(images))), micro_batch=B, output="jpeg", **EDIT)
+        assert len(files) == len(images) and files[0][:2] == b"\xff\xd8" and files[0][-2:] == b"\xff\xd9"
+        return files
+    jf = e2e_jpeg(1)
+    ms_jpeg = timed(lambda: e2e_jpeg(a.steps), 1, 0)
+    e2e["jpeg_output"] = {"value": world * B * a.steps / (ms_jpeg * 1e-3), "ms_per_step": ms_jpeg / a.steps,
+                          "file_bytes_per_step": int(sum(len(f) for f in jf)), "d2h_prefix_bytes_per_image": int(getattr(editor, "_jpeg_prefix", 0)),
+                          "api": "FastEditor.edit_many(..., output='jpeg') -> bytes of the *.jpg files (GPU baseline JPEG encoder, byte-identical to Pillow)"}
     # batch-1 latency of the reference's own call, FastEditor.edit (host PIL in -> host PIL out)
     lat = None
     if world == 1:
