@@ -18,6 +18,7 @@
 // The two warpgroups ping-pong: while one does its softmax the tensor core serves the other (FlashAttention-4 style).
 // Warp roles (384 threads): w0 TMA producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 softmax(q=0), w8-11 softmax(q=1).
 #include "tc_common.cuh"
+#include <stdlib.h>
 #include <type_traits>
 
 #ifndef FIE_ATT_EMU
@@ -337,6 +338,289 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Persistent form of k_attention_d64 (round 2).  With 1024 keys a CTA lives for 8 K/V steps (~12 us of steady state) and pays ~5 us
+// of set-up and drain around them: block scheduling, barrier init, the 512-column TMEM allocation, the first Q / K / V round trip,
+// the O read-out and store.  Here <= 148 CTAs each walk a strided list of (batch, head, 256-row query block) items with everything
+// allocated once: the producer runs ahead across items (Q is double-buffered, the K/V ring simply continues), the MMA warp issues
+// S = Q K^T for the FIRST tile of the next item as soon as the last tile of the current one has been consumed, and a softmax
+// warpgroup goes from the epilogue of one item straight into scores that are already waiting in TMEM.
+// Barrier parities follow GLOBAL counters (tiles processed by this CTA), not per-item ones.  No extra barrier protects O_q / P_q across
+// items: a softmax warpgroup reads O_q of item n (epilogue) before it arrives on p_full for the first tile of item n + 1, and the MMA
+// warp only overwrites O_q / reads P_q after that arrival.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATTP_OFF_KV = 2 * ATT_QT * ATT_TILE_BYTES;                          // after Q[2 buffers][2 tiles]
+constexpr int ATTP_OFF_BAR = ATTP_OFF_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;
+constexpr int ATTP_SMEM = ATTP_OFF_BAR + 256;
+
+__global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constant__ AttnParams p, int heads, int batch) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // persistent grid (<= 1 CTA per SM): the next kernel may start launching (see gemm_conv.cu)
+    uint8_t* sQ = smem;                                   // buffer u: Q tiles at u * 32K
+    uint8_t* sKV = smem + ATTP_OFF_KV;                    // stage s: K at s*32K, V at s*32K + 16K
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTP_OFF_BAR);
+    uint64_t* q_full = bars;                 // [2]
+    uint64_t* q_empty = bars + 2;            // [2]
+    uint64_t* kv_full = bars + 4;            // [3]
+    uint64_t* kv_empty = bars + 7;           // [3]
+    uint64_t* s_full = bars + 10;            // [2]
+    uint64_t* p_full = bars + 12;            // [2]
+    uint64_t* o_full = bars + 14;            // [2]
+    uint64_t* s_free = bars + 16;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("fie: attention smem base misaligned\n"); __trap(); }
+
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+    const int nqp = (p.nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM);
+    const int items = batch * heads * nqp;
+    const int n_tiles = (p.nkv + ATT_BN - 1) / ATT_BN;
+    const int my_items = blockIdx.x < (unsigned)items ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // items blockIdx.x, + gridDim.x, ...
+
+    if (threadIdx.x == 0) {
+        for (int u = 0; u < 2; ++u) { mbar_init(&q_full[u], 1); mbar_init(&q_empty[u], 1); }
+        for (int s = 0; s < ATT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int q = 0; q < ATT_QT; ++q) { mbar_init(&s_full[q], 1); mbar_init(&p_full[q], 128); mbar_init(&o_full[q], 1); mbar_init(&s_free[q], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&p.q_map); tma_prefetch_desc(&p.k_map); tma_prefetch_desc(&p.v_map); }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            int s = 0; uint32_t ph = 0;
+            for (int n = 0; n < my_items; ++n) {
+                const int it = (int)blockIdx.x + n * (int)gridDim.x;
+                const int qp = it % nqp, head = (it / nqp) % heads, b = it / (nqp * heads);
+                const int u = n & 1;
+                mbar_wait(&q_empty[u], (uint32_t)(((n >> 1) & 1) ^ 1));
+                mbar_arrive_expect_tx(&q_full[u], ATT_QT * ATT_TILE_BYTES);
+                for (int q = 0; q < ATT_QT; ++q)
+                    tma_load_3d(&p.q_map, &q_full[u], sQ + (u * ATT_QT + q) * ATT_TILE_BYTES, head * ATT_D, (qp * ATT_QT + q) * ATT_BM, b);
+                for (int j = 0; j < n_tiles; ++j) {
+                    mbar_wait(&kv_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
+                    tma_load_3d(&p.k_map, &kv_full[s], sKV + s * 2 * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, b);
+                    tma_load_3d(&p.v_map, &kv_full[s], sKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, b);
+                    if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc_qk = umma_idesc_f16(ATT_BM, ATT_BN, 0, 0);
+        const uint32_t idesc_pv = umma_idesc_f16(ATT_BM, ATT_D, 0, 1);   // B (= V) is MN-major
+        const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
+        // S_q = Q_q(buffer u) K_s^T; `last` = this is the item's last Q K^T: its completion releases the Q buffer
+        auto issue_qk = [&](int q, int s, int u, bool last) {
+            if (elect_one_sync()) {
+                const uint64_t ad = umma_desc_sw128(aQ + (u * ATT_QT + q) * ATT_TILE_BYTES), bd = umma_desc_sw128(aKV + s * 2 * ATT_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k) umma_f16(tmem + q * 128, ad + 2 * k, bd + 2 * k, idesc_qk, k ? 1u : 0u);
+                umma_commit(&s_full[q]);
+                if (last && q == ATT_QT - 1) umma_commit(&q_empty[u]);
+            }
+            __syncwarp();
+        };
+        if (my_items > 0) {
+            mbar_wait(&q_full[0], 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_qk(0, 0, 0, n_tiles == 1);
+            issue_qk(1, 0, 0, n_tiles == 1);
+        }
+        int s = 0; uint32_t ph = 0;                 // stage / phase of the current tile
+        uint32_t g = 0;                             // tiles processed by this CTA: parity source of the per-tile barriers
+        for (int n = 0; n < my_items; ++n) {
+            for (int j = 0; j < n_tiles; ++j, ++g) {
+                int sn = s + 1; uint32_t phn = ph; if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
+                const bool next_same = j + 1 < n_tiles, next_item = !next_same && n + 1 < my_items;
+                if (next_same || next_item) {
+                    const int un = next_same ? (n & 1) : ((n + 1) & 1);
+                    if (next_item) mbar_wait(&q_full[un], (uint32_t)(((n + 1) >> 1) & 1));
+                    mbar_wait(&kv_full[sn], phn);
+                    const bool last_qk = next_same ? (j + 2 == n_tiles) : (n_tiles == 1);
+                    for (int q = 0; q < ATT_QT; ++q) {
+                        mbar_wait(&s_free[q], g & 1u);
+                        tc_fence_after();
+                        issue_qk(q, sn, un, last_qk);
+                    }
+                }
+                for (int q = 0; q < ATT_QT; ++q) {
+                    mbar_wait(&p_full[q], g & 1u);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t aV = aKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES;
+#pragma unroll
+                        for (int k = 0; k < ATT_BN / 16; ++k) {
+                            const uint64_t bd = umma_desc_sw128(aV + k * 2048, 1024, 1024);
+                            umma_f16_ts(tmem + 256 + q * 64, tmem + 384 + q * 64 + k * 8, bd, idesc_pv, (j | k) ? 1u : 0u);   // O restarts with every item
+                        }
+                        umma_commit(&o_full[q]);
+                        if (q == ATT_QT - 1) umma_commit(&kv_empty[s]);
+                    }
+                    __syncwarp();
+                }
+                s = sn; ph = phn;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== softmax / epilogue: warpgroup = Q tile, thread = row (same arithmetic as k_attention_d64) =====================
+        const int q = (warp - 4) >> 2;
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr, tP = tmem + 384 + q * 64 + lane_addr;
+        const float sl2 = p.scale_log2;
+        auto exp_cols = [&](const uint32_t* r, int col0, float mneg, int kv_left, auto full_c, auto max_c, auto nu_c, uint32_t* pp, float (&mx)[4]) -> float {
+            constexpr bool FULL = decltype(full_c)::value;
+            constexpr bool WITH_MAX = decltype(max_c)::value;
+            constexpr int NU = decltype(nu_c)::value;
+            f32x2 psa = 0ull, psb = 0ull;
+            const f32x2 sl22 = pack2(sl2, sl2), mneg2 = pack2(mneg, mneg);
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = u * 8 + 2 * i;
+                    if (WITH_MAX) {
+                        if (FULL) mx[i] = fmaxf(fmaxf(mx[i], __uint_as_float(r[c])), __uint_as_float(r[c + 1]));
+                        else { if (col0 + c < kv_left) mx[i] = fmaxf(mx[i], __uint_as_float(r[c])); if (col0 + c + 1 < kv_left) mx[i] = fmaxf(mx[i], __uint_as_float(r[c + 1])); }
+                    }
+                    const f32x2 x2 = ffma2(pack2u(r[c], r[c + 1]), sl22, mneg2);
+                    float x0, x1, p0, p1;
+                    unpack2(x2, x0, x1);
+                    if (2 * i >= 8 - FIE_ATT_EMU) ex2_emulated2(pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f)), p0, p1);
+                    else { p0 = ex2_approx(x0); p1 = ex2_approx(x1); }
+                    if (!FULL) { if (col0 + c >= kv_left) p0 = 0.f; if (col0 + c + 1 >= kv_left) p1 = 0.f; }
+                    if (i & 1) psb = fadd2(psb, pack2(p0, p1)); else psa = fadd2(psa, pack2(p0, p1));
+                    __half2 h = __floats2half2_rn(p0, p1);
+                    pp[4 * u + i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+            }
+            float s0, s1;
+            unpack2(fadd2(psa, psb), s0, s1);
+            return s0 + s1;
+        };
+        auto half_max = [&](const uint32_t (&r)[64], int hf, int kv_left, bool full_tile, float (&mx)[4]) {
+            if (full_tile) {
+#pragma unroll
+                for (int i = 0; i < 64; i += 8) {
+                    mx[0] = fmaxf(fmaxf(mx[0], __uint_as_float(r[i])), __uint_as_float(r[i + 1])); mx[1] = fmaxf(fmaxf(mx[1], __uint_as_float(r[i + 2])), __uint_as_float(r[i + 3]));
+                    mx[2] = fmaxf(fmaxf(mx[2], __uint_as_float(r[i + 4])), __uint_as_float(r[i + 5])); mx[3] = fmaxf(fmaxf(mx[3], __uint_as_float(r[i + 6])), __uint_as_float(r[i + 7]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) if (hf * 64 + i < kv_left) mx[0] = fmaxf(mx[0], __uint_as_float(r[i]));
+            }
+        };
+        const std::true_type yes{}; const std::false_type no{};
+        const std::integral_constant<int, 8> n8{}; const std::integral_constant<int, 4> n4{};
+        uint32_t g = 0;                                   // tiles processed: parity of s_full / o_full
+        for (int n = 0; n < my_items; ++n) {
+            const int it = (int)blockIdx.x + n * (int)gridDim.x;
+            const int qp = it % nqp, head = (it / nqp) % heads, b = it / (nqp * heads);
+            float m_run = -INFINITY, l_run = 0.f;
+            for (int j = 0; j < n_tiles; ++j, ++g) {
+                mbar_wait(&s_full[q], g & 1u);
+                tc_fence_after();
+                const int kv_left = p.nkv - j * ATT_BN;
+                const bool full_tile = kv_left >= ATT_BN;
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                uint32_t pp0[32];
+                float psum = 0.f;
+                {
+                    uint32_t ra[64];
+                    tmem_ld_32x64(tS, ra);
+                    tmem_ld_wait();
+                    if (j == 0) half_max(ra, 0, kv_left, full_tile, mx4);
+                    else if (full_tile) psum = exp_cols(ra, 0, -m_run * sl2, kv_left, yes, yes, n8, pp0, mx4);
+                    else psum = exp_cols(ra, 0, -m_run * sl2, kv_left, no, yes, n8, pp0, mx4);
+                }
+                uint32_t rb[64];
+                tmem_ld_32x64(tS + 64, rb);
+                tmem_ld_wait();
+                half_max(rb, 1, kv_left, full_tile, mx4);
+                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                const bool move = (j == 0) || ((mx - m_run) * sl2 > 8.0f);
+                float alpha = 1.0f;
+                if (j > 0) {                                // P_q and O_q are free once PV(q, previous tile) has completed
+                    mbar_wait(&o_full[q], (g - 1) & 1u);
+                    tc_fence_after();
+                }
+                if (__any_sync(0xffffffffu, move)) {
+                    if (move) { alpha = ex2_approx((m_run - fmaxf(mx, m_run)) * sl2); m_run = fmaxf(mx, m_run); }
+                    if (j > 0) {
+#pragma unroll 1
+                        for (int hq = 0; hq < 2; ++hq) {
+                            uint32_t ro[32];
+                            tmem_ld_32x32(tO + (uint32_t)(hq * 32), ro);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                            tmem_st_32x32(tO + (uint32_t)(hq * 32), ro);
+                        }
+                    }
+                    float dummy[4];
+                    psum = 0.f;
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        uint32_t rq[32];
+                        tmem_ld_32x32(tS + (uint32_t)(hq * 32), rq);
+                        tmem_ld_wait();
+                        if (full_tile) psum += exp_cols(rq, hq * 32, -m_run * sl2, kv_left, yes, no, n4, pp0 + hq * 16, dummy);
+                        else psum += exp_cols(rq, hq * 32, -m_run * sl2, kv_left, no, no, n4, pp0 + hq * 16, dummy);
+                    }
+                }
+                tmem_st_32x32(tP, pp0);
+                tc_fence_before();
+                mbar_arrive(&s_free[q]);
+                {
+                    uint32_t pp1[32];
+                    float dummy[4];
+                    if (full_tile) psum += exp_cols(rb, 64, -m_run * sl2, kv_left, yes, no, n8, pp1, dummy);
+                    else psum += exp_cols(rb, 64, -m_run * sl2, kv_left, no, no, n8, pp1, dummy);
+                    tmem_st_32x32(tP + 32u, pp1);
+                }
+                l_run = l_run * alpha + psum;
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&p_full[q]);
+            }
+            // ---- epilogue of this item: O_q / l -> global (g already counts the item's last tile) ----
+            mbar_wait(&o_full[q], (g - 1) & 1u);
+            tc_fence_after();
+            const float inv_l = 1.0f / l_run;
+            const int qrow = (qp * ATT_QT + q) * ATT_BM + row;
+            __half* orow = p.out + ((long long)b * p.nq + qrow) * p.ldo + head * ATT_D;
+            {
+                uint32_t r[64];
+                tmem_ld_32x64(tO, r);
+                tmem_ld_wait();
+                tc_fence_before();                          // the O_q read is complete before this thread's next p_full arrive lets the MMA warp overwrite it
+                if (qrow < p.nq) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int e = u * 8 + 2 * i;
+                            hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
+                        }
+                        *reinterpret_cast<uint4*>(orow + u * 8) = v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Cross-attention form (nkv <= 128: the 77 prompt tokens): one K/V tile, so the work per (batch, head, 256 query rows) is a
 // short latency chain (Q K^T -> softmax -> P V -> store) and one CTA per item, as above, spends most of its life in set-up.
 // Here 148 persistent CTAs each walk a contiguous range of items; the producer keeps the next item's Q / K / V in flight in a
@@ -578,6 +862,25 @@ static int attention_d64(const void* q, long long ldq, const void* k, long long 
         cfg.attrs = pdl_attr; cfg.numAttrs = pdl ? 1 : 0;
         cudaError_t e = cudaLaunchKernelEx(&cfg, k_attention_d64_kv1, p, heads, b);
         if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_attention_d64_kv1): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
+        return check_launch("fie_attention_d64_f16");
+    }
+    static int persist = -1;                             // FIE_ATT_PERSIST=0: one CTA per (batch, head, query block) as in round 1
+    if (persist < 0) { const char* e = getenv("FIE_ATT_PERSIST"); persist = e ? atoi(e) : 1; }
+    if (persist && !g_att_trace) {
+        static bool attrp_dev[kMaxDevices] = {false};
+        bool& attrp = attrp_dev[current_device()];
+        if (!attrp) {
+            cudaError_t e = cudaFuncSetAttribute(k_attention_d64_p, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTP_SMEM);
+            if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(k_attention_d64_p): %s", cudaGetErrorString(e)); return FIE_ERR_CUDA; }
+            attrp = true;
+        }
+        const long long items = (long long)b * heads * ((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM));
+        const int sms = device_sm_count();
+        cudaLaunchConfig_t cfgp = {};
+        cfgp.gridDim = dim3((unsigned)(items < sms ? items : sms)); cfgp.blockDim = dim3(384); cfgp.dynamicSmemBytes = ATTP_SMEM; cfgp.stream = (cudaStream_t)stream;
+        cfgp.attrs = pdl_attr; cfgp.numAttrs = pdl ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfgp, k_attention_d64_p, p, heads, b);
+        if (e != cudaSuccess) { set_error("cudaLaunchKernelEx(k_attention_d64_p): %s", cudaGetErrorString(e)); cudaGetLastError(); return FIE_ERR_CUDA; }
         return check_launch("fie_attention_d64_f16");
     }
     dim3 grid((nq + ATT_QT * ATT_BM - 1) / (ATT_QT * ATT_BM), heads, b);
