@@ -348,8 +348,12 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
 // items: a softmax warpgroup reads O_q of item n (epilogue) before it arrives on p_full for the first tile of item n + 1, and the MMA
 // warp only overwrites O_q / reads P_q after that arrival.
 // ------------------------------------------------------------------------------------------------
+#ifndef FIE_ATTP_STAGES
+#define FIE_ATTP_STAGES 3
+#endif
+constexpr int ATTP_KV_STAGES = FIE_ATTP_STAGES;                                    // K/V ring depth (prefetch distance across items)
 constexpr int ATTP_OFF_KV = 2 * ATT_QT * ATT_TILE_BYTES;                          // after Q[2 buffers][2 tiles]
-constexpr int ATTP_OFF_BAR = ATTP_OFF_KV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES;
+constexpr int ATTP_OFF_BAR = ATTP_OFF_KV + ATTP_KV_STAGES * 2 * ATT_TILE_BYTES;
 constexpr int ATTP_SMEM = ATTP_OFF_BAR + 256;
 
 __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constant__ AttnParams p, int heads, int batch) {
@@ -360,13 +364,13 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTP_OFF_BAR);
     uint64_t* q_full = bars;                 // [2]
     uint64_t* q_empty = bars + 2;            // [2]
-    uint64_t* kv_full = bars + 4;            // [3]
-    uint64_t* kv_empty = bars + 7;           // [3]
-    uint64_t* s_full = bars + 10;            // [2]
-    uint64_t* p_full = bars + 12;            // [2]
-    uint64_t* o_full = bars + 14;            // [2]
-    uint64_t* s_free = bars + 16;            // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* kv_full = bars + 4;                          // [ATTP_KV_STAGES]
+    uint64_t* kv_empty = kv_full + ATTP_KV_STAGES;         // [ATTP_KV_STAGES]
+    uint64_t* s_full = kv_empty + ATTP_KV_STAGES;          // [2]
+    uint64_t* p_full = s_full + 2;                         // [2]
+    uint64_t* o_full = p_full + 2;                         // [2]
+    uint64_t* s_free = o_full + 2;                         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
     if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("fie: attention smem base misaligned\n"); __trap(); }
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int u = 0; u < 2; ++u) { mbar_init(&q_full[u], 1); mbar_init(&q_empty[u], 1); }
-        for (int s = 0; s < ATT_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int s = 0; s < ATTP_KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         for (int q = 0; q < ATT_QT; ++q) { mbar_init(&s_full[q], 1); mbar_init(&p_full[q], 128); mbar_init(&o_full[q], 1); mbar_init(&s_free[q], 128); }
         mbar_fence_init();
     }
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constan
                     mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
                     tma_load_3d(&p.k_map, &kv_full[s], sKV + s * 2 * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, b);
                     tma_load_3d(&p.v_map, &kv_full[s], sKV + s * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, b);
-                    if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
+                    if (++s == ATTP_KV_STAGES) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -435,7 +439,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constan
         uint32_t g = 0;                             // tiles processed by this CTA: parity source of the per-tile barriers
         for (int n = 0; n < my_items; ++n) {
             for (int j = 0; j < n_tiles; ++j, ++g) {
-                int sn = s + 1; uint32_t phn = ph; if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
+                int sn = s + 1; uint32_t phn = ph; if (sn == ATTP_KV_STAGES) { sn = 0; phn ^= 1; }
                 const bool next_same = j + 1 < n_tiles, next_item = !next_same && n + 1 < my_items;
                 if (next_same || next_item) {
                     const int un = next_same ? (n & 1) : ((n + 1) & 1);
