@@ -143,7 +143,11 @@ class EditEngine:
         torch.cuda.synchronize(self.dev)
         graph = torch.cuda.CUDAGraph()
         l0 = ops.LAUNCHES
-        with torch.cuda.graph(graph):
+        # an explicit capture stream on THIS engine's device: torch.cuda.graph's default capture stream is a process-wide singleton that
+        # lives on the device of the first capture, which would silently move a cuda:1 engine's capture (and its launches) to cuda:0
+        if getattr(self, "_capture_stream", None) is None:
+            self._capture_stream = torch.cuda.Stream(device=self.dev)
+        with torch.cuda.graph(graph, stream=self._capture_stream):
             out = self._edit_core(st["img"], st["pe"], st["pl"], st["nz"], return_latents=True, **args)
         st.update(graph=graph, out=out, launches=ops.LAUNCHES - l0)
         ops.LAUNCHES = l0                         # capture records launches, it does not execute them
