@@ -363,7 +363,11 @@ def groupnorm(x0: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: fl
     with _prof("groupnorm", 4.0 * out.numel(), "B", f"[{n},{hw},{c0}+{c1}]" + (" fused-stats" if ready else "")):
         check(_lib.lib().fie_groupnorm_f16(_p(x0), c0, _p(x1), c1, _p(out), n, hw, groups, _p(gamma), _p(beta), float(eps), int(silu),
                                             _p(stats), int(ready), _stream()), "fie_groupnorm_f16")
-    _count(1 if ready else 2)
+    # launches: apply only (producer statistics), the single-pass slab kernel (default policy of csrc/norm.cu: the (image, group) slab fits
+    # one CTA's shared memory), or statistics + apply
+    cpg = (c0 + c1) // groups
+    slab = (not ready) and cpg % 2 == 0 and hw >= 64 and hw * cpg * 2 <= 192 * 1024 and os.environ.get("FIE_GN_SLAB", "1") != "0"
+    _count(1 if (ready or slab) else 2)
     return out
 
 
