@@ -37,3 +37,21 @@ def test_jpeg_oracle_extremes_and_default_quality():
 def test_jpeg_oracle_full_size():
     a = synthetic_image(0, 1024, 1024, "shapes")
     assert J.encode(a, 75) == pil_bytes(a, 75)
+
+
+def test_c_abi_header_writer_matches_pillow_without_a_gpu():
+    """fie_jpeg_write_header is host code of libfie_b200.so: the 623 bytes before the scan must equal Pillow's (SOI, JFIF APP0, DQT x 2,
+    SOF0 4:2:0, DHT x 4, SOS) for any size and quality — checked here on the CPU box through the C-ABI."""
+    import ctypes
+    from fast_image_editing_with_generative_models_b200 import _lib
+    L = _lib.lib()
+    n = L.fie_jpeg_header_bytes()
+    assert n == 623
+    for (h, w, q) in [(1024, 1024, 75), (37, 53, 90), (1, 1, 30), (600, 800, 95)]:
+        buf = (ctypes.c_ubyte * 1024)()
+        assert L.fie_jpeg_write_header(buf, h, w, q) == n
+        ours = bytes(buf[:n])
+        ref = pil_bytes(np.zeros((h, w, 3), np.uint8), q)
+        assert ours == ref[:n], (h, w, q)
+        ql, qc = J.quant_tables(q)
+        assert ours == J.header(h, w, ql, qc)
