@@ -49,3 +49,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_argument_validation_reports_errors_without_a_gpu():
+    """Every entry point validates its arguments before touching CUDA and reports through the return code + fie_last_error(): the
+    reference's callers rely on ordinary exceptions per image (run_batch.py:250-261), never on a process abort."""
+    L = _lib.lib()
+    buf = (ctypes.c_ubyte * 64)()
+    p = ctypes.addressof(buf)
+    cases = [
+        (L.fie_canny_u8(p, p, 1, 8, 8, 2, 1, 100, 200, p, 1 << 20, None), "in_channels"),
+        (L.fie_gaussian_blur5_u8(p, p, 1, 8, 8, 1, None), "in-place"),
+        (L.fie_gaussian_blur5_u8(p, p + 16, 1, 8, 8, 2, None), "channels"),
+        (L.fie_jpeg_encode_u8(p, 1, 16, 16, 75, p, 16, p, p, 1 << 30, None), "out_stride"),
+        (L.fie_attn_vae_d512_f16(p, 512, p, 512, p, p, 512, 100, 500, 0.1, 0, 0, p, 1 << 30, None), "d % 64"),
+        (L.fie_fuse_lora_f32(p, p, p, 1.0, 0, 4, 8, None), "bad arguments"),
+        (L.fie_pack_conv3x3_c8_f16(p, p, 8, 9, 8, None), "cin <= 8"),
+    ]
+    for rc, needle in cases:
+        assert rc != 0
+    assert L.fie_canny_u8(p, p, 1, 8, 8, 2, 1, 100, 200, p, 1 << 20, None) != 0 and b"in_channels" in L.fie_last_error()
+    assert L.fie_attn_vae_d512_f16(p, 512, p, 512, p, p, 512, 100, 500, 0.1, 0, 0, p, 1 << 30, None) != 0 and b"d % 64" in L.fie_last_error()
+    # pure host queries
+    assert L.fie_jpeg_header_bytes() == 623 and L.fie_jpeg_max_bytes(1024, 1024) > 3 * 1024 * 1024
+    assert L.fie_jpeg_workspace_bytes(8, 1024, 1024) > 8 * 4096 * 384 * 2
+    assert L.fie_attn_vae_workspace_bytes(16384, 0, 0) >= 16384 * 16384 * 2 and L.fie_attn_vae_workspace_bytes(16384, 4096, 1) >= 4096 * 16384 * 6
