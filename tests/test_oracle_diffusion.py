@@ -165,3 +165,26 @@ def test_blocks_match_an_independent_torch_nn_restatement():
         want = r(xi, temb)
         got = O.resnet_block(p, rp, xi, temb, ucfg.norm_groups, ucfg.norm_eps)
     assert float((got - want).abs().max()) < 2e-5 * float(want.abs().max())
+
+
+def test_vae_attention_matches_an_independent_torch_nn_restatement():
+    """AutoencoderKL mid-block attention: ONE head over all C channels (scale 1 / sqrt(C)), GroupNorm before, residual after — against
+    nn.GroupNorm + nn.MultiheadAttention(num_heads=1), which own their reshapes and their scale."""
+    import torch.nn as nn
+    torch.manual_seed(2)
+    vcfg = C.tiny_vae_config()
+    p = S.make_vae_params(vcfg)
+    pre = "encoder.mid_block.attentions.0"
+    c = p[pre + ".to_q.weight"].shape[0]
+    gn = nn.GroupNorm(vcfg.norm_groups, c, eps=vcfg.norm_eps)
+    mha = nn.MultiheadAttention(c, 1, bias=True, batch_first=True)
+    with torch.no_grad():
+        gn.weight.copy_(p[pre + ".group_norm.weight"]); gn.bias.copy_(p[pre + ".group_norm.bias"])
+        mha.in_proj_weight.copy_(torch.cat([p[f"{pre}.to_{t}.weight"] for t in "qkv"]))
+        mha.in_proj_bias.copy_(torch.cat([p[f"{pre}.to_{t}.bias"] for t in "qkv"]))
+        mha.out_proj.weight.copy_(p[pre + ".to_out.0.weight"]); mha.out_proj.bias.copy_(p[pre + ".to_out.0.bias"])
+        x = torch.randn(2, c, 6, 5)
+        h = gn(x).flatten(2).transpose(1, 2)
+        want = mha(h, h, h, need_weights=False)[0].transpose(1, 2).reshape(x.shape) + x
+        got = O._vae_attn(p, pre, x, vcfg.norm_groups, vcfg.norm_eps)
+    assert float((got - want).abs().max()) < 2e-5 * float(want.abs().max())
