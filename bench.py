@@ -167,8 +167,10 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "1024x1024 4-step edit images/sec", "value": value, "unit": "images/s", "n_gpus": a.gpus,
             "steps": len(times), "steps_requested": a.steps, "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "images_per_step": 1, "strength": 0.5, "executed_steps": 2, "cfg": 1.5,
-                       "note": "a step of this arm = one image of the GPU arm's per-GPU batch (independent images)"},
+            # the GPU arm's config, key for key (same workload); what a step of THIS arm is (one of its independent images) is stated in
+            # cpu_baseline.sample and reference_step
+            "config": arm_config(a, max(a.gpus, 1), launch="torch CPU ops (fp32 oracle port of the diffusers pipeline), all host threads"),
+            "reference_step": "one timed step = ONE full 1024x1024 edit of one image of the workload's per-GPU batch (the images are independent)",
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample,
                              "seconds_per_edit": [round(x, 2) for x in times], "stages_s": {k: round(v, 2) for k, v in (stages or {}).items()}},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -181,6 +183,14 @@ def workload_name(a):
     tag = {0: "configs[0], the reference's CPU case", 2: "configs[2], latency", 3: "configs[3]"}[a.config]
     return (f"{a.model.upper()} + LCM + ControlNet-Canny(small) + VAE full edit, {'fp32' if a.config == 0 else 'fp16'}, {a.batch} x 1024x1024 "
             f"images/GPU (BASELINE {tag}), 4 LCM steps @ strength 0.5 (2 executed), CFG 1.5")
+
+
+def arm_config(a, world, launch):
+    """The `config` object of the JSON line — identical keys and workload for the B200 arm and the reference arm."""
+    return {"workload": workload_name(a), "images_per_gpu": a.batch, "global_batch": a.batch * world, "strength": 0.5, "executed_steps": 2,
+            "cfg": 1.5, "parallelism": f"dp{world} (independent images, NCCL all-gather of uint8 outputs)",
+            "weights": "seeded random-init of the named architectures", "launch": launch,
+            "l2": "inputs larger than L2 (5 GB weights + GB-scale activations per step)"}
 
 
 def load_peaks():
@@ -371,10 +381,7 @@ def main():
         line = {"metric": "1024x1024 4-step edit images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
                 "warmup": W, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16", "data": "synthetic",
-                "config": {"workload": workload_name(a), "images_per_gpu": B, "global_batch": B * world, "strength": 0.5, "executed_steps": 2,
-                           "cfg": 1.5, "parallelism": f"dp{world} (independent images, NCCL all-gather of uint8 outputs)",
-                           "weights": "seeded random-init of the named architectures", "launch": "eager" if a.no_graph else "cuda-graph replay of the whole edit",
-                           "l2": "inputs larger than L2 (5 GB weights + GB-scale activations per step)"},
+                "config": arm_config(a, world, launch="eager" if a.no_graph else "cuda-graph replay of the whole edit"),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "image_roofline": {"tflop_per_image": TFLOP_PER_IMAGE[a.model], "achieved_tflops_per_gpu": value / world * TFLOP_PER_IMAGE[a.model],
                                    "frac_of_peak": value / world * TFLOP_PER_IMAGE[a.model] / peak_tf},
