@@ -52,6 +52,36 @@ __device__ __forceinline__ void ex2_emulated2(f32x2 x2, float& p0, float& p1) {
     p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
+
+// O row (64 fp32 accumulators of one thread = one query row) * 1/l -> 64 fp16 = 128 contiguous bytes of the output.
+// 256-bit stores (one full 32-byte sector per instruction) when the row is 32-byte aligned, else 128-bit ones.
+__device__ __forceinline__ void store_o_row(__half* orow, const uint32_t (&r)[64], float inv_l, bool wide) {
+    if (wide) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = u * 16 + 2 * i;
+                const __half2 h = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
+                o[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            stg256(orow + u * 16, o);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = u * 8 + 2 * i;
+                hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
+            }
+            *reinterpret_cast<uint4*>(orow + u * 8) = v;
+        }
+    }
+}
+
 constexpr int ATT_BM = 128, ATT_BN = 128, ATT_D = 64, ATT_QT = 2, ATT_KV_STAGES = 3;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;                                   // 16 KiB (Q, K or V tile)
 constexpr int ATT_OFF_KV = ATT_QT * ATT_TILE_BYTES;                            // after Q0, Q1
@@ -178,6 +208,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
         const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr, tP = tmem + 384 + q * 64 + lane_addr;
         float m_run = -INFINITY, l_run = 0.f;
         const float sl2 = p.scale_log2;
+        const bool wide_o = (p.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;   // 32-byte aligned output rows
         // exp2 of one 64-column half against the reference max folded into mneg -> packed fp16 in pp (the A operand layout of
         // P V: two columns per 32-bit TMEM column); returns the row sum of the half.  FULL: no column masking.  WITH_MAX: also
         // folds the raw scores into the four running-max accumulators mx[] (one FMNMX3 per column pair), so that the maximum
@@ -318,18 +349,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64(const __grid_constant_
             uint32_t r[64];
             tmem_ld_32x64(tO, r);
             tmem_ld_wait();
-            if (qrow < p.nq) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int e = u * 8 + 2 * i;
-                        hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
-                    }
-                    *reinterpret_cast<uint4*>(orow + u * 8) = v;
-                }
-            }
+            if (qrow < p.nq) store_o_row(orow, r, inv_l, wide_o);
         }
         tc_fence_before();
     }
@@ -478,6 +498,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constan
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr, tP = tmem + 384 + q * 64 + lane_addr;
         const float sl2 = p.scale_log2;
+        const bool wide_o = (p.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;   // 32-byte aligned output rows
         auto exp_cols = [&](const uint32_t* r, int col0, float mneg, int kv_left, auto full_c, auto max_c, auto nu_c, uint32_t* pp, float (&mx)[4]) -> float {
             constexpr bool FULL = decltype(full_c)::value;
             constexpr bool WITH_MAX = decltype(max_c)::value;
@@ -604,18 +625,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_p(const __grid_constan
                 tmem_ld_32x64(tO, r);
                 tmem_ld_wait();
                 tc_fence_before();                          // the O_q read is complete before this thread's next p_full arrive lets the MMA warp overwrite it
-                if (qrow < p.nq) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int e = u * 8 + 2 * i;
-                            hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
-                        }
-                        *reinterpret_cast<uint4*>(orow + u * 8) = v;
-                    }
-                }
+                if (qrow < p.nq) store_o_row(orow, r, inv_l, wide_o);
             }
         }
         tc_fence_before();
@@ -729,6 +739,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         const uint32_t tS = tmem + q * 128 + lane_addr, tO = tmem + 256 + q * 64 + lane_addr;
         const float sl2 = p.scale_log2;
+        const bool wide_o = (p.ldo & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 31) == 0;   // 32-byte aligned output rows
         uint8_t* prow = sP + q * 32768 + row * 128;
         const int sw = row & 7;
         const int kv = p.nkv;                                 // <= 128 valid columns
@@ -780,19 +791,7 @@ __global__ void __launch_bounds__(384, 1) k_attention_d64_kv1(const __grid_const
             mbar_arrive(&o_free[q]);                              // S_q (read above) and O_q are in registers
             const float inv_l = 1.0f / l;
             const int qrow = (qp * ATT_QT + q) * ATT_BM + row;
-            if (qrow < p.nq) {
-                __half* orow = p.out + ((long long)b * p.nq + qrow) * p.ldo + head * ATT_D;
-#pragma unroll
-                for (int uu = 0; uu < 8; ++uu) {
-                    uint4 v; __half2* hh = reinterpret_cast<__half2*>(&v);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int e = uu * 8 + 2 * i;
-                        hh[i] = __floats2half2_rn(__uint_as_float(r[e]) * inv_l, __uint_as_float(r[e + 1]) * inv_l);
-                    }
-                    *reinterpret_cast<uint4*>(orow + uu * 8) = v;
-                }
-            }
+            if (qrow < p.nq) store_o_row(p.out + ((long long)b * p.nq + qrow) * p.ldo + head * ATT_D, r, inv_l, wide_o);
         }
         tc_fence_before();
     }
