@@ -5,7 +5,7 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="${FIE_OUT:-$HERE/../libfie_b200.so}"     # FIE_OUT: experiment builds (load with FIE_LIB=...)
 OBJ="${FIE_OBJ:-_obj}"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-SRCS="capi.cu canny.cu resize.cu elementwise.cu norm.cu conv_small.cu gemm_conv.cu attention.cu attn_vae.cu jpeg.cu pack.cu"
+SRCS="capi.cu canny.cu resize.cu elementwise.cu norm.cu conv_small.cu gemm_conv.cu attention.cu attn_vae.cu jpeg.cu pack.cu metrics.cu"
 mkdir -p "$HERE/$OBJ"
 pids=()
 for s in $SRCS; do

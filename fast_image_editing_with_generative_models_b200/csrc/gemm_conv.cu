@@ -191,6 +191,9 @@ __device__ __noinline__ void epi_slow_chunk(const GemmParams& p, uint32_t taddr,
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf_f(v[i]);
     } else if (p.act == FIE_ACT_QUICKGELU) {
         for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
+    } else if (p.act == FIE_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= p.scale;
@@ -624,6 +627,9 @@ __global__ void __launch_bounds__(384, 1) k_gemm_conv(const __grid_constant__ Ge
                         } else if (p.act == FIE_ACT_QUICKGELU) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
+                        } else if (p.act == FIE_ACT_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
                         }
                     }
                     if (p.m_bias) {
@@ -789,7 +795,7 @@ static int fill_epilogue(GemmParams& p, const fie_epilogue* ep, long long M, int
     p.ld_row_bias = ep->ld_row_bias > 0 ? ep->ld_row_bias : N;
     p.m_bias = ep->m_bias; p.residual = (const __half*)ep->residual; p.ld_res = ep->ld_res;
     p.scale = ep->scale; p.act = ep->act; p.out_f32 = ep->out_f32;
-    FIE_REQUIRE(p.act >= 0 && p.act <= 4, "epilogue: bad act %d", p.act);
+    FIE_REQUIRE(p.act >= 0 && p.act <= FIE_ACT_RELU, "epilogue: bad act %d", p.act);
     FIE_REQUIRE(!(p.act == FIE_ACT_GEGLU && (N % 64)), "GEGLU needs N %% 64 == 0");
     FIE_REQUIRE(!(p.residual && p.ld_res <= 0), "epilogue: residual needs ld_res");
     p.gn_stats = (unsigned long long*)ep->gn_stats; p.gn_groups = ep->gn_groups; p.gn_rows = ep->gn_rows_per_image; p.gn_cpg = 0;

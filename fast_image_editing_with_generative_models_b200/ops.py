@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import Epilogue, check
 
-ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_QUICKGELU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_QUICKGELU, ACT_RELU = 0, 1, 2, 3, 4, 5
 LAUNCHES = 0  # number of our kernels launched through this module (bench reports it)
 _KERNELS_PER_CALL = {"canny3": 4, "canny1": 3, "groupnorm": 2}
 
@@ -180,18 +180,18 @@ def jpeg_bytes(img_u8: torch.Tensor, quality: int = 75):
 _RS_TABLES = {}
 
 
-def resize_lanczos(img_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
-    """uint8 [N,H,W,3] (CUDA) -> uint8 [N,out_h,out_w,3], bit-identical to PIL ``Image.resize((out_w, out_h), Image.LANCZOS)``."""
-    from .resize import lanczos_tables
-    _req(img_u8, torch.uint8, "resize_lanczos")
+def resize_pillow(img_u8: torch.Tensor, out_h: int, out_w: int, filter_name: str = "lanczos") -> torch.Tensor:
+    """uint8 [N,H,W,3] (CUDA) -> uint8 [N,out_h,out_w,3], bit-identical to PIL ``Image.resize((out_w, out_h), Image.LANCZOS | BICUBIC)``."""
+    from .resize import pillow_tables
+    _req(img_u8, torch.uint8, "resize_pillow")
     n, h, w, c = img_u8.shape
     if c != 3:
-        raise _lib.FieError("resize_lanczos: RGB images expected")
+        raise _lib.FieError("resize_pillow: RGB images expected")
     dev = img_u8.device
-    key = (h, w, out_h, out_w, str(dev))
+    key = (filter_name, h, w, out_h, out_w, str(dev))
     if key not in _RS_TABLES:
-        bx, kx, ksx = lanczos_tables(w, out_w)
-        by, ky, ksy = lanczos_tables(h, out_h)
+        bx, kx, ksx = pillow_tables(w, out_w, filter_name)
+        by, ky, ksy = pillow_tables(h, out_h, filter_name)
         _RS_TABLES[key] = (bx.to(dev), kx.to(dev), ksx, by.to(dev), ky.to(dev), ksy)
     bx, kx, ksx, by, ky, ksy = _RS_TABLES[key]
     out = torch.empty((n, out_h, out_w, 3), dtype=torch.uint8, device=dev)
@@ -201,6 +201,161 @@ def resize_lanczos(img_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor
               "fie_resample_lanczos_u8")
     _count((out_w != w) + (out_h != h))
     return out
+
+
+def resize_lanczos(img_u8: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    return resize_pillow(img_u8, out_h, out_w, "lanczos")
+
+
+def _f3(vals):
+    return None if vals is None else (ctypes.c_float * 3)(*[float(v) for v in vals])
+
+
+def resize_aa_normalize(img: torch.Tensor, out_h: int, out_w: int, mean=None, std=None) -> torch.Tensor:
+    """uint8 (read as v/255) or fp32 [N,H,W,3] -> fp32 [N,out_h,out_w,3]: torchvision ``Resize(antialias=True)`` (bilinear) followed by
+    ``Normalize(mean, std)`` — DinoDistanceMetric._to_tensor, reference ``src/metrics.py:124-136``."""
+    from .resize import aa_bilinear_tables
+    if img.dtype not in (torch.uint8, torch.float32) or not img.is_cuda or not img.is_contiguous() or img.shape[-1] != 3:
+        raise _lib.FieError("resize_aa_normalize: contiguous uint8 / fp32 CUDA [N,H,W,3] expected")
+    n, h, w, _ = img.shape
+    dev = img.device
+    key = ("aa", h, w, out_h, out_w, str(dev))
+    if key not in _RS_TABLES:
+        bx, kx, ksx = aa_bilinear_tables(w, out_w)
+        by, ky, ksy = aa_bilinear_tables(h, out_h)
+        _RS_TABLES[key] = (bx.to(dev), kx.to(dev), ksx, by.to(dev), ky.to(dev), ksy)
+    bx, kx, ksx, by, ky, ksy = _RS_TABLES[key]
+    out = torch.empty((n, out_h, out_w, 3), dtype=torch.float32, device=dev)
+    tmp = torch.empty((n, h, out_w, 3), dtype=torch.float32, device=dev) if out_w != w else None
+    check(_lib.lib().fie_resample_f32(_p(img), int(img.dtype == torch.uint8), _p(out), _p(tmp), n, h, w, out_h, out_w, _p(bx), _p(kx), ksx, _p(by), _p(ky), ksy,
+                                      _f3(mean), _f3(std), _stream()), "fie_resample_f32")
+    _count(1 + (out_w != w))
+    return out
+
+
+def ssim_u8(a: torch.Tensor, b: torch.Tensor, kernel_size: int = 11, sigma: float = 1.5, k1: float = 0.01, k2: float = 0.03) -> torch.Tensor:
+    """uint8 [N,H,W,C] pairs -> fp64 [N] mean SSIM (torchmetrics ``StructuralSimilarityIndexMeasure(data_range=1.0)`` per image)."""
+    _req(a, torch.uint8, "ssim_u8"); _req(b, torch.uint8, "ssim_u8")
+    if a.shape != b.shape or a.dim() != 4:
+        raise _lib.FieError("ssim_u8: two [N,H,W,C] images of one shape expected")
+    n, h, w, c = a.shape
+    out = torch.empty((n,), dtype=torch.float64, device=a.device)
+    check(_lib.lib().fie_ssim_u8(_p(a), _p(b), n, h, w, c, kernel_size, float(sigma), float(k1), float(k2), _p(out), _stream()), "fie_ssim_u8")
+    _count()
+    return out / float(c * (h - kernel_size + 1) * (w - kernel_size + 1))
+
+
+def sqdiff_u8(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """uint8 [N,...] pairs -> int64 [N] exact sums of squared byte differences."""
+    _req(a, torch.uint8, "sqdiff_u8"); _req(b, torch.uint8, "sqdiff_u8")
+    if a.shape != b.shape:
+        raise _lib.FieError("sqdiff_u8: shapes differ")
+    n = a.shape[0]
+    out = torch.empty((n,), dtype=torch.int64, device=a.device)
+    check(_lib.lib().fie_sqdiff_u8(_p(a), _p(b), n, a.numel() // n, _p(out), _stream()), "fie_sqdiff_u8")
+    _count()
+    return out
+
+
+def patchify(img: torch.Tensor, patch: int, mean=None, std=None) -> torch.Tensor:
+    """uint8 (v/255) or fp32 [N,H,W,3] -> fp16 [N*(H/P)*(W/P), P*P*3] patch rows (K order py, px, c), optionally normalised."""
+    if img.dtype not in (torch.uint8, torch.float32) or not img.is_cuda or not img.is_contiguous() or img.shape[-1] != 3:
+        raise _lib.FieError("patchify: contiguous uint8 / fp32 CUDA [N,H,W,3] expected")
+    n, h, w, _ = img.shape
+    out = torch.empty((n * (h // patch) * (w // patch), patch * patch * 3), dtype=torch.float16, device=img.device)
+    check(_lib.lib().fie_patchify_f16(_p(img), int(img.dtype == torch.uint8), _p(out), n, h, w, patch, _f3(mean), _f3(std), _stream()), "fie_patchify_f16")
+    _count()
+    return out
+
+
+def vit_assemble(patches: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, n: int) -> torch.Tensor:
+    """patch rows fp16 [n*np, c] + class token [c] + position embeddings [np+1, c] -> tokens fp16 [n*(np+1), c]."""
+    for t in (patches, cls, pos):
+        _req(t, torch.float16, "vit_assemble")
+    c = patches.shape[-1]
+    npatch = patches.shape[0] // n
+    if pos.shape[0] != npatch + 1 or pos.shape[-1] != c or cls.numel() != c:
+        raise _lib.FieError("vit_assemble: position embeddings must be [n_patches + 1, c]")
+    out = torch.empty((n * (npatch + 1), c), dtype=torch.float16, device=patches.device)
+    check(_lib.lib().fie_vit_assemble_f16(_p(patches), _p(cls), _p(pos), _p(out), n, npatch, c, _stream()), "fie_vit_assemble_f16")
+    _count()
+    return out
+
+
+def l2norm_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None, eps: float = 1e-4) -> torch.Tensor:
+    """fp16 [rows, c] (row stride allowed) -> rows / max(|row|, eps)."""
+    if x.dtype != torch.float16 or not x.is_cuda or x.stride(-1) != 1:
+        raise _lib.FieError("l2norm_rows: fp16 CUDA rows with unit inner stride required")
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty((rows, c), dtype=torch.float16, device=x.device)
+    check(_lib.lib().fie_l2norm_rows_f16(_p(x), x.stride(0), _p(out), out.stride(0), rows, c, float(eps), _stream()), "fie_l2norm_rows_f16")
+    _count()
+    return out
+
+
+def sqdiff_f32(a: torch.Tensor, b: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """fp32 matrices (row strides allowed) -> fp64 [1] sum of squared differences over the leading rows x cols window."""
+    for t in (a, b):
+        if t.dtype != torch.float32 or not t.is_cuda or t.stride(-1) != 1:
+            raise _lib.FieError("sqdiff_f32: fp32 CUDA rows with unit inner stride required")
+    out = torch.empty((1,), dtype=torch.float64, device=a.device)
+    check(_lib.lib().fie_sqdiff_f32(_p(a), a.stride(0), _p(b), b.stride(0), rows, cols, _p(out), _stream()), "fie_sqdiff_f32")
+    _count()
+    return out
+
+
+def cosine_rows(a: torch.Tensor, b: torch.Tensor, eps: float = 1e-8) -> torch.Tensor:
+    """fp16 [rows, c] pairs -> fp32 [rows] cosine similarities."""
+    for t in (a, b):
+        if t.dtype != torch.float16 or not t.is_cuda or t.stride(-1) != 1:
+            raise _lib.FieError("cosine_rows: fp16 CUDA rows with unit inner stride required")
+    rows, c = a.shape
+    out = torch.empty((rows,), dtype=torch.float32, device=a.device)
+    check(_lib.lib().fie_cosine_rows_f16(_p(a), a.stride(0), _p(b), b.stride(0), _p(out), rows, c, float(eps), _stream()), "fie_cosine_rows_f16")
+    _count()
+    return out
+
+
+def im2col3x3(x: torch.Tensor, stride: int = 1, pad: int = 1, shift=None, scale=None, kpad: Optional[int] = None) -> torch.Tensor:
+    """fp16 [N,H,W,C] (channel-strided views allowed) or the uint8 RGB network input -> fp16 [N*OH*OW, kpad >= 9C] (K order ky, kx, c;
+    default kpad = 9C rounded up to 8, columns beyond 9C zero)."""
+    if x.dtype not in (torch.uint8, torch.float16) or not x.is_cuda or x.stride(-1) != 1:
+        raise _lib.FieError("im2col3x3: fp16 / uint8 CUDA NHWC tensor required")
+    n, h, w, c = x.shape
+    ld = x.stride(-2)
+    if x.stride(1) != w * ld or x.stride(0) != h * w * ld:
+        raise _lib.FieError("im2col3x3: only the channel dimension may be strided")
+    oh, ow = (h + 2 * pad - 3) // stride + 1, (w + 2 * pad - 3) // stride + 1
+    kpad = (9 * c + 7) // 8 * 8 if kpad is None else int(kpad)
+    out = torch.empty((n * oh * ow, kpad), dtype=torch.float16, device=x.device)
+    check(_lib.lib().fie_im2col3x3_f16(_p(x), int(x.dtype == torch.uint8), ld, _p(out), n, h, w, c, stride, pad, kpad, _f3(shift), _f3(scale), _stream()),
+          "fie_im2col3x3_f16")
+    _count()
+    return out
+
+
+def maxpool3s2_ceil(x: torch.Tensor) -> torch.Tensor:
+    """fp16 [N,H,W,C] -> MaxPool2d(3, 2, ceil_mode=True)."""
+    _req(x, torch.float16, "maxpool3s2_ceil")
+    n, h, w, c = x.shape
+    oh, ow = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+    out = torch.empty((n, oh, ow, c), dtype=torch.float16, device=x.device)
+    check(_lib.lib().fie_maxpool3s2_ceil_f16(_p(x), _p(out), n, h, w, c, _stream()), "fie_maxpool3s2_ceil_f16")
+    _count()
+    return out
+
+
+def lpips_layer(f0: torch.Tensor, f1: torch.Tensor, lin: torch.Tensor) -> torch.Tensor:
+    """fp16 [N,H,W,C] feature pairs, lin fp32 [C] -> fp64 [N]: spatial mean of sum_c lin[c] (unit(f0) - unit(f1))^2."""
+    _req(f0, torch.float16, "lpips_layer"); _req(f1, torch.float16, "lpips_layer"); _req(lin, torch.float32, "lpips_layer")
+    n, h, w, c = f0.shape
+    if f1.shape != f0.shape or lin.numel() != c:
+        raise _lib.FieError("lpips_layer: shape mismatch")
+    out = torch.empty((n,), dtype=torch.float64, device=f0.device)
+    check(_lib.lib().fie_lpips_layer_f16(_p(f0), _p(f1), _p(lin), n, h * w, c, _p(out), _stream()), "fie_lpips_layer_f16")
+    _count()
+    return out / float(h * w)
 
 
 def preprocess(img_u8: torch.Tensor, c_out: int = 4, normalize: bool = True) -> torch.Tensor:

@@ -69,6 +69,46 @@ int fie_resample_lanczos_u8(const void* in_u8, void* out_u8, void* tmp_u8, int n
                             const int* bounds_x, const int* coeff_x, int ksize_x, const int* bounds_y, const int* coeff_y, int ksize_y,
                             void* stream);
 
+/* ---- Evaluation metrics: the non-GEMM stages of the reference's MetricsCalculator, src/metrics.py:150-381 ----
+ * The networks themselves (CLIP ViT-B/16 towers, DINO ViT-B/8, SqueezeNet 1.1) run on fie_gemm_f16 / fie_layernorm_f16 /
+ * fie_attention_d64_f16. */
+/* torchmetrics StructuralSimilarityIndexMeasure(data_range=1.0), src/metrics.py:175-177,214-237: a, b uint8 [n,h,w,c] read as v/255;
+ * Gaussian window kernel_size (odd, <= 11; default 11) / sigma (1.5), k1 0.01, k2 0.03, valid region only (what the reflect-pad +
+ * crop of torchmetrics leaves).  out_sum double [n] = sum of the SSIM map over channels and valid pixels (mean = / (c (h-k+1) (w-k+1))).  Pixels are float32 v/255 as in
+ * the reference; the local moments are accumulated in double (float32 moments carry ~1e-4 of cancellation noise in flat regions). */
+int fie_ssim_u8(const void* a, const void* b, int n, int h, int w, int c, int kernel_size, float sigma, float k1, float k2,
+                double* out_sum, void* stream);
+/* exact sum of (a - b)^2 over per_image bytes of each image -> uint64 [n]: MSE = sum / (255^2 per_image), PSNR = -10 log10(MSE)
+ * (PeakSignalNoiseRatio / MeanSquaredError at src/metrics.py:190-197,285-336) */
+int fie_sqdiff_u8(const void* a, const void* b, int n, long long per_image, unsigned long long* out, void* stream);
+/* torchvision transforms.Resize(size, antialias=True) + Normalize on a float image (DinoDistanceMetric._to_tensor, src/metrics.py:124-136):
+ * in uint8 (read as v/255) or fp32 [n,h,w,3] -> fp32 [n,oh,ow,3] = (resampled - mean) / std.  Separable, horizontal then vertical;
+ * bounds_* int32 [out,2] = (first input index, count), coeff_* fp32 [out,ksize] normalised weights (resize.py: aten's
+ * _upsample_bilinear2d_aa tables); a pass whose size does not change is skipped.  tmp: fp32 [n,h,ow,3] when ow != w. */
+int fie_resample_f32(const void* in, int in_is_u8, void* out_f32, void* tmp_f32, int n, int h, int w, int oh, int ow,
+                     const int* bounds_x, const float* coeff_x, int ksize_x, const int* bounds_y, const float* coeff_y, int ksize_y,
+                     const float* mean3, const float* std3, void* stream);
+/* ViT patch embedding as a GEMM operand: in uint8 (v/255) or fp32 [n,h,w,3] -> fp16 [n (h/P) (w/P), P P 3], K order (py, px, c);
+ * mean3/std3 (host pointers, both or neither) normalise on the way */
+int fie_patchify_f16(const void* in, int in_is_u8, void* out, int n, int h, int w, int patch, const float* mean3, const float* std3, void* stream);
+/* tokens [n, n_patches + 1, c] = (class token | patch rows [n, n_patches, c]) + position embeddings [n_patches + 1, c]; fp16, c % 8 == 0 */
+int fie_vit_assemble_f16(const void* patches, const void* cls, const void* pos, void* out, int n, int n_patches, int c, void* stream);
+/* out[r] = in[r] / max(|in[r]|, eps), fp16 rows (fp32 math): the cosine self-similarity of DINO keys (src/metrics.py:79-84) is then a GEMM */
+int fie_l2norm_rows_f16(const void* in, long long ld_in, void* out, long long ld_out, long long rows, int c, float eps, void* stream);
+/* out_sum[0] = sum over a rows x cols window of (a - b)^2, fp32 inputs, double accumulation (F.mse_loss of two similarity maps, :146) */
+int fie_sqdiff_f32(const void* a, long long lda, const void* b, long long ldb, long long rows, int cols, double* out_sum, void* stream);
+/* out[r] = <a[r], b[r]> / max(|a[r]| |b[r]|, eps), fp16 rows -> fp32 [rows]: CLIPScore = 100 max(cos, 0) (src/metrics.py:264-283) */
+int fie_cosine_rows_f16(const void* a, long long lda, const void* b, long long ldb, float* out, long long rows, int c, float eps, void* stream);
+/* LPIPS / SqueezeNet 1.1 (LearnedPerceptualImagePatchSimilarity(net_type='squeeze'), src/metrics.py:180-182,239-262).
+ * im2col of a 3x3 convolution for fie_gemm_f16: in fp16 [n,h,w,ld_in] (first c channels) -> fp16 [n oh ow, kpad], K order (ky, kx, c),
+ * columns >= 9c zero.  in_is_u8: the RGB network input, mapped to ((v/255*2-1) - shift3[c]) / scale3[c] (LPIPS ScalingLayer). */
+int fie_im2col3x3_f16(const void* in, int in_is_u8, long long ld_in, void* out, int n, int h, int w, int c, int stride, int pad, int kpad,
+                      const float* shift3, const float* scale3, void* stream);
+/* MaxPool2d(3, stride 2, ceil_mode=True): fp16 [n,h,w,c] -> [n, ceil((h-3)/2)+1, ceil((w-3)/2)+1, c]; c % 8 == 0 */
+int fie_maxpool3s2_ceil_f16(const void* in, void* out, int n, int h, int w, int c, void* stream);
+/* one LPIPS layer: out_sum double [n] = sum over pixels of sum_c lin[c] (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2; f0, f1 fp16 [n,hw,c] */
+int fie_lpips_layer_f16(const void* f0, const void* f1, const float* lin, int n, long long hw, int c, double* out_sum, void* stream);
+
 /* ---- Pre/post-processing: replaces VaeImageProcessor.preprocess/postprocess inside the diffusers call
  *      at reference src/pipeline.py:261-272 ---- */
 /* uint8 [n,h,w,3] -> fp16 [n,h,w,c_out] (c_out >= 3, extra channels zero): x/127.5-1 (normalize=1) or x/255 */
@@ -117,7 +157,8 @@ int fie_layernorm_f16(const void* x, void* out, long long rows, int c, const flo
 /* ---- Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM + TMA) ----
  * D[M, N] = epilogue( A[M, K] * B[N, K]^T ), fp16 operands, fp32 accumulation in TMEM.
  * Replaces F.linear (cuBLASLt) and F.conv2d (cuDNN) in every diffusers module on the path. */
-enum { FIE_ACT_NONE = 0, FIE_ACT_SILU = 1, FIE_ACT_GEGLU = 2, FIE_ACT_GELU = 3 /* exact erf GELU */, FIE_ACT_QUICKGELU = 4 /* x*sigmoid(1.702x), CLIP-L */ };
+enum { FIE_ACT_NONE = 0, FIE_ACT_SILU = 1, FIE_ACT_GEGLU = 2, FIE_ACT_GELU = 3 /* exact erf GELU */, FIE_ACT_QUICKGELU = 4 /* x*sigmoid(1.702x), CLIP-L */,
+       FIE_ACT_RELU = 5 /* max(x, 0): the SqueezeNet of the LPIPS metric */ };
 
 typedef struct {
     /* epilogue: v = acc + col_bias[n] + row_bias[m / rows_per_group][n]  (+ chan_bias[m] if per-row bias)
