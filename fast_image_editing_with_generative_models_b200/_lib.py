@@ -38,7 +38,7 @@ SIGNATURES = {
     "fie_jpeg_max_bytes": (c_size_t, [c_int, c_int]),
     "fie_jpeg_encode_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t, c_void_p]),
     "fie_resample_lanczos_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
-    "fie_ssim_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "fie_ssim_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p]),
     "fie_sqdiff_u8": (c_int, [c_void_p, c_void_p, c_int, c_ll, c_void_p, c_void_p]),
     "fie_resample_f32": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                  c_void_p, c_void_p, c_void_p]),

@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(256) k_sqdiff_f32(const float* __restrict__ a,
     double acc = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / cols; const int c = (int)(i - r * cols);
-        const float d = a[r * lda + c] - b[r * ldb + c];
-        acc += (double)d * (double)d;
+        const double d = (double)a[r * lda + c] - (double)b[r * ldb + c];
+        acc += d * d;
     }
     const double s = block_sum_double(acc, red);
     if (threadIdx.x == 0) atomicAdd(out, s);
@@ -299,7 +299,10 @@ __global__ void __launch_bounds__(256) k_lpips_layer(const __half* __restrict__ 
         qa = warp_sum(qa); qb = warp_sum(qb);
         const float ia = 1.0f / (sqrtf(qa) + 1e-10f), ib = 1.0f / (sqrtf(qb) + 1e-10f);
         float s = 0.f;
-        for (int i = lane; i < c; i += 32) { const float d = __half2float(a[i]) * ia - __half2float(b[i]) * ib; s = fmaf(__ldg(lin + i), d * d, s); }
+        for (int i = lane; i < c; i += 32) {
+            const float d = __fmul_rn(__half2float(a[i]), ia) - __fmul_rn(__half2float(b[i]), ib);     // no FMA contraction: identical features give exactly 0
+            s = fmaf(__ldg(lin + i), d * d, s);
+        }
         acc += (double)s;                                   // every lane holds a partial: summed over the block below
     }
     const double tot = block_sum_double(acc, red);
@@ -313,23 +316,23 @@ using namespace fie;
     do { cudaError_t e_ = cudaMemsetAsync((ptr), 0, (bytes), (stream));                                       \
          if (e_ != cudaSuccess) { set_error("%s: memset: %s", (what), cudaGetErrorString(e_)); return FIE_ERR_CUDA; } } while (0)
 
-extern "C" int fie_ssim_u8(const void* a, const void* b, int n, int h, int w, int c, int kernel_size, float sigma, float k1, float k2,
+extern "C" int fie_ssim_u8(const void* a, const void* b, int n, int h, int w, int c, int kernel_size, double sigma, double k1, double k2,
                            double* out_sum, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FIE_REQUIRE(a && b && out_sum && n > 0 && c > 0, "fie_ssim_u8: bad args");
-    FIE_REQUIRE(kernel_size >= 1 && kernel_size <= SS_MAXK && (kernel_size & 1) && sigma > 0.f, "fie_ssim_u8: kernel_size must be odd and <= %d", SS_MAXK);
+    FIE_REQUIRE(kernel_size >= 1 && kernel_size <= SS_MAXK && (kernel_size & 1) && sigma > 0., "fie_ssim_u8: kernel_size must be odd and <= %d", SS_MAXK);
     FIE_REQUIRE(h >= kernel_size && w >= kernel_size, "fie_ssim_u8: image smaller than the window");
     FIE_REQUIRE((long long)n * c <= 65535, "fie_ssim_u8: too many (image, channel) planes");
     SsimWeights wt;
     double tot = 0.;
-    for (int i = 0; i < kernel_size; ++i) { const double d = (double)(i - (kernel_size - 1) / 2) / (double)sigma; wt.w[i] = exp(-(d * d) / 2.0); tot += wt.w[i]; }
+    for (int i = 0; i < kernel_size; ++i) { const double d = (double)(i - (kernel_size - 1) / 2) / sigma; wt.w[i] = exp(-(d * d) / 2.0); tot += wt.w[i]; }
     for (int i = 0; i < kernel_size; ++i) wt.w[i] /= tot;
     for (int i = kernel_size; i < SS_MAXK; ++i) wt.w[i] = 0.;
     FIE_ZERO(out_sum, sizeof(double) * n, stream, "fie_ssim_u8");
     const int vh = h - kernel_size + 1, vw = w - kernel_size + 1;
     dim3 grid(ceil_div(vw, SS_TW), ceil_div(vh, SS_TH), n * c);
     FIE_REQUIRE(grid.y <= 65535, "fie_ssim_u8: image too tall");
-    k_ssim_u8<<<grid, 256, 0, stream>>>((const uint8_t*)a, (const uint8_t*)b, h, w, c, kernel_size, wt, (double)k1 * k1, (double)k2 * k2, out_sum);
+    k_ssim_u8<<<grid, 256, 0, stream>>>((const uint8_t*)a, (const uint8_t*)b, h, w, c, kernel_size, wt, k1 * k1, k2 * k2, out_sum);
     return check_launch("fie_ssim_u8");
 }
 

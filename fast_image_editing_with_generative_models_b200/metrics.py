@@ -81,7 +81,7 @@ def _as_u8_nhwc(img, dev) -> torch.Tensor:
     else:
         if hasattr(img, "convert"):
             img = img.convert("RGB")
-        arr = torch.from_numpy(np.ascontiguousarray(np.asarray(img, dtype=np.uint8)))
+        arr = torch.from_numpy(np.array(img, dtype=np.uint8))                  # (a copy: PIL hands out read-only buffers)
     if arr.dim() != 3 or arr.shape[-1] != 3:
         raise ValueError(f"metrics: RGB image expected, got shape {tuple(arr.shape)}")
     if not arr.is_cuda:
@@ -126,15 +126,20 @@ class DinoDistanceMetric:
             sims.append(ops.gemm(kn[:t], kn, out_f32=True))                     # [T, tp] fp32 cosine similarities
         return sims, t
 
+    def _distance_dev(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        """uint8 CUDA [1,H,W,3] pair -> fp64 [1] distance on the device (no host synchronisation)."""
+        if a.shape == b.shape:                                   # one ViT pass over both images (rows of a batch are computed independently)
+            (sa, sb), t = self._self_similarity(torch.cat([a, b], 0))
+        else:
+            (sa,), t = self._self_similarity(a)
+            (sb,), tb = self._self_similarity(b)
+            if t != tb:
+                raise ValueError("DinoDistanceMetric: source and edited image give different token counts")
+        return ops.sqdiff_f32(sb, sa, t, t) / float(t * t)
+
     def calculate_distance(self, source_img, edited_img) -> float:
         with torch.cuda.device(self.device), torch.no_grad():
-            a, b = _as_u8_nhwc(source_img, self.device), _as_u8_nhwc(edited_img, self.device)
-            (sa,), t = self._self_similarity(a)
-            (sb,), _ = self._self_similarity(b)
-            if sa.shape != sb.shape:
-                raise ValueError("DinoDistanceMetric: source and edited image give different token counts")
-            total = ops.sqdiff_f32(sb, sa, t, t)
-            return float(total.item()) / float(t * t)
+            return float(self._distance_dev(_as_u8_nhwc(source_img, self.device), _as_u8_nhwc(edited_img, self.device)).item())
 
 
 class MetricsCalculator:
@@ -214,27 +219,12 @@ class MetricsCalculator:
             raise RuntimeError(f"MetricsCalculator(networks=False) has no {name} network")
         return net
 
-    # ---- the reference's public methods --------------------------------------------------------------------------------------
-    def calculate_ssim(self, img1, img2) -> float:
-        with torch.cuda.device(self.device):
-            return float(ops.ssim_u8(self._at_metric_size(img1), self._at_metric_size(img2)).item())
+    # ---- device-side halves: uint8 CUDA tensors in, device scalars out (no host synchronisation) -----------------------------------
+    def _ssim_dev(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return ops.ssim_u8(a, b)
 
-    def calculate_lpips(self, img1, img2) -> float:
-        with torch.cuda.device(self.device):
-            return float(self._need(self.lpips_net, "LPIPS").distance(self._at_metric_size(img1), self._at_metric_size(img2)).item())
-
-    def _squared_error(self, img1, img2):
-        a, b = self._at_metric_size(img1), self._at_metric_size(img2)
-        return int(ops.sqdiff_u8(a, b).item()), a.numel()
-
-    def calculate_mse(self, img1, img2) -> float:
-        with torch.cuda.device(self.device):
-            s, n = self._squared_error(img1, img2)
-        return s / (255.0 * 255.0 * n)
-
-    def calculate_psnr(self, img1, img2) -> float:
-        mse = self.calculate_mse(img1, img2)
-        return float("inf") if mse == 0.0 else 10.0 * math.log10(1.0 / mse)
+    def _lpips_dev(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+        return self._need(self.lpips_net, "LPIPS").distance(a, b)
 
     def clip_image_input(self, img) -> torch.Tensor:
         """The CLIP image processor on one image: Pillow-bicubic resize of the shorter side to the tower's input size, centre crop -> uint8
@@ -250,27 +240,62 @@ class MetricsCalculator:
             t = t[:, top:top + s, left:left + s].contiguous()
         return t
 
-    def calculate_clip_score(self, img, text) -> float:
+    def _clip_cosine_dev(self, img, text) -> torch.Tensor:
+        x = self.clip_image_input(img)
+        img_emb = self.clip_vision.embed(x, vit.CLIP_MEAN, vit.CLIP_STD)
+        if self._tokenizer is not None:
+            ids = torch.tensor(self._tokenizer([text]), dtype=torch.int64)
+        else:
+            ids = pseudo_token_ids(text, self._text_vocab).unsqueeze(0)
+        _, _, txt_emb = self._need(self.clip_text, "CLIP").forward(ids)
+        return ops.cosine_rows(img_emb, txt_emb)
+
+    @staticmethod
+    def _mse_psnr(sq_sum: int, count: int):
+        mse = sq_sum / (255.0 * 255.0 * count)
+        return mse, (float("inf") if mse == 0.0 else 10.0 * math.log10(1.0 / mse))
+
+    # ---- the reference's public methods --------------------------------------------------------------------------------------
+    def calculate_ssim(self, img1, img2) -> float:
+        with torch.cuda.device(self.device):
+            return float(self._ssim_dev(self._at_metric_size(img1), self._at_metric_size(img2)).item())
+
+    def calculate_lpips(self, img1, img2) -> float:
+        with torch.cuda.device(self.device):
+            return float(self._lpips_dev(self._at_metric_size(img1), self._at_metric_size(img2)).item())
+
+    def calculate_mse(self, img1, img2) -> float:
+        with torch.cuda.device(self.device):
+            a, b = self._at_metric_size(img1), self._at_metric_size(img2)
+            return self._mse_psnr(int(ops.sqdiff_u8(a, b).item()), a.numel())[0]
+
+    def calculate_psnr(self, img1, img2) -> float:
+        with torch.cuda.device(self.device):
+            a, b = self._at_metric_size(img1), self._at_metric_size(img2)
+            return self._mse_psnr(int(ops.sqdiff_u8(a, b).item()), a.numel())[1]
+
+    def clip_cosine(self, img, text) -> float:
+        """cos(image features, text features) of the CLIP towers (CLIPScore before the x100 and the floor at 0)."""
         with torch.cuda.device(self.device), torch.no_grad():
-            x = self.clip_image_input(img)
-            img_emb = self.clip_vision.embed(x, vit.CLIP_MEAN, vit.CLIP_STD)
-            if self._tokenizer is not None:
-                ids = torch.tensor(self._tokenizer([text]), dtype=torch.int64)
-            else:
-                ids = pseudo_token_ids(text, self._text_vocab).unsqueeze(0)
-            _, _, txt_emb = self._need(self.clip_text, "CLIP").forward(ids)
-            cos = float(ops.cosine_rows(img_emb, txt_emb).item())
-        return max(100.0 * cos, 0.0)
+            return float(self._clip_cosine_dev(img, text).item())
+
+    def calculate_clip_score(self, img, text) -> float:
+        return max(100.0 * self.clip_cosine(img, text), 0.0)
 
     def calculate_all_metrics(self, source_img, edited_img, prompt) -> Dict[str, float]:
-        metrics = {}
-        metrics["ssim"] = self.calculate_ssim(source_img, edited_img)
-        metrics["lpips"] = self.calculate_lpips(source_img, edited_img)
-        metrics["clip_score"] = self.calculate_clip_score(edited_img, prompt)
-        metrics["psnr"] = self.calculate_psnr(source_img, edited_img)
-        metrics["mse"] = self.calculate_mse(source_img, edited_img)
-        metrics["dino_distance"] = self._need(self.dino_metric, "DINO").calculate_distance(source_img, edited_img)
-        return metrics
+        """All six metrics of one (source, edited, prompt) triple — reference ``src/metrics.py:338-381`` — with each image uploaded once,
+        the 512^2 copies made once, every kernel queued before the first result is read back (one host synchronisation per pair)."""
+        with torch.cuda.device(self.device), torch.no_grad():
+            src, edt = self._pil_to_tensor(source_img), self._pil_to_tensor(edited_img)
+            a, b = self._at_metric_size(src), self._at_metric_size(edt)
+            ssim = self._ssim_dev(a, b)
+            lp = self._lpips_dev(a, b)
+            cos = self._clip_cosine_dev(edt, prompt)
+            sq = ops.sqdiff_u8(a, b)
+            dino = self._need(self.dino_metric, "DINO")._distance_dev(src, edt)
+            mse, psnr = self._mse_psnr(int(sq.item()), a.numel())
+            return {"ssim": float(ssim.item()), "lpips": float(lp.item()), "clip_score": max(100.0 * float(cos.item()), 0.0), "psnr": psnr, "mse": mse,
+                    "dino_distance": float(dino.item())}
 
     def clear_memory(self):
         """Clear GPU memory cache."""

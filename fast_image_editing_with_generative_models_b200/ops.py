@@ -324,7 +324,7 @@ def im2col3x3(x: torch.Tensor, stride: int = 1, pad: int = 1, shift=None, scale=
         raise _lib.FieError("im2col3x3: fp16 / uint8 CUDA NHWC tensor required")
     n, h, w, c = x.shape
     ld = x.stride(-2)
-    if x.stride(1) != w * ld or x.stride(0) != h * w * ld:
+    if (h > 1 and x.stride(1) != w * ld) or (n > 1 and x.stride(0) != h * w * ld):        # (the stride of a size-1 dimension is arbitrary)
         raise _lib.FieError("im2col3x3: only the channel dimension may be strided")
     oh, ow = (h + 2 * pad - 3) // stride + 1, (w + 2 * pad - 3) // stride + 1
     kpad = (9 * c + 7) // 8 * 8 if kpad is None else int(kpad)

@@ -76,7 +76,7 @@ int fie_resample_lanczos_u8(const void* in_u8, void* out_u8, void* tmp_u8, int n
  * Gaussian window kernel_size (odd, <= 11; default 11) / sigma (1.5), k1 0.01, k2 0.03, valid region only (what the reflect-pad +
  * crop of torchmetrics leaves).  out_sum double [n] = sum of the SSIM map over channels and valid pixels (mean = / (c (h-k+1) (w-k+1))).  Pixels are float32 v/255 as in
  * the reference; the local moments are accumulated in double (float32 moments carry ~1e-4 of cancellation noise in flat regions). */
-int fie_ssim_u8(const void* a, const void* b, int n, int h, int w, int c, int kernel_size, float sigma, float k1, float k2,
+int fie_ssim_u8(const void* a, const void* b, int n, int h, int w, int c, int kernel_size, double sigma, double k1, double k2,
                 double* out_sum, void* stream);
 /* exact sum of (a - b)^2 over per_image bytes of each image -> uint64 [n]: MSE = sum / (255^2 per_image), PSNR = -10 log10(MSE)
  * (PeakSignalNoiseRatio / MeanSquaredError at src/metrics.py:190-197,285-336) */

@@ -102,16 +102,19 @@ def clip_preprocess(img_u8: np.ndarray, size: int = 224) -> torch.Tensor:
 
 
 @torch.no_grad()
-def clip_score(model, img_u8: np.ndarray, input_ids: torch.Tensor) -> float:
-    """``model``: a ``transformers.CLIPModel``.  100 * cos(image features, text features), floored at 0."""
+def clip_cosine(model, img_u8: np.ndarray, input_ids: torch.Tensor) -> float:
+    """``model``: a ``transformers.CLIPModel``.  cos(image features, text features) = torchmetrics' score / 100 before its floor."""
     dev = next(model.parameters()).device
     px = clip_preprocess(img_u8, model.config.vision_config.image_size).to(dev)
-    v = model.vision_model(pixel_values=px).pooler_output
-    v = model.visual_projection(v)
-    t = model.text_model(input_ids=input_ids.to(dev)).pooler_output
-    t = model.text_projection(t)
+    v = model.visual_projection(model.vision_model(pixel_values=px).pooler_output)
+    t = model.text_projection(model.text_model(input_ids=input_ids.to(dev)).pooler_output)
     v, t = v / v.norm(p=2, dim=-1, keepdim=True), t / t.norm(p=2, dim=-1, keepdim=True)
-    return max(float(100 * (v * t).sum(-1)), 0.0)
+    return float((v * t).sum(-1))
+
+
+def clip_score(model, img_u8: np.ndarray, input_ids: torch.Tensor) -> float:
+    """torchmetrics ``CLIPScore``: 100 * cosine, floored at 0."""
+    return max(100.0 * clip_cosine(model, img_u8, input_ids), 0.0)
 
 
 # ---------------------------------------------------------------------------------------------------------------------------

@@ -65,11 +65,20 @@ def test_argument_validation_reports_errors_without_a_gpu():
         (L.fie_attn_vae_d512_f16(p, 512, p, 512, p, p, 512, 100, 500, 0.1, 0, 0, p, 1 << 30, None), "d % 64"),
         (L.fie_fuse_lora_f32(p, p, p, 1.0, 0, 4, 8, None), "bad arguments"),
         (L.fie_pack_conv3x3_c8_f16(p, p, 8, 9, 8, None), "cin <= 8"),
+        (L.fie_ssim_u8(p, p, 1, 8, 8, 3, 11, 1.5, 0.01, 0.03, p, None), "smaller than the window"),
+        (L.fie_ssim_u8(p, p, 1, 32, 32, 3, 10, 1.5, 0.01, 0.03, p, None), "odd"),
+        (L.fie_patchify_f16(p, 1, p, 1, 30, 32, 16, None, None, None), "multiples of the patch"),
+        (L.fie_vit_assemble_f16(p, p, p, p, 1, 4, 12, None), "multiple of 8"),
+        (L.fie_im2col3x3_f16(p, 0, 16, p, 1, 8, 8, 16, 1, 1, 100, None, None, None), "kpad"),
+        (L.fie_maxpool3s2_ceil_f16(p, p, 1, 8, 8, 12, None), "multiple of 8"),
+        (L.fie_resample_f32(p, 1, p, None, 1, 8, 8, 8, 4, None, None, 0, None, None, 0, None, None, None), "tables missing"),
     ]
     for rc, needle in cases:
         assert rc != 0
     assert L.fie_canny_u8(p, p, 1, 8, 8, 2, 1, 100, 200, p, 1 << 20, None) != 0 and b"in_channels" in L.fie_last_error()
     assert L.fie_attn_vae_d512_f16(p, 512, p, 512, p, p, 512, 100, 500, 0.1, 0, 0, p, 1 << 30, None) != 0 and b"d % 64" in L.fie_last_error()
+    assert L.fie_ssim_u8(p, p, 1, 8, 8, 3, 11, 1.5, 0.01, 0.03, p, None) != 0 and b"smaller than the window" in L.fie_last_error()
+    assert L.fie_patchify_f16(p, 1, p, 1, 30, 32, 16, None, None, None) != 0 and b"patch size" in L.fie_last_error()
     # pure host queries
     assert L.fie_jpeg_header_bytes() == 623 and L.fie_jpeg_max_bytes(1024, 1024) > 3 * 1024 * 1024
     assert L.fie_jpeg_workspace_bytes(8, 1024, 1024) > 8 * 4096 * 384 * 2
