@@ -111,11 +111,17 @@ class DinoDistanceMetric:
         with torch.cuda.device(self.device):
             self.model = vit.VisionTransformer(params, cfg, self.device)
 
-    def _self_similarity(self, img_u8: torch.Tensor):
+    def _preprocess(self, img_u8: torch.Tensor) -> torch.Tensor:
+        """``_to_tensor`` (reference src/metrics.py:124-136): /255, Resize(resize_to, antialias=True), ImageNet normalisation -> fp32 [n,h,w,3]."""
         n, h, w, _ = img_u8.shape
         s = self.resize_to                                                      # transforms.Resize(int): the shorter side becomes `s`
         oh, ow = (s, int(s * w / h)) if h <= w else (int(s * h / w), s)
-        x = ops.resize_aa_normalize(img_u8, oh, ow, vit.IMAGENET_MEAN, vit.IMAGENET_STD)
+        return ops.resize_aa_normalize(img_u8, oh, ow, vit.IMAGENET_MEAN, vit.IMAGENET_STD)
+
+    def _self_similarity(self, img_u8: torch.Tensor, preprocessed: bool = False):
+        """-> ([fp32 [T, T_padded] cosine self-similarity of the block-``layer`` keys, one per image], T)."""
+        x = img_u8 if preprocessed else self._preprocess(img_u8)
+        n = x.shape[0]
         keys = self.model.keys(x, self.layer)                                   # [n*T, C] view
         t = keys.shape[0] // n
         tp = (t + 31) // 32 * 32
@@ -128,11 +134,12 @@ class DinoDistanceMetric:
 
     def _distance_dev(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         """uint8 CUDA [1,H,W,3] pair -> fp64 [1] distance on the device (no host synchronisation)."""
-        if a.shape == b.shape:                                   # one ViT pass over both images (rows of a batch are computed independently)
-            (sa, sb), t = self._self_similarity(torch.cat([a, b], 0))
+        xa, xb = self._preprocess(a), self._preprocess(b)
+        if xa.shape == xb.shape:                                 # one ViT pass over both images (rows of a batch are computed independently)
+            (sa, sb), t = self._self_similarity(torch.cat([xa, xb], 0), preprocessed=True)
         else:
-            (sa,), t = self._self_similarity(a)
-            (sb,), tb = self._self_similarity(b)
+            (sa,), t = self._self_similarity(xa, preprocessed=True)
+            (sb,), tb = self._self_similarity(xb, preprocessed=True)
             if t != tb:
                 raise ValueError("DinoDistanceMetric: source and edited image give different token counts")
         return ops.sqdiff_f32(sb, sa, t, t) / float(t * t)
