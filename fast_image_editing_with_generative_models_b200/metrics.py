@@ -95,19 +95,18 @@ class DinoDistanceMetric:
 
     def __init__(self, device: str = "cuda", model_name: str = "dino_vitb8", resize_to: int = 224, layer: int = 11, checkpoint: Optional[str] = None,
                  params: Optional[Dict[str, torch.Tensor]] = None, config: Optional[vit.ViTConfig] = None):
-        if model_name != "dino_vitb8" and config is None:
-            raise ValueError("DinoDistanceMetric: only dino_vitb8 is configured (pass config= for another DINO ViT)")
+        if model_name != "dino_vitb8" and config is None and params is None and checkpoint is None:
+            raise ValueError("DinoDistanceMetric: without a checkpoint only dino_vitb8 is configured (pass checkpoint=, params= or config=)")
         self.device = torch.device("cuda:0" if str(device) == "cuda" else device)
         self.layer, self.resize_to = layer, resize_to
-        cfg = config or vit.dino_vitb8_config()
         self.synthetic_weights = params is None and checkpoint is None
+        if params is None and checkpoint is not None:
+            params = {k: v.float() for k, v in torch.load(checkpoint, map_location="cpu", weights_only=True).items()}
+        cfg = config or (vit.dino_config_from_params(params, model_name) if params is not None else vit.dino_vitb8_config())
         if params is None:
-            if checkpoint is not None:
-                params = {k: v.float() for k, v in torch.load(checkpoint, map_location="cpu", weights_only=True).items()}
-            else:
-                warnings.warn("DinoDistanceMetric: no DINO checkpoint given — the ViT runs on seeded RANDOM weights; the distance is a structural "
-                              "test value, not the published metric", RuntimeWarning, stacklevel=2)
-                params = vit.make_vit_params(cfg)
+            warnings.warn("DinoDistanceMetric: no DINO checkpoint given — the ViT runs on seeded RANDOM weights; the distance is a structural "
+                          "test value, not the published metric", RuntimeWarning, stacklevel=2)
+            params = vit.make_vit_params(cfg)
         with torch.cuda.device(self.device):
             self.model = vit.VisionTransformer(params, cfg, self.device)
 

@@ -58,6 +58,17 @@ def tiny_vit_config(style: str = "clip", image_size: int = 64, patch_size: int =
                      projection_dim=64 if style == "clip" else None, seed=43)
 
 
+def dino_config_from_params(params: Dict[str, Tensor], name: str = "dino-vit") -> ViTConfig:
+    """The architecture of a DINO ``VisionTransformer`` checkpoint read off its tensor shapes (dino_vits8 / vits16 / vitb8 / vitb16 all
+    have 64-wide heads)."""
+    c = params["cls_token"].shape[-1]
+    ps = params["patch_embed.proj.weight"].shape[-1]
+    side = int(round((params["pos_embed"].shape[1] - 1) ** 0.5))
+    layers = 1 + max(int(k.split(".")[1]) for k in params if k.startswith("blocks."))
+    return ViTConfig(name=name, style="dino", image_size=side * ps, patch_size=ps, hidden_size=c, num_layers=layers, num_heads=c // 64,
+                     intermediate_size=params["blocks.0.mlp.fc1.weight"].shape[0], hidden_act="gelu", layer_norm_eps=1e-6, projection_dim=None)
+
+
 def make_vit_params(cfg: ViTConfig) -> Dict[str, Tensor]:
     """Seeded random-init state dict with the key names of the style's published checkpoint (fp32, CPU)."""
     g = torch.Generator("cpu").manual_seed(cfg.seed)

@@ -306,3 +306,49 @@ def test_metrics_calculator_all_metrics_on_pil_images(cuda_dev):
     t = torch.from_numpy(src).permute(2, 0, 1).float() / 255.0
     assert calc.calculate_mse(t, Image.fromarray(src)) == 0.0
     calc.clear_memory()
+
+
+def test_metrics_from_checkpoint_files_written_by_the_real_libraries(cuda_dev, tmp_path):
+    """``MetricsCalculator(checkpoints=...)`` on files produced by transformers (``CLIPModel.save_pretrained``), torchvision
+    (``squeezenet1_1().state_dict()``) and a DINO-named ``.pth``; the scores must match the modules that wrote the files."""
+    import warnings
+    import torchvision
+    from transformers import CLIPConfig, CLIPModel
+    from fast_image_editing_with_generative_models_b200 import lpips as L
+    from fast_image_editing_with_generative_models_b200 import vit
+    from fast_image_editing_with_generative_models_b200.metrics import DinoDistanceMetric, MetricsCalculator
+    from fast_image_editing_with_generative_models_b200.text_encoder import pseudo_token_ids
+    torch.manual_seed(7)
+    hc = CLIPConfig(text_config=dict(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, max_position_embeddings=77,
+                                     eos_token_id=2, bos_token_id=0, pad_token_id=1),
+                    vision_config=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, image_size=64, patch_size=16),
+                    projection_dim=64)
+    hf = CLIPModel(hc).eval()
+    hf.save_pretrained(tmp_path / "clip")
+    sq = torchvision.models.squeezenet1_1(weights=None).eval()
+    torch.save(sq.state_dict(), tmp_path / "squeezenet1_1.pth")
+    lins = {f"lin{k}.model.1.weight": torch.rand(1, c, 1, 1) * (2.0 / c) for k, c in enumerate(L.TAP_CHANNELS)}
+    torch.save(lins, tmp_path / "lpips.pth")
+    dcfg = vit.tiny_vit_config("dino", image_size=64, patch_size=8)
+    dparams = vit.make_vit_params(dcfg)
+    torch.save(dparams, tmp_path / "dino.pth")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        calc = MetricsCalculator(device="cuda", checkpoints={"clip": str(tmp_path / "clip"), "squeezenet": str(tmp_path / "squeezenet1_1.pth"), "lpips": str(tmp_path / "lpips.pth")})
+    assert calc.synthetic == ["DINO ViT-B/8"] and any("pseudo token ids" in str(x.message) for x in w)       # (no vocab.json next to the model)
+    a, b = _img(70), _noisy(_img(70), 71, 25)
+    text = "a photo of a cat"
+    got = calc.clip_cosine(a, text)
+    ref = MO.clip_cosine(hf.to(cuda_dev), a, pseudo_token_ids(text, 1000).unsqueeze(0))
+    print(f"\n[files] clip cosine {got:.5f} vs transformers {ref:.5f}")
+    assert abs(got - ref) < 5e-3
+    got = calc.calculate_lpips(a, b)
+    ref = MO.lpips_squeeze(sq.features.to(cuda_dev), [lins[f"lin{k}.model.1.weight"].reshape(-1) for k in range(7)], a, b)
+    print(f"[files] lpips {got:.6g} vs torchvision backbone {ref:.6g}")
+    assert abs(got - ref) <= 2e-2 * ref
+    metric = DinoDistanceMetric(device="cuda", checkpoint=str(tmp_path / "dino.pth"), resize_to=64, layer=2)      # architecture read off the tensor shapes
+    assert (metric.model.cfg.patch_size, metric.model.cfg.image_size, metric.model.cfg.num_layers, metric.model.cfg.num_heads) == (8, 64, 3, 2)
+    ref = MO.dino_distance(MO.DinoViT(dparams, 8, 2).to(cuda_dev), a, b, layer=2, resize_to=64)
+    got = metric.calculate_distance(a, b)
+    print(f"[files] dino distance {got:.6g} vs oracle {ref:.6g}")
+    assert abs(got - ref) <= 2 * math.sqrt(ref) * 4e-3 + 1.6e-5

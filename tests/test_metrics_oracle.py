@@ -226,3 +226,40 @@ def test_metrics_calculator_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         MetricsCalculator(device="cuda")
+
+
+def test_metric_checkpoint_formats_written_by_the_real_libraries(tmp_path, monkeypatch):
+    """The on-disk formats MetricsCalculator reads, produced here by the libraries that publish them: ``CLIPModel.save_pretrained``
+    (transformers), ``torch.save(squeezenet1_1().state_dict())`` (torchvision), a DINO-named ``.pth`` — keys and shapes must be exactly
+    what the towers consume (constructed on the CPU: no kernel runs)."""
+    import torchvision
+    from transformers import CLIPConfig, CLIPModel
+    from fast_image_editing_with_generative_models_b200 import metrics as M
+    from fast_image_editing_with_generative_models_b200.text_encoder import CLIPTextEncoder
+    hc = CLIPConfig(text_config=dict(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, max_position_embeddings=77),
+                    vision_config=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=64, patch_size=16),
+                    projection_dim=64)
+    CLIPModel(hc).save_pretrained(tmp_path / "clip-vit-base-patch16")
+    vcfg, tcfg, sd = M.load_clip_model_dir(str(tmp_path / "clip-vit-base-patch16"))
+    assert (vcfg.hidden_size, vcfg.num_layers, vcfg.image_size, vcfg.patch_size, vcfg.projection_dim) == (128, 2, 64, 16, 64)
+    assert (tcfg.hidden_size, tcfg.num_layers, tcfg.num_heads, tcfg.vocab_size, tcfg.projection_dim, tcfg.hidden_act) == (128, 2, 2, 1000, 64, "quick_gelu")
+    tower = vit.VisionTransformer(sd, vcfg, "cpu")
+    assert tower.w_patch.shape == (128, 16 * 16 * 3) and tower.pos.shape == (17, 128) and tower.proj.shape == (64, 128) and len(tower.layers) == 2
+    text = CLIPTextEncoder(sd, tcfg, "cpu")
+    assert text.proj.shape == (64, 128) and len(text.layers) == 2
+    # torchvision's SqueezeNet + lpips' lin layers, DINO's hub checkpoint layout
+    torch.save(torchvision.models.squeezenet1_1(weights=None).state_dict(), tmp_path / "squeezenet1_1.pth")
+    lp = lpips_mod.make_lpips_params()
+    torch.save({k: v for k, v in lp.items() if k.startswith("lin")}, tmp_path / "lpips_squeeze.pth")
+    dcfg = vit.tiny_vit_config("dino", image_size=32, patch_size=8)
+    torch.save(vit.make_vit_params(dcfg), tmp_path / "dino_vitbase8_pretrain.pth")
+    monkeypatch.setenv("FIE_METRIC_CHECKPOINTS", str(tmp_path))
+    found = M.metric_checkpoints_from_env()
+    assert set(found) == {"clip", "dino", "squeezenet", "lpips"}
+    p = {k: v.float() for k, v in torch.load(found["squeezenet"], weights_only=True).items()}
+    p.update(torch.load(found["lpips"], weights_only=True))
+    net = lpips_mod.LPIPSSqueeze(p, "cpu")                      # ignores torchvision's classifier.* entries, finds every features.* / lin* key
+    assert net.w0.shape == (64, 64) and len(net.fires) == 8 and [l.numel() for l in net.lins] == list(lpips_mod.TAP_CHANNELS)
+    assert vit.VisionTransformer(torch.load(found["dino"], weights_only=True), dcfg, "cpu").b_patch.shape == (128,)
+    monkeypatch.delenv("FIE_METRIC_CHECKPOINTS")
+    assert M.metric_checkpoints_from_env() == {}
