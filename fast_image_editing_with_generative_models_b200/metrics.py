@@ -160,13 +160,15 @@ class MetricsCalculator:
         ck = dict(metric_checkpoints_from_env())
         ck.update(checkpoints or {})
         self.checkpoints = ck
-        self.synthetic = []
+        self.synthetic, self._notes = [], []
         self.lpips_net = self.clip_vision = self.clip_text = self.dino_metric = self._tokenizer = None
         print(f"[MetricsCalculator] Initializing on {self.device}...")
         if networks:
             with torch.cuda.device(self.device), warnings.catch_warnings():
                 warnings.simplefilter("ignore", RuntimeWarning)                  # one combined warning below
                 self._build_networks(ck)
+            for note in self._notes:
+                warnings.warn(note, RuntimeWarning, stacklevel=2)
             if self.synthetic:
                 warnings.warn(f"MetricsCalculator: no checkpoint for {', '.join(self.synthetic)} — those networks run on seeded RANDOM weights; "
                               "their scores are structural test values, not quality measurements (set FIE_METRIC_CHECKPOINTS or checkpoints=)",
@@ -190,7 +192,7 @@ class MetricsCalculator:
                 from .tokenizer import CLIPBPETokenizer
                 self._tokenizer = CLIPBPETokenizer.from_files(ck["clip"])
             else:
-                warnings.warn("MetricsCalculator: CLIP checkpoint without vocab.json / merges.txt; prompts are mapped to pseudo token ids", RuntimeWarning)
+                self._notes.append("MetricsCalculator: CLIP checkpoint without vocab.json / merges.txt; prompts are mapped to pseudo token ids")
         else:
             vcfg, tcfg = vit.clip_b16_vision_config(), clip_b16_text_config()
             sd = dict(vit.make_vit_params(vcfg))
