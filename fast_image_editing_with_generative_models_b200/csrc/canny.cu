@@ -12,6 +12,7 @@
 // The hysteresis result is the unique closure of strong pixels through candidates, so the union-find
 // formulation is bit-exact with OpenCV's stack-based flood fill without any host round trip.
 #include "fie_common.cuh"
+#include <stdlib.h>
 
 namespace fie {
 
@@ -175,6 +176,176 @@ __global__ void __launch_bounds__(256) k_nms(const uint8_t* __restrict__ src, ui
     }
 }
 
+// ---- fast tile kernel for the pipeline's shape (RGB input, W % 64 == 0, H % 32 == 0, 4-byte aligned rows) -----------------------------
+// Same arithmetic and the same outputs as k_nms<3>, with four pixels per task so that address arithmetic, loads and stores are paid per
+// 32-bit word instead of per byte (k_nms spends ~250 thread instructions per pixel and is issue-bound; ncu profiles/r2p_canny.md):
+//   A  gray: 36 rows x 18 groups of 4 px (columns x0-4 .. x0+67), three aligned 32-bit RGB words per group -> one packed gray word;
+//      rows and the two out-of-image column groups are clamped (BORDER_REPLICATE)
+//   B  Sobel on 2 x 16-bit lanes per register (sums are <= 1020, the differences are biased by 2048 so no borrow crosses a lane),
+//      L1 magnitude and the NMS direction class of the pixel itself -> (mag << 2 | class) as 16 bits, 0 outside the image
+//   C  NMS + double threshold on the tile's 32 x 16 groups; groups without a pixel above `low` (the common case) stop after one load
+//   D  tile-local union-find over the candidates, E  packed state words and the depth-1 parents go to global memory (as k_nms).
+constexpr int FG = (TW + 8) / 4;                       // 18 staged groups per row
+
+__device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2) {
+    const uint32_t r0 = w0 & 255, g0 = (w0 >> 8) & 255, b0 = (w0 >> 16) & 255;
+    const uint32_t r1 = w0 >> 24, g1 = w1 & 255, b1 = (w1 >> 8) & 255;
+    const uint32_t r2 = (w1 >> 16) & 255, g2 = w1 >> 24, b2 = w2 & 255;
+    const uint32_t r3 = (w2 >> 8) & 255, g3 = (w2 >> 16) & 255, b3 = w2 >> 24;
+    const uint32_t y0 = (9798u * r0 + 19235u * g0 + 3735u * b0 + 16384u) >> 15;
+    const uint32_t y1 = (9798u * r1 + 19235u * g1 + 3735u * b1 + 16384u) >> 15;
+    const uint32_t y2 = (9798u * r2 + 19235u * g2 + 3735u * b2 + 16384u) >> 15;
+    const uint32_t y3 = (9798u * r3 + 19235u * g3 + 3735u * b3 + 16384u) >> 15;
+    return y0 | (y1 << 8) | (y2 << 16) | (y3 << 24);
+}
+
+// (mag << 2) | direction class of one pixel: 0 horizontal, 1 vertical, 2 diagonal with dx, dy of equal sign, 3 of opposite sign
+__device__ __forceinline__ uint32_t mag_class(int dx, int dy) {
+    const int ax = abs(dx), ayp = abs(dy);
+    const int m = ax + ayp;
+    const int ay = ayp << 15;                          // <= 1020 << 15 < 2^31
+    const int t22 = ax * TG22;                         // <= 1020 * 13573
+    const int t67 = t22 + (ax << 16);                  // <= 80.7e6 < 2^31
+    const uint32_t cls = ay < t22 ? 0u : (ay > t67 ? 1u : (((dx ^ dy) < 0) ? 3u : 2u));
+    return ((uint32_t)m << 2) | cls;
+}
+
+__global__ void __launch_bounds__(256, 6) k_nms_rgb_fast(const uint8_t* __restrict__ src, uint8_t* __restrict__ state,
+                                                      uint32_t* __restrict__ parent, int H, int W, int low, int high) {
+    __shared__ uint32_t sgw[TH + 4][FG];               // gray, 4 px per word, image rows y0-2.., columns x0-4..
+    __shared__ __align__(8) uint32_t smc[TH + 2][2 * FG];   // (mag << 2 | class), 2 px per word, image rows y0-1.., columns x0-4..
+    __shared__ uint32_t slab[TH * TW];
+    __shared__ __align__(4) uint8_t sst[TH * TW];
+    const int img = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, tid = threadIdx.x;
+    const uint8_t* g = src + (size_t)img * H * W * 3;
+    const size_t row_bytes = (size_t)W * 3;
+    // A
+    for (int t = tid; t < (TH + 4) * FG; t += 256) {
+        const int ly = t / FG, gx = t - ly * FG;
+        const int y = min(max(y0 + ly - 2, 0), H - 1);
+        const int xg = x0 - 4 + 4 * gx;
+        uint32_t w;
+        if (xg >= 0 && xg < W) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(g + (size_t)y * row_bytes + (size_t)xg * 3);
+            w = gray4(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+        } else {
+            const uint8_t* p = g + (size_t)y * row_bytes + (size_t)(xg < 0 ? 0 : W - 1) * 3;
+            w = ((9798u * p[0] + 19235u * p[1] + 3735u * p[2] + 16384u) >> 15) * 0x01010101u;
+        }
+        sgw[ly][gx] = w;
+    }
+    __syncthreads();
+    // B
+    const bool border = blockIdx.x == 0 || blockIdx.x == gridDim.x - 1 || blockIdx.y == 0 || blockIdx.y == gridDim.y - 1;
+    for (int t = tid; t < (TH + 2) * FG; t += 256) {
+        const int ly = t / FG, gx = t - ly * FG;
+        const int gl = max(gx - 1, 0), gr = min(gx + 1, FG - 1);
+        uint32_t L[3], C[3], R[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const uint32_t wl = sgw[ly + r][gl], wc = sgw[ly + r][gx], wr = sgw[ly + r][gr];
+            L[r] = __byte_perm(wl, wc, 0x6543);        // columns c-1 .. c+2
+            C[r] = wc;                                 // columns c   .. c+3
+            R[r] = __byte_perm(wc, wr, 0x4321);        // columns c+1 .. c+4
+        }
+        uint32_t out[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t sel = hf ? 0x4342u : 0x4140u;                       // bytes (2, 3) or (0, 1) -> two 16-bit lanes
+            const uint32_t Lt = __byte_perm(L[0], 0, sel), Lm = __byte_perm(L[1], 0, sel), Lb = __byte_perm(L[2], 0, sel);
+            const uint32_t Ct = __byte_perm(C[0], 0, sel), Cb = __byte_perm(C[2], 0, sel);
+            const uint32_t Rt = __byte_perm(R[0], 0, sel), Rm = __byte_perm(R[1], 0, sel), Rb = __byte_perm(R[2], 0, sel);
+            const uint32_t DX = (Rt + 2 * Rm + Rb) + 0x08000800u - (Lt + 2 * Lm + Lb);
+            const uint32_t DY = (Lb + 2 * Cb + Rb) + 0x08000800u - (Lt + 2 * Ct + Rt);
+            const uint32_t a = mag_class((int)(DX & 0xFFFFu) - 2048, (int)(DY & 0xFFFFu) - 2048);
+            const uint32_t b = mag_class((int)(DX >> 16) - 2048, (int)(DY >> 16) - 2048);
+            out[hf] = a | (b << 16);
+        }
+        if (border) {                                   // magnitude 0 outside the image
+            const int y = y0 - 1 + ly, xg = x0 - 4 + 4 * gx;
+            if (y < 0 || y >= H) { out[0] = 0; out[1] = 0; }
+            else {
+                if (xg < 0 || xg >= W) out[0] &= 0xFFFF0000u;
+                if (xg + 1 < 0 || xg + 1 >= W) out[0] &= 0x0000FFFFu;
+                if (xg + 2 < 0 || xg + 2 >= W) out[1] &= 0xFFFF0000u;
+                if (xg + 3 < 0 || xg + 3 >= W) out[1] &= 0x0000FFFFu;
+            }
+        }
+        *reinterpret_cast<uint2*>(&smc[ly][2 * gx]) = make_uint2(out[0], out[1]);
+    }
+    __syncthreads();
+    // C
+    const uint32_t lowc = (uint32_t)low << 2 | 3u;      // (mag << 2 | class) > lowc  <=>  mag > low
+    for (int t = tid; t < TH * (TW / 4); t += 256) {
+        const int ly = t >> 4, gq = t & 15;             // tile row, group of 4 tile pixels; staged column of pixel 0 = 4 + 4 gq
+        const uint2 c = *reinterpret_cast<const uint2*>(&smc[ly + 1][2 + 2 * gq]);
+        uint32_t sw = 0;
+        if ((c.x & 0xFFFFu) > lowc || (c.x >> 16) > lowc || (c.y & 0xFFFFu) > lowc || (c.y >> 16) > lowc) {
+            int m[3][6];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const uint32_t wl = smc[ly + r][1 + 2 * gq], wr = smc[ly + r][4 + 2 * gq];
+                const uint2 wc = r == 1 ? c : *reinterpret_cast<const uint2*>(&smc[ly + r][2 + 2 * gq]);
+                m[r][0] = (int)(wl >> 18);
+                m[r][1] = (int)((wc.x & 0xFFFFu) >> 2); m[r][2] = (int)(wc.x >> 18);
+                m[r][3] = (int)((wc.y & 0xFFFFu) >> 2); m[r][4] = (int)(wc.y >> 18);
+                m[r][5] = (int)((wr & 0xFFFFu) >> 2);
+            }
+            const uint32_t cls4[4] = {c.x & 3u, (c.x >> 16) & 3u, c.y & 3u, (c.y >> 16) & 3u};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int mm = m[1][k + 1];
+                uint32_t st = 0;
+                if (mm > low) {
+                    bool keep;
+                    if (cls4[k] == 0) keep = mm > m[1][k] && mm >= m[1][k + 2];
+                    else if (cls4[k] == 1) keep = mm > m[0][k + 1] && mm >= m[2][k + 1];
+                    else if (cls4[k] == 2) keep = mm > m[0][k] && mm > m[2][k + 2];
+                    else keep = mm > m[0][k + 2] && mm > m[2][k];
+                    if (keep) st = mm > high ? 2u : 1u;
+                }
+                if (st) slab[4 * t + k] = (uint32_t)(4 * t + k) | (st == 2 ? 0u : kWeakBit);
+                sw |= st << (8 * k);
+            }
+        }
+        reinterpret_cast<uint32_t*>(sst)[t] = sw;
+    }
+    __syncthreads();
+    // D: unions with the W, NW, N, NE neighbours (each 8-connected pair once)
+    for (int t = tid; t < TH * (TW / 4); t += 256) {
+        const uint32_t sw = reinterpret_cast<const uint32_t*>(sst)[t];
+        if (!sw) continue;
+        const int ly = t >> 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((sw >> (8 * k)) & 0xFFu)) continue;
+            const int i = 4 * t + k, lx = i & (TW - 1);
+            if (lx > 0 && sst[i - 1]) uf_union(slab, i, i - 1);
+            if (ly > 0) {
+                if (lx > 0 && sst[i - TW - 1]) uf_union(slab, i, i - TW - 1);
+                if (sst[i - TW]) uf_union(slab, i, i - TW);
+                if (lx < TW - 1 && sst[i - TW + 1]) uf_union(slab, i, i - TW + 1);
+            }
+        }
+    }
+    __syncthreads();
+    // E
+    for (int t = tid; t < TH * (TW / 4); t += 256) {
+        const int ly = t >> 4, gq = t & 15;
+        const size_t o = (size_t)img * H * W + (size_t)(y0 + ly) * W + x0 + 4 * gq;
+        const uint32_t sw = reinterpret_cast<const uint32_t*>(sst)[t];
+        *reinterpret_cast<uint32_t*>(state + o) = sw;
+        if (!sw) continue;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (!((sw >> (8 * k)) & 0xFFu)) continue;
+            const uint32_t r = uf_find(slab, (uint32_t)(4 * t + k));
+            const uint32_t rl = r & kIdxMask;
+            parent[o + k] = (uint32_t)((y0 + (int)(rl / TW)) * W + x0 + (int)(rl % TW)) | (r & kWeakBit);
+        }
+    }
+}
+
 // Joins the tile-local components across the tile seams (global lock-free union-find on the per-image parent array): one thread per
 // pixel on the left side of a vertical seam or the upper side of a horizontal seam, united with its up-to-three candidate neighbours on
 // the other side.  Every 8-connected pair that straddles a seam is covered exactly once.
@@ -330,13 +501,20 @@ extern "C" int fie_canny_u8(const void* img, void* edges, int n, int h, int w, i
     uint8_t* state = gray + pxr;
     uint32_t* parent = (uint32_t*)(state + pxr);
     (void)gray;                                   // (the gray plane is no longer materialised: k_nms<3> converts on the fly)
+    static int fast_env = -1;                       // FIE_CANNY_FAST=0: the generic kernels for every shape (A/B, debugging)
+    if (fast_env < 0) { const char* e = getenv("FIE_CANNY_FAST"); fast_env = e ? atoi(e) : 1; }
     dim3 g1(ceil_div(w, TW), ceil_div(h, TH), n);
-    if (in_channels == 3) k_nms<3><<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
+    const bool fast_tile = fast_env && in_channels == 3 && (w % TW) == 0 && (h % TH) == 0 && low >= 0 && high < 8192 &&
+                           ((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(state)) & 3) == 0;
+    if (fast_tile) k_nms_rgb_fast<<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
+    else if (in_channels == 3) k_nms<3><<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
     else k_nms<1><<<g1, 256, 0, stream>>>((const uint8_t*)img, state, parent, h, w, low, high);
     const long long seam_px = (long long)((w - 1) / TW) * h + (long long)((h - 1) / TH) * w;
     if (seam_px > 0) k_seams<<<dim3((unsigned)((seam_px + 255) / 256), n), 256, 0, stream>>>(state, parent, h, w);
     const bool fin4 = (w & 3) == 0 && ((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(edges)) & 3) == 0;
     dim3 g2(ceil_div(fin4 ? w / 4 : w, 64), ceil_div(h, 4), n);
+    // (measured on B200: 16-pixel / 128-bit and shared-memory-staged variants of this kernel are not faster -- its time is the latency of
+    //  the root chains that k_seams leaves behind, paid by every warp that holds a candidate, not the store pattern)
     k_finalize<<<g2, 256, 0, stream>>>(state, parent, (uint8_t*)edges, h, w, out_channels);
     return check_launch("fie_canny_u8");
 }
