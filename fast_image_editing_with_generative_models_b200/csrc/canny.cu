@@ -8,6 +8,7 @@
 //               label so they win the root); global memory receives depth-1 trees (parent = the tile-local root)
 //   k_seams     global lock-free union-find (atomicMin on roots), but only over the pixel pairs that straddle a tile seam
 //   k_finalize  edge = candidate whose root is a strong pixel -> 0/255 (optionally replicated x3)
+//   (the global finds of k_seams and k_finalize halve the paths they walk: uf_find_halve)
 //   (k_gray     RGB -> gray as a separate plane: only for the optional Gaussian pre-stage / fie_rgb_to_gray_u8)
 // The hysteresis result is the unique closure of strong pixels through candidates, so the union-find
 // formulation is bit-exact with OpenCV's stack-based flood fill without any host round trip.
@@ -52,14 +53,28 @@ __device__ __forceinline__ uint32_t uf_find(const uint32_t* P, uint32_t idx) {
     while ((v & kIdxMask) != idx) { idx = v & kIdxMask; v = ((volatile const uint32_t*)P)[idx]; }
     return v;   // root's label value (strong roots have kWeakBit clear)
 }
+// The same with path halving for the GLOBAL forest: a visited node is re-pointed at its grandparent.  Every entry holds the label of its
+// parent and links only ever go to smaller labels, so atomicMin keeps the forest valid under concurrent unions; the chains that
+// k_finalize has to walk afterwards get shorter.
+__device__ __forceinline__ uint32_t uf_find_halve(uint32_t* P, uint32_t idx) {
+    uint32_t v = ((volatile uint32_t*)P)[idx];
+    while ((v & kIdxMask) != idx) {
+        const uint32_t p = v & kIdxMask;
+        const uint32_t gv = ((volatile uint32_t*)P)[p];
+        if ((gv & kIdxMask) != p) atomicMin(&P[idx], gv);
+        idx = p; v = gv;
+    }
+    return v;
+}
+template <bool HALVE = false>
 __device__ __forceinline__ void uf_union(uint32_t* P, uint32_t i, uint32_t j) {
-    uint32_t a = uf_find(P, i), b = uf_find(P, j);
+    uint32_t a = HALVE ? uf_find_halve(P, i) : uf_find(P, i), b = HALVE ? uf_find_halve(P, j) : uf_find(P, j);
     while ((a & kIdxMask) != (b & kIdxMask)) {
         if (a > b) { uint32_t t = a; a = b; b = t; }
         uint32_t old = atomicMin(&P[b & kIdxMask], a);
         if (old == b) break;
-        b = uf_find(P, old & kIdxMask);
-        a = uf_find(P, a & kIdxMask);
+        b = HALVE ? uf_find_halve(P, old & kIdxMask) : uf_find(P, old & kIdxMask);
+        a = HALVE ? uf_find_halve(P, a & kIdxMask) : uf_find(P, a & kIdxMask);
     }
 }
 
@@ -364,7 +379,7 @@ __global__ void __launch_bounds__(256) k_seams(const uint8_t* __restrict__ state
         const uint32_t me = (uint32_t)(y * W + x);
         for (int d = -1; d <= 1; ++d) {
             const int yy = y + d;
-            if (yy >= 0 && yy < H && s[(size_t)yy * W + x + 1]) uf_union(P, me, (uint32_t)(yy * W + x + 1));
+            if (yy >= 0 && yy < H && s[(size_t)yy * W + x + 1]) uf_union<true>(P, me, (uint32_t)(yy * W + x + 1));
         }
     } else {
         const long long u = t - nv;
@@ -374,16 +389,16 @@ __global__ void __launch_bounds__(256) k_seams(const uint8_t* __restrict__ state
         const uint32_t me = (uint32_t)(y * W + x);
         for (int d = -1; d <= 1; ++d) {
             const int xx = x + d;
-            if (xx >= 0 && xx < W && s[(size_t)(y + 1) * W + xx]) uf_union(P, me, (uint32_t)((y + 1) * W + xx));
+            if (xx >= 0 && xx < W && s[(size_t)(y + 1) * W + xx]) uf_union<true>(P, me, (uint32_t)((y + 1) * W + xx));
         }
     }
 }
 
 // 4 pixels per thread when the row width allows it: one 32-bit state load, one (1 channel) or three (3 channels) 32-bit stores.
-__global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ state, const uint32_t* __restrict__ parent,
+__global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ state, uint32_t* parent,
                                                   uint8_t* __restrict__ out, int H, int W, int out_channels) {
     const int img = blockIdx.z;
-    const uint32_t* P = parent + (size_t)img * H * W;
+    uint32_t* P = parent + (size_t)img * H * W;                    // (written too: path halving while the roots are looked up)
     if ((W & 3) == 0 && ((reinterpret_cast<uintptr_t>(state) | reinterpret_cast<uintptr_t>(out)) & 3) == 0) {
         const int x = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4, y = blockIdx.y * 4 + (threadIdx.x >> 6);
         if (x >= W || y >= H) return;
@@ -392,7 +407,7 @@ __global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ st
         uint32_t e = 0;                                             // 4 edge bytes
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if ((st >> (8 * k)) & 0xFFu) { const uint32_t r = uf_find(P, (uint32_t)(y * W + x + k)); if (!(r & kWeakBit)) e |= 0xFFu << (8 * k); }
+            if ((st >> (8 * k)) & 0xFFu) { const uint32_t r = uf_find_halve(P, (uint32_t)(y * W + x + k)); if (!(r & kWeakBit)) e |= 0xFFu << (8 * k); }
         if (out_channels == 1) *reinterpret_cast<uint32_t*>(out + o) = e;
         else {
             // bytes e0 e0 e0 e1 | e1 e1 e2 e2 | e2 e3 e3 e3
@@ -408,7 +423,7 @@ __global__ void __launch_bounds__(256) k_finalize(const uint8_t* __restrict__ st
     if (x >= W || y >= H) return;
     const size_t o = (size_t)img * H * W + (size_t)y * W + x;
     uint8_t v = 0;
-    if (state[o]) { uint32_t r = uf_find(P, y * W + x); v = (r & kWeakBit) ? 0 : 255; }
+    if (state[o]) { uint32_t r = uf_find_halve(P, y * W + x); v = (r & kWeakBit) ? 0 : 255; }
     if (out_channels == 1) out[o] = v;
     else { out[o * 3] = v; out[o * 3 + 1] = v; out[o * 3 + 2] = v; }
 }
