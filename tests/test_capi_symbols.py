@@ -51,6 +51,19 @@ def test_product_does_not_import_oracle():
                 assert "import oracle" not in src and "from oracle" not in src, f
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is test infrastructure: besides tests/, only __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference legs)
+    may import it — not the CLIs, not the drop-in modules, not the helper scripts."""
+    offenders = []
+    for rel in ("scripts", "src"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, rel)):
+            offenders += [os.path.join(dirpath, f) for f in files if f.endswith((".py", ".sh"))]
+    offenders += [os.path.join(ROOT, f) for f in ("run_batch.py", "run_single_image.py", "evaluate.py")]
+    for path in offenders:
+        src = open(path).read()
+        assert "import oracle" not in src and "from oracle" not in src, path
+
+
 def test_argument_validation_reports_errors_without_a_gpu():
     """Every entry point validates its arguments before touching CUDA and reports through the return code + fie_last_error(): the
     reference's callers rely on ordinary exceptions per image (run_batch.py:250-261), never on a process abort."""
