@@ -52,6 +52,12 @@ def test_sqdiff_u8_is_exact(cuda_dev):
     got = ops.sqdiff_u8(_dev(a, cuda_dev), _dev(b, cuda_dev)).cpu().numpy()
     ref = ((a.astype(np.int64) - b.astype(np.int64)) ** 2).reshape(3, -1).sum(1)
     assert np.array_equal(got, ref) and got[1] == 0
+    # plane size a multiple of 16 bytes: the 128-bit / dp4a path, incl. the largest possible differences
+    a = np.stack([_img(9, 64, 80, False), np.zeros((64, 80, 3), np.uint8), _img(10, 64, 80, False)])
+    b = np.stack([_img(11, 64, 80, False), np.full((64, 80, 3), 255, np.uint8), a[2]])
+    got = ops.sqdiff_u8(_dev(a, cuda_dev), _dev(b, cuda_dev)).cpu().numpy()
+    ref = ((a.astype(np.int64) - b.astype(np.int64)) ** 2).reshape(3, -1).sum(1)
+    assert np.array_equal(got, ref) and got[1] == 255 * 255 * 64 * 80 * 3 and got[2] == 0
 
 
 @pytest.mark.parametrize("h,w,oh,ow", [(512, 512, 224, 224), (1024, 1024, 224, 224), (300, 200, 336, 224), (100, 120, 224, 268)])
