@@ -263,3 +263,24 @@ def test_metric_checkpoint_formats_written_by_the_real_libraries(tmp_path, monke
     assert vit.VisionTransformer(torch.load(found["dino"], weights_only=True), dcfg, "cpu").b_patch.shape == (128,)
     monkeypatch.delenv("FIE_METRIC_CHECKPOINTS")
     assert M.metric_checkpoints_from_env() == {}
+
+
+def test_clip_cosine_restatement_equals_transformers_forward():
+    """``CLIPModel.forward`` returns ``logits_per_image = exp(logit_scale) * cos(image_embeds, text_embeds)`` computed by transformers itself
+    (projection, pooling and L2 normalisation included); the oracle's hand-assembled cosine must agree — and CLIPScore is 100 x that, floored."""
+    from transformers import CLIPConfig, CLIPModel
+    from fast_image_editing_with_generative_models_b200.text_encoder import pseudo_token_ids
+    torch.manual_seed(3)
+    hc = CLIPConfig(text_config=dict(vocab_size=1000, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, max_position_embeddings=77,
+                                     eos_token_id=2, bos_token_id=0, pad_token_id=1),
+                    vision_config=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, image_size=64, patch_size=16),
+                    projection_dim=64)
+    m = CLIPModel(hc).eval()
+    img = _img(12, 200, 150)
+    ids = pseudo_token_ids("a photo of a dog", 1000).unsqueeze(0)
+    with torch.no_grad():
+        out = m(input_ids=ids, pixel_values=MO.clip_preprocess(img, 64))
+    ref = float(out.logits_per_image[0, 0] / m.logit_scale.exp())
+    got = MO.clip_cosine(m, img, ids)
+    assert abs(got - ref) < 1e-5, (got, ref)
+    assert MO.clip_score(m, img, ids) == max(100.0 * got, 0.0)
