@@ -6,7 +6,7 @@ The reference computes its metrics with third-party packages that are NOT instal
 
 | function | restates | pin |
 |---|---|---|
-| :func:`ssim` | torchmetrics ``functional/image/ssim.py::_ssim_update`` (Gaussian 11, sigma 1.5, reflect pad + crop, variance clamp) | **unpinned** against torchmetrics; checked against an independent float64 valid-window evaluation of Wang et al.'s formula (``tests/test_metrics_oracle.py``) |
+| :func:`ssim` | torchmetrics ``functional/image/ssim.py::_ssim_update`` (Gaussian 11, sigma 1.5, reflect pad + crop, variance clamp) | **unpinned** against torchmetrics; checked against an independent float64 valid-window evaluation of Wang et al.'s formula and against ``scipy.ndimage.gaussian_filter(sigma=1.5, truncate=3.5)`` as the window (``tests/test_metrics_oracle.py``) |
 | :func:`mse`, :func:`psnr` | ``MeanSquaredError``, ``PeakSignalNoiseRatio(data_range=1.0)`` | definitions; exact integer arithmetic cross-check |
 | :func:`clip_score` | torchmetrics ``multimodal/clip_score.py::_clip_score_update`` (100 * cosine, floor 0) | towers = ``transformers.CLIPModel`` itself; the cosine equals ``CLIPModel.forward().logits_per_image / exp(logit_scale)``; image processor = Pillow bicubic (the PIL path of transformers 4.x ``CLIPImageProcessor``: shortest edge 224, centre crop, 1/255, mean / std) |
 | :class:`DinoViT`, :func:`dino_distance` | facebookresearch/dino ``vision_transformer.py`` + reference ``src/metrics.py:24-148`` | pinned against ``transformers.ViTModel`` (the HF port of the same checkpoint family) with remapped weights; resize = ``torch.nn.functional.interpolate(antialias=True)`` = what torchvision ``Resize`` calls |

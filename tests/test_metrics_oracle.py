@@ -284,3 +284,18 @@ def test_clip_cosine_restatement_equals_transformers_forward():
     got = MO.clip_cosine(m, img, ids)
     assert abs(got - ref) < 1e-5, (got, ref)
     assert MO.clip_score(m, img, ids) == max(100.0 * got, 0.0)
+
+
+def test_ssim_window_equals_scipy_gaussian_filter():
+    """A third evaluation with a library Gaussian: ``scipy.ndimage.gaussian_filter(sigma=1.5, truncate=3.5)`` is the same 11-tap normalised
+    window (radius int(3.5 * 1.5 + 0.5) = 5); away from the border, which torchmetrics crops, the SSIM map must coincide."""
+    from scipy.ndimage import gaussian_filter
+    a, b = _img(13), _img(14)
+    x, y = (a.astype(np.float32) / 255.0).astype(np.float64), (b.astype(np.float32) / 255.0).astype(np.float64)
+    f = lambda m: np.stack([gaussian_filter(m[..., c], sigma=1.5, truncate=3.5) for c in range(3)], -1)
+    mx, my = f(x), f(y)
+    vx, vy, cxy = np.maximum(f(x * x) - mx * mx, 0), np.maximum(f(y * y) - my * my, 0), f(x * y) - mx * my
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    full = ((2 * mx * my + c1) * (2 * cxy + c2)) / ((mx * mx + my * my + c1) * (vx + vy + c2))
+    ref = float(full[5:-5, 5:-5].mean())
+    assert abs(MO.ssim(a, b, dtype=torch.float64) - ref) < 1e-9
