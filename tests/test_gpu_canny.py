@@ -78,3 +78,18 @@ def test_gaussian_prestage_matches_cv2_golden(cuda_dev):
     ref = c_oracle.canny_u8(c_oracle.gaussian_blur5_u8(gray), 100, 200)
     assert np.array_equal(ops.canny(d, 100, 200, gaussian_blur=True).cpu().numpy(), ref)
     assert not np.array_equal(ops.canny(d, 100, 200).cpu().numpy(), ref)                       # the default path has no blur
+
+
+@pytest.mark.parametrize("h,w", [(32, 64), (64, 64), (32, 128), (96, 192), (256, 64), (512, 512)])
+def test_canny_tile_aligned_small_shapes(cuda_dev, h, w):
+    """Shapes that take the four-pixel tile kernel (W % 64 == 0, H % 32 == 0) with few tiles, so that one CTA touches several image borders
+    at once; dense (noise) and sparse (shapes) candidate maps, several threshold pairs incl. low = 0, 1- and 3-channel outputs."""
+    from fast_image_editing_with_generative_models_b200 import ops
+    imgs = np.stack([synthetic_image(s + h + w, h, w, kind) for s, kind in enumerate(("shapes", "noise", "smooth", "noise"))])
+    d = torch.from_numpy(imgs).to(cuda_dev)
+    for lo, hi in ((100, 200), (0, 40), (50, 60), (200, 100), (300, 900)):
+        ref = c_oracle.canny_u8(imgs, lo, hi)
+        out = ops.canny(d, lo, hi)
+        assert np.array_equal(out.cpu().numpy(), ref), (h, w, lo, hi, int((out.cpu().numpy() != ref).sum()))
+    rgb = ops.canny(d, 100, 200, out_channels=3).cpu().numpy()
+    assert np.array_equal(rgb, np.repeat(c_oracle.canny_u8(imgs, 100, 200)[..., None], 3, axis=-1))
