@@ -4,7 +4,6 @@ resamplers' host tables, transformers' CLIP modules for the parameter naming —
 import csv
 import json
 import math
-import os
 
 import numpy as np
 import pytest
