@@ -1,12 +1,5 @@
-"""Drop-in import surface of the reference (``from src.pipeline import FastEditor``, reference ``src/__init__.py:4-7``).
-``MetricsCalculator`` is imported lazily: the reference imports it eagerly, which needs torchmetrics (absent here)."""
+"""Drop-in import surface of the reference (``from src import FastEditor, MetricsCalculator``, reference ``src/__init__.py:4-7``)."""
 from .pipeline import FastEditor
+from .metrics import MetricsCalculator
 
 __all__ = ["FastEditor", "MetricsCalculator"]
-
-
-def __getattr__(name):
-    if name == "MetricsCalculator":
-        from .metrics import MetricsCalculator
-        return MetricsCalculator
-    raise AttributeError(name)
