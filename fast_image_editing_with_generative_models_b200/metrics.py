@@ -93,7 +93,7 @@ class DinoDistanceMetric:
     """DINO-based structural distance (reference ``src/metrics.py:113-148``): MSE between the cosine self-similarity maps of the block-
     ``layer`` keys of the source and the edited image."""
 
-    def __init__(self, device: str = "cuda", model_name: str = "dino_vitb8", resize_to: int = 224, layer: int = 11, checkpoint: Optional[str] = None,
+    def __init__(self, device: str, model_name: str = "dino_vitb8", resize_to: int = 224, layer: int = 11, *, checkpoint: Optional[str] = None,
                  params: Optional[Dict[str, torch.Tensor]] = None, config: Optional[vit.ViTConfig] = None):
         if model_name != "dino_vitb8" and config is None and params is None and checkpoint is None:
             raise ValueError("DinoDistanceMetric: without a checkpoint only dino_vitb8 is configured (pass checkpoint=, params= or config=)")
@@ -151,7 +151,7 @@ class DinoDistanceMetric:
 class MetricsCalculator:
     """Image quality and editing metrics (reference ``src/metrics.py:150-386``): SSIM, LPIPS, CLIP score, PSNR, MSE, DINO distance."""
 
-    def __init__(self, device: str = "cuda", checkpoints: Optional[Dict[str, str]] = None, networks: bool = True):
+    def __init__(self, device="cuda", *, checkpoints: Optional[Dict[str, str]] = None, networks: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("MetricsCalculator: the B200 path has no CPU fallback (a CUDA device is required)")
         self.device = torch.device("cuda:0" if str(device) == "cuda" else device)

@@ -77,3 +77,40 @@ def test_cli_flags_match_the_reference():
                  "control_scale", "canny_low", "canny_high", "seed", "no_cpu_offload", "quality_mode", "full_precision", "full_controlnet",
                  "skip_existing", "save_comparisons"):
         assert flag in batch, flag                                                              # run_batch.py:19-100 of the reference
+
+
+# ---- the evaluation side of the drop-in (reference src/metrics.py:113-386) ----------------------------------------------------------------
+REF_METRICS = "/root/reference/src/metrics.py"
+METRIC_METHODS = {"__init__": [("device", "cuda")],                                             # src/metrics.py:163
+                  "calculate_ssim": ["img1", "img2"], "calculate_lpips": ["img1", "img2"], "calculate_clip_score": ["img", "text"],
+                  "calculate_psnr": ["img1", "img2"], "calculate_mse": ["img1", "img2"],
+                  "calculate_all_metrics": ["source_img", "edited_img", "prompt"], "clear_memory": []}
+DINO_INIT = [("device", inspect._empty), ("model_name", "dino_vitb8"), ("resize_to", 224), ("layer", 11)]   # src/metrics.py:116
+
+
+def test_metrics_calculator_signatures_match_the_reference():
+    from src.metrics import DinoDistanceMetric, MetricsCalculator
+    for name, expected in METRIC_METHODS.items():
+        got = _positional(getattr(MetricsCalculator, name))
+        if name == "__init__":
+            assert got == expected                          # checkpoints= / networks= are keyword arguments after the reference's one
+        else:
+            assert [g[0] for g in got] == expected, name
+    got = _positional(DinoDistanceMetric.__init__)
+    assert [g[0] for g in got[:4]] == [e[0] for e in DINO_INIT] and [g[1] for g in got[1:4]] == [e[1] for e in DINO_INIT[1:]]
+    assert [g[0] for g in _positional(DinoDistanceMetric.calculate_distance)] == ["source_img", "edited_img"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_METRICS), reason="reference source not mounted")
+def test_expected_metric_signatures_are_the_reference_ones():
+    tree = ast.parse(open(REF_METRICS).read())
+    classes = {n.name: {f.name: f for f in n.body if isinstance(f, ast.FunctionDef)} for n in tree.body if isinstance(n, ast.ClassDef)}
+    calc = classes["MetricsCalculator"]
+    for name, expected in METRIC_METHODS.items():
+        args = [a.arg for a in calc[name].args.args if a.arg != "self"]
+        assert args == [e[0] if isinstance(e, tuple) else e for e in expected], name
+    assert [ast.literal_eval(d) for d in calc["__init__"].args.defaults] == ["cuda"]
+    dino = classes["DinoDistanceMetric"]
+    assert [a.arg for a in dino["__init__"].args.args if a.arg != "self"] == [e[0] for e in DINO_INIT]
+    assert [ast.literal_eval(d) for d in dino["__init__"].args.defaults] == [e[1] for e in DINO_INIT[1:]]
+    assert [a.arg for a in dino["calculate_distance"].args.args if a.arg != "self"] == ["source_img", "edited_img"]
